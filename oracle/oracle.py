@@ -1,0 +1,200 @@
+"""ctypes binding of the test-only CPU oracle (oracle/gotoh_oracle.c).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module.  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+NW, SG, SW = 0, 1, 2
+
+
+class Config(C.Structure):
+    _fields_ = [("mode", C.c_int), ("s1_beg", C.c_int), ("s1_end", C.c_int), ("s2_beg", C.c_int),
+                ("s2_end", C.c_int), ("open", C.c_int), ("gap", C.c_int)]
+
+
+class CMatrix(C.Structure):
+    _fields_ = [("matrix", C.POINTER(C.c_int)), ("mapper", C.POINTER(C.c_int)), ("size", C.c_int),
+                ("is_pssm", C.c_int), ("length", C.c_int)]
+
+
+class Out(C.Structure):
+    _fields_ = [("score", C.c_int), ("end_query", C.c_int), ("end_ref", C.c_int),
+                ("matches", C.c_int), ("similar", C.c_int), ("length", C.c_int),
+                ("trace", C.POINTER(C.c_int8)), ("score_table", C.POINTER(C.c_int)),
+                ("matches_table", C.POINTER(C.c_int)), ("similar_table", C.POINTER(C.c_int)),
+                ("length_table", C.POINTER(C.c_int)),
+                ("score_row", C.POINTER(C.c_int)), ("matches_row", C.POINTER(C.c_int)),
+                ("similar_row", C.POINTER(C.c_int)), ("length_row", C.POINTER(C.c_int)),
+                ("score_col", C.POINTER(C.c_int)), ("matches_col", C.POINTER(C.c_int)),
+                ("similar_col", C.POINTER(C.c_int)), ("length_col", C.POINTER(C.c_int))]
+
+
+def build(force=False):
+    """Compile the checker libraries next to their sources (gcc only, seconds)."""
+    targets = ["libpsb_oracle.so"]
+    if os.path.exists(os.path.join(_HERE, "striped_cpu.cpp")):
+        targets.append("libpsb_striped.so")
+    if force:
+        subprocess.run(["make", "-C", _HERE, "clean"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE] + targets, check=True, capture_output=True)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libpsb_oracle.so")
+        src = os.path.join(_HERE, "gotoh_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        _lib = C.CDLL(path)
+        _lib.psbo_align.restype = C.c_int
+        _lib.psbo_cigar.restype = C.c_int
+        _lib.psbo_traceback.restype = C.c_int
+        _lib.psbo_align_batch.restype = C.c_int
+        _lib.psbo_cigar_decode.restype = C.c_int
+    return _lib
+
+
+class Matrix:
+    """Plain-data substitution matrix for the oracle (independent of the product's matrices)."""
+
+    def __init__(self, table, mapper, is_pssm=False):
+        self.table = np.ascontiguousarray(table, dtype=np.int32)
+        self.mapper = np.ascontiguousarray(mapper, dtype=np.int32)
+        assert self.mapper.shape == (256,)
+        self.size = int(self.table.shape[1])
+        self.is_pssm = bool(is_pssm)
+        self.length = int(self.table.shape[0])
+        self.c = CMatrix(self.table.ctypes.data_as(C.POINTER(C.c_int)),
+                         self.mapper.ctypes.data_as(C.POINTER(C.c_int)), self.size, int(self.is_pssm),
+                         self.length)
+
+    @staticmethod
+    def create(alphabet: bytes, match: int, mismatch: int):
+        """parasail_matrix_create semantics: size = len+1, wildcard row/col 0,
+        both cases of a letter map to its index, every other byte to the wildcard."""
+        n = len(alphabet) + 1
+        t = np.full((n, n), mismatch, dtype=np.int32)
+        np.fill_diagonal(t, match)
+        t[n - 1, :] = 0
+        t[:, n - 1] = 0
+        mapper = np.full(256, n - 1, dtype=np.int32)
+        for i, ch in enumerate(alphabet):
+            mapper[ord(chr(ch).upper())] = i
+            mapper[ord(chr(ch).lower())] = i
+        return Matrix(t, mapper)
+
+    @staticmethod
+    def from_table(alphabet: str, rows):
+        """Square matrix from an explicit table whose last letter is the wildcard."""
+        n = len(alphabet)
+        t = np.array(rows, dtype=np.int32).reshape(n, n)
+        mapper = np.full(256, n - 1, dtype=np.int32)
+        for i, ch in enumerate(alphabet):
+            mapper[ord(ch.upper())] = i
+            mapper[ord(ch.lower())] = i
+        return Matrix(t, mapper)
+
+
+def _u8(b):
+    return np.frombuffer(bytes(b), dtype=np.uint8) if not isinstance(b, np.ndarray) else np.ascontiguousarray(b, dtype=np.uint8)
+
+
+def align(q, r, mat: Matrix, mode=NW, open=0, gap=0, s1_beg=True, s1_end=True, s2_beg=True, s2_end=True,
+          tables=False, rowcol=False, trace=False):
+    """One pair through the oracle.  Returns a dict with score/ends/stats and any requested
+    tables, rows/cols, trace bytes, CIGAR (ops, text, beg_query, beg_ref) and traceback strings."""
+    qa, ra = _u8(q), _u8(r)
+    qlen = mat.length if mat.is_pssm else len(qa)
+    rlen = len(ra)
+    cfg = Config(mode, int(s1_beg), int(s1_end), int(s2_beg), int(s2_end), open, gap)
+    out = Out()
+    keep = {}
+
+    def arr(name, n, dtype=np.int32, ctype=C.c_int):
+        a = np.zeros(n, dtype=dtype)
+        keep[name] = a
+        setattr(out, name, a.ctypes.data_as(C.POINTER(ctype)))
+
+    if tables:
+        for nm in ("score_table", "matches_table", "similar_table", "length_table"):
+            arr(nm, qlen * rlen)
+    if rowcol:
+        for nm in ("score_row", "matches_row", "similar_row", "length_row"):
+            arr(nm, rlen)
+        for nm in ("score_col", "matches_col", "similar_col", "length_col"):
+            arr(nm, qlen)
+    if trace:
+        arr("trace", qlen * rlen, np.int8, C.c_int8)
+    rc = lib().psbo_align(qa.ctypes.data_as(C.c_void_p), C.c_int(len(qa)), ra.ctypes.data_as(C.c_void_p),
+                          C.c_int(rlen), C.byref(cfg), C.byref(mat.c), C.byref(out))
+    if rc != 0:
+        raise ValueError("oracle rejected the input (empty sequence?)")
+    res = dict(score=out.score, end_query=out.end_query, end_ref=out.end_ref, matches=out.matches,
+               similar=out.similar, length=out.length)
+    for k, v in keep.items():
+        res[k] = v.reshape(qlen, rlen) if k.endswith("table") or k == "trace" else v
+    if trace:
+        ops = np.zeros(qlen + rlen + 4, dtype=np.uint32)
+        bq, br = C.c_int(), C.c_int()
+        n = lib().psbo_cigar(keep["trace"].ctypes.data_as(C.c_void_p), qa.ctypes.data_as(C.c_void_p),
+                             C.c_int(qlen), ra.ctypes.data_as(C.c_void_p), C.c_int(rlen), C.byref(mat.c),
+                             C.c_int(out.end_query), C.c_int(out.end_ref), ops.ctypes.data_as(C.c_void_p),
+                             C.byref(bq), C.byref(br))
+        res["cigar_ops"] = ops[:n].copy()
+        res["cigar"] = decode_cigar(ops[:n])
+        res["beg_query"], res["beg_ref"] = bq.value, br.value
+        bufs = [C.create_string_buffer(qlen + rlen + 1) for _ in range(3)]
+        lib().psbo_traceback(keep["trace"].ctypes.data_as(C.c_void_p), qa.ctypes.data_as(C.c_void_p),
+                             C.c_int(qlen), ra.ctypes.data_as(C.c_void_p), C.c_int(rlen), C.byref(mat.c),
+                             C.c_int(out.end_query), C.c_int(out.end_ref), C.c_char(b"|"), C.c_char(b" "),
+                             C.c_char(b" "), bufs[0], bufs[1], bufs[2])
+        res["traceback"] = tuple(b.value.decode() for b in bufs)
+    return res
+
+
+def decode_cigar(ops):
+    tab = "MIDNSHP=X"
+    return "".join(f"{int(o) >> 4}{tab[int(o) & 15]}" for o in ops)
+
+
+def align_batch(qcat, qoff, rcat, roff, mat: Matrix, mode=NW, open=0, gap=0, s1_beg=True, s1_end=True,
+                s2_beg=True, s2_end=True, shared_query=False, stats=False, cigar=False):
+    """n pairs through the oracle (single thread).  Returns dict of int32 arrays (+ CIGAR CSR)."""
+    qcat, rcat = _u8(qcat), _u8(rcat)
+    qoff = np.ascontiguousarray(qoff, dtype=np.int64)
+    roff = np.ascontiguousarray(roff, dtype=np.int64)
+    n = len(roff) - 1
+    cfg = Config(mode, int(s1_beg), int(s1_end), int(s2_beg), int(s2_end), open, gap)
+    res = {k: np.zeros(n, dtype=np.int32) for k in ("score", "end_query", "end_ref", "matches", "similar",
+                                                     "length", "beg_query", "beg_ref")}
+    cap = 0
+    cig_ops = np.zeros(1, dtype=np.uint32)
+    cig_off = np.zeros(n + 1, dtype=np.int64)
+    if cigar:
+        qtot = (qoff[1] - qoff[0]) * n if shared_query else qoff[-1] - qoff[0]
+        cap = int(qtot + roff[-1] - roff[0]) + 8
+        cig_ops = np.zeros(cap, dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    want_stats = stats
+    rc = lib().psbo_align_batch(p(qcat), p(qoff), p(rcat), p(roff), C.c_int64(n), C.c_int(int(shared_query)),
+                                C.byref(cfg), C.byref(mat.c), p(res["score"]), p(res["end_query"]),
+                                p(res["end_ref"]), p(res["matches"]) if want_stats else None,
+                                p(res["similar"]) if want_stats else None,
+                                p(res["length"]) if want_stats else None, C.c_int(int(cigar)), p(cig_ops),
+                                C.c_int64(cap), p(cig_off), p(res["beg_query"]), p(res["beg_ref"]))
+    if rc != 0:
+        raise RuntimeError("oracle batch failed")
+    if cigar:
+        res["cigar_off"] = cig_off
+        res["cigar_ops"] = cig_ops[: cig_off[-1]].copy()
+    return res

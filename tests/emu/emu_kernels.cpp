@@ -1,0 +1,30 @@
+// emu_kernels.cpp -- TEST ONLY.  Compiles the product's kernel sources with -DPSB_EMULATE
+// (every lane an OS thread, see csrc/psb_simt.h) so that the warp programs can be stepped
+// on a CPU-only box and compared with the oracle before any GPU time is spent.
+#define PSB_EMULATE 1
+#include "../../parasail_rs_b200/csrc/kern_gotoh32.cuh"
+#include <cstdio>
+
+using namespace psb;
+
+template <int K, bool STATS, bool TRACE, typename W>
+static void run32(const Gotoh32Params &p, int nblocks) {
+    size_t smem = gotoh32_smem_bytes(p.size, 1, STATS, sizeof(W));
+    emu::launch(nblocks, smem, [&]() { gotoh32_kernel<K, STATS, TRACE, W>(p); });
+}
+
+extern "C" int emu_gotoh32(int K, int stats, int trace, int wide_stats, const Gotoh32Params *pp, int nblocks) {
+    Gotoh32Params p = *pp;
+#define CASE(KK)                                                                              \
+    case KK:                                                                                  \
+        if (trace) run32<KK, false, true, unsigned>(p, nblocks);                              \
+        else if (stats && wide_stats) run32<KK, true, false, unsigned long long>(p, nblocks); \
+        else if (stats) run32<KK, true, false, unsigned>(p, nblocks);                         \
+        else run32<KK, false, false, unsigned>(p, nblocks);                                   \
+        return 0;
+    switch (K) {
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(8) CASE(16)
+    }
+    return -1;
+}
+extern "C" int emu_sizeof_params() { return (int)sizeof(Gotoh32Params); }

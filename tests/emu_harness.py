@@ -1,0 +1,88 @@
+"""Builds and drives tests/emu/emu_kernels.cpp: the product's kernel sources compiled with
+-DPSB_EMULATE so that warp programs run on CPU threads (test-only, never shipped)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
+OUT = os.path.join(ROOT, "tests", "emu", "libpsb_emu.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        deps = [SRC] + [os.path.join(ROOT, "parasail_rs_b200", "csrc", f)
+                        for f in os.listdir(os.path.join(ROOT, "parasail_rs_b200", "csrc")) if f.endswith((".cuh", ".h"))]
+        if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+            subprocess.run(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-o", OUT, SRC], check=True)
+        _lib = C.CDLL(OUT)
+    return _lib
+
+
+class Gotoh32Params(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("q_off", C.c_void_p), ("r", C.c_void_p), ("r_off", C.c_void_p),
+                ("order", C.c_void_p), ("n", C.c_int), ("shared_query", C.c_int), ("matrix", C.c_void_p),
+                ("size", C.c_int), ("is_pssm", C.c_int), ("open", C.c_int), ("gap", C.c_int),
+                ("mode", C.c_int), ("s1_beg", C.c_int), ("s1_end", C.c_int), ("s2_beg", C.c_int),
+                ("s2_end", C.c_int), ("score", C.c_void_p), ("end_query", C.c_void_p), ("end_ref", C.c_void_p),
+                ("matches", C.c_void_p), ("similar", C.c_void_p), ("length", C.c_void_p), ("bnd", C.c_void_p),
+                ("bnd_stride", C.c_longlong), ("trace", C.c_void_p), ("trace_off", C.c_void_p),
+                ("counter", C.c_void_p)]
+
+
+def trace_to_rowmajor(blob, off, K, lq, lr):
+    """kernel trace layout [strip][step][lane][K] -> row-major lq x lr bytes"""
+    nsteps = lr + 31
+    out = np.zeros((lq, lr), dtype=np.int8)
+    i = np.arange(lq)
+    strip, rem = i // (32 * K), i % (32 * K)
+    t, k = rem // K, rem % K
+    for j in range(lr):
+        s = j + t
+        idx = off + ((strip * nsteps + s) * 32 + t) * K + k
+        out[:, j] = blob[idx].astype(np.int8)
+    return out
+
+
+def gotoh32(qs, rs, mat, K, mode, open, gap, flags=(1, 1, 1, 1), stats=False, trace=False, wide=False,
+            shared_query=False, nblocks=1):
+    """Run the emulated general kernel on pairs (lists of uint8 arrays of raw residues)."""
+    assert lib().emu_sizeof_params() == C.sizeof(Gotoh32Params)
+    mapper = mat.mapper.astype(np.uint8)
+    qm = [mapper[np.asarray(q, dtype=np.uint8)] for q in qs]
+    rm = [mapper[np.asarray(r, dtype=np.uint8)] for r in rs]
+    n = len(rm)
+    qcat = np.concatenate(qm).astype(np.uint8)
+    qoff = np.zeros(len(qm) + 1, dtype=np.int64); qoff[1:] = np.cumsum([len(x) for x in qm])
+    rcat = np.concatenate(rm).astype(np.uint8)
+    roff = np.zeros(n + 1, dtype=np.int64); roff[1:] = np.cumsum([len(x) for x in rm])
+    table = np.ascontiguousarray(mat.table, dtype=np.int32)
+    outs = {k: np.full(n, -777, dtype=np.int32) for k in ("score", "end_query", "end_ref", "matches", "similar", "length")}
+    maxlr = int(max(len(x) for x in rm))
+    per_col = 2 + (2 * (2 if wide else 1) if stats else 0)
+    bnd = np.zeros(nblocks * per_col * maxlr + 16, dtype=np.int32)
+    counter = np.zeros(1, dtype=np.int32)
+    trace_off = np.zeros(n, dtype=np.int64)
+    tot = 0
+    for p in range(n):
+        lq = len(qm[0]) if shared_query else len(qm[p])
+        nstrips = (lq + 32 * K - 1) // (32 * K)
+        trace_off[p] = tot
+        tot += ((nstrips * (len(rm[p]) + 31) * 32 * K + 15) // 16) * 16
+    blob = np.zeros(tot if trace else 16, dtype=np.uint8)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    p = Gotoh32Params(ptr(qcat), ptr(qoff), ptr(rcat), ptr(roff), None, n, int(shared_query), ptr(table),
+                      mat.size, int(mat.is_pssm), open, gap, mode, flags[0], flags[1], flags[2], flags[3],
+                      ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(outs["matches"]),
+                      ptr(outs["similar"]), ptr(outs["length"]), ptr(bnd), per_col * maxlr, ptr(blob),
+                      ptr(trace_off), ptr(counter))
+    rc = lib().emu_gotoh32(K, int(stats), int(trace), int(wide), C.byref(p), nblocks)
+    assert rc == 0
+    if trace:
+        outs["trace"] = [trace_to_rowmajor(blob, int(trace_off[i]), K, len(qm[0]) if shared_query else len(qm[i]), len(rm[i]))
+                         for i in range(n)]
+    return outs
