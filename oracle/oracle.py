@@ -198,3 +198,40 @@ def align_batch(qcat, qoff, rcat, roff, mat: Matrix, mode=NW, open=0, gap=0, s1_
         res["cigar_off"] = cig_off
         res["cigar_ops"] = cig_ops[: cig_off[-1]].copy()
     return res
+
+
+# ---- the striped AVX2 CPU baseline (oracle/striped_cpu.cpp) -----------------------------------
+_slib = None
+
+
+def striped_lib():
+    global _slib
+    if _slib is None:
+        path = os.path.join(_HERE, "libpsb_striped.so")
+        src = os.path.join(_HERE, "striped_cpu.cpp")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        _slib = C.CDLL(path)
+        _slib.psbs_sw_scan.restype = C.c_double
+        _slib.psbs_hardware_threads.restype = C.c_int
+    return _slib
+
+
+def striped_sw_scan(query, cat, off, mat: Matrix, open, gap, threads=0):
+    """parasail-equivalent striped AVX2 `sw_striped_profile_sat` over a database, `threads` host
+    threads (0 = all).  Returns (dict of arrays incl. 'width', elapsed seconds)."""
+    q, cat = _u8(query), _u8(cat)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    n = len(off) - 1
+    L = striped_lib()
+    if threads <= 0:
+        threads = L.psbs_hardware_threads()
+    res = {k: np.zeros(n, dtype=np.int32) for k in ("score", "end_query", "end_ref")}
+    width = np.zeros(n, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    secs = L.psbs_sw_scan(p(q), C.c_int(len(q)), p(cat), p(off), C.c_int64(n), p(mat.table), C.c_int(mat.size),
+                          p(mat.mapper), C.c_int(open), C.c_int(gap), C.c_int(threads), p(res["score"]),
+                          p(res["end_query"]), p(res["end_ref"]), p(width))
+    res["width"] = width
+    res["threads"] = threads
+    return res, float(secs)

@@ -1,0 +1,997 @@
+// engine.cu -- host side of the GPU path: device context, batching, kernel launches, the
+// resident database and the resident query profile.  No CPU fallback exists: every entry
+// point fails with PSB_ENODEV / PSB_ECUDA (and psb_last_error text) when the device is unusable.
+//
+// Batch entry points: psb_align_pairs (many pairs, SURVEY configs C1/C3/C4) and psb_scan (one
+// resident profile vs a resident packed database, C2).  parasail-rs's per-pair
+// Aligner::align [REF src/aligner/mod.rs:397-452] arrives here as an n = 1 batch (result.cpp).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_scan.cuh>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "kern_gotoh32.cuh"
+#include "kern_sw16.cuh"
+#include "kern_util.cuh"
+#include "psb_internal.h"
+
+namespace psb {
+
+// ---- per-host-thread context ----------------------------------------------------------------
+struct Ctx {
+    bool ready = false;
+    int device = -1;          // -1: take the current CUDA device on first use
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sms = 0;
+    double last_ms = 0.0;
+    int launches = 0;
+};
+static thread_local Ctx g_ctx;
+
+#define PSB_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+            return PSB_ECUDA;                                                                   \
+        }                                                                                       \
+    } while (0)
+
+static int ensure_ctx() {
+    Ctx &c = g_ctx;
+    if (c.ready) {
+        cudaError_t e = cudaSetDevice(c.device);
+        if (e != cudaSuccess) { set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); return PSB_ECUDA; }
+        return PSB_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libparasail_b200 has no CPU fallback (needs an sm_100a GPU)");
+        return PSB_ENODEV;
+    }
+    if (c.device < 0) {
+        if (cudaGetDevice(&c.device) != cudaSuccess) c.device = 0;
+    }
+    if (c.device >= ndev) { set_error("psb_set_device: device index out of range"); return PSB_EINVAL; }
+    PSB_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    PSB_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major < 10) {
+        set_error(std::string("device ") + prop.name + " is not sm_100-class; this library ships sm_100a code only");
+        return PSB_ENODEV;
+    }
+    c.sms = prop.multiProcessorCount;
+    PSB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    if (!c.stream) c.stream = c.own_stream;
+    PSB_CUDA(cudaEventCreate(&c.ev0));
+    PSB_CUDA(cudaEventCreate(&c.ev1));
+    // keep freed stream-ordered allocations cached so repeated batches do not hit the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    c.ready = true;
+    return PSB_OK;
+}
+
+// stream-ordered device buffer (RAII)
+struct DevMem {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = nullptr;
+    DevMem() = default;
+    DevMem(const DevMem &) = delete;
+    DevMem &operator=(const DevMem &) = delete;
+    ~DevMem() { release(); }
+    int alloc(size_t n, cudaStream_t stream) {
+        release();
+        s = stream; bytes = n;
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMallocAsync(&p, n, stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error(std::string("cudaMallocAsync(") + std::to_string(n) + "): " + cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? PSB_ENOMEM : PSB_ECUDA;
+        }
+        return PSB_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+#define PSB_TRY(expr) do { int rc_ = (expr); if (rc_ != PSB_OK) return rc_; } while (0)
+
+// pinned host blocks are slow to create; recycle them process-wide by size class
+static std::mutex g_pin_mu;
+static std::multimap<size_t, void *> g_pin_free;
+static void *pinned_alloc(size_t bytes) {
+    size_t cls = 4096;
+    while (cls < bytes) cls <<= 1;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        auto it = g_pin_free.find(cls);
+        if (it != g_pin_free.end()) { void *p = it->second; g_pin_free.erase(it); return p; }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, cls) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+static void pinned_free(void *p, size_t bytes) {
+    if (!p) return;
+    size_t cls = 4096;
+    while (cls < bytes) cls <<= 1;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_free.size() < 64) g_pin_free.emplace(cls, p);
+    else cudaFreeHost(p);
+}
+
+struct BatchImpl {
+    std::vector<std::pair<void *, size_t>> blocks;
+    void *take(size_t bytes) {
+        void *p = pinned_alloc(bytes);
+        if (p) blocks.emplace_back(p, bytes);
+        return p;
+    }
+};
+
+static void fill_lut(unsigned *lut, const uint8_t *mapper) {
+    for (int i = 0; i < 64; ++i)
+        lut[i] = (unsigned)mapper[4 * i] | ((unsigned)mapper[4 * i + 1] << 8) | ((unsigned)mapper[4 * i + 2] << 16) |
+                 ((unsigned)mapper[4 * i + 3] << 24);
+}
+
+// ---- kernel dispatch --------------------------------------------------------------------------
+static const int kClassK[] = {1, 2, 4, 6, 8, 10, 12, 16};
+static constexpr int kNumClass = 8;
+static int class_of_len(int lq) {
+    for (int c = 0; c < kNumClass; ++c) if (lq <= 32 * kClassK[c]) return c;
+    return kNumClass - 1;
+}
+
+enum Variant { V_SCORE = 0, V_STATS32, V_STATS64, V_TRACE, V_TABLE };
+
+template <int K> static const void *gotoh32_fn_k(Variant v) {
+    switch (v) {
+        case V_SCORE: return (const void *)gotoh32_kernel<K, false, false, false, unsigned>;
+        case V_STATS32: return (const void *)gotoh32_kernel<K, true, false, false, unsigned>;
+        case V_STATS64: return (const void *)gotoh32_kernel<K, true, false, false, unsigned long long>;
+        case V_TRACE: return (const void *)gotoh32_kernel<K, false, true, false, unsigned>;
+        case V_TABLE: return (const void *)gotoh32_kernel<K, true, false, true, unsigned long long>;
+    }
+    return nullptr;
+}
+static const void *gotoh32_fn(int K, Variant v) {
+    switch (K) {
+        case 1: return gotoh32_fn_k<1>(v);
+        case 2: return gotoh32_fn_k<2>(v);
+        case 4: return gotoh32_fn_k<4>(v);
+        case 6: return gotoh32_fn_k<6>(v);
+        case 8: return gotoh32_fn_k<8>(v);
+        case 10: return gotoh32_fn_k<10>(v);
+        case 12: return gotoh32_fn_k<12>(v);
+        case 16: return gotoh32_fn_k<16>(v);
+    }
+    return nullptr;
+}
+
+static constexpr int kWarpsPerBlock = 4;
+
+static int launch_gotoh32(int K, Variant v, Gotoh32Params &p, int nwork, long long *grid_warps_out = nullptr) {
+    Ctx &c = g_ctx;
+    const void *fn = gotoh32_fn(K, v);
+    const bool stats = v == V_STATS32 || v == V_STATS64 || v == V_TABLE;
+    const int statw = v == V_STATS32 ? 4 : 8;
+    const size_t smem = gotoh32_smem_bytes(p.is_pssm ? 0 : p.size, kWarpsPerBlock, stats, statw);
+    if (smem > 200 * 1024) { set_error("substitution matrix too large for shared memory"); return PSB_EUNSUPPORTED; }
+    if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = std::min<long long>((nwork + kWarpsPerBlock - 1) / kWarpsPerBlock, (long long)c.sms * per_sm);
+    if (blocks < 1) blocks = 1;
+    if (grid_warps_out) *grid_warps_out = blocks * kWarpsPerBlock;
+    void *args[] = {&p};
+    PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kWarpsPerBlock * 32), args, smem, c.stream));
+    c.launches++;
+    return PSB_OK;
+}
+
+static long long max_grid_warps() { return (long long)g_ctx.sms * 16 * kWarpsPerBlock; }
+
+// ---- many pairs ---------------------------------------------------------------------------------
+struct PairChunk {
+    int64_t lo, hi;  // pair range of the caller's batch handled by this pass
+};
+
+static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_batch_t *b, int64_t *csr_used) {
+    Ctx &c = g_ctx;
+    const FnConfig &cfg = req.cfg;
+    const HostMatrix &m = *req.matrix;
+    const int64_t n = hi - lo;
+    const bool pssm = m.type == PARASAIL_MATRIX_TYPE_PSSM;
+    const bool want_table = req.extra && (cfg.table || cfg.rowcol);
+    const bool want_trace = cfg.trace;
+
+    // lengths, classes, byte ranges
+    const int64_t q_lo = req.shared_query ? req.q_off[0] : req.q_off[lo];
+    const int64_t q_hi = req.shared_query ? req.q_off[1] : req.q_off[hi];
+    const int64_t r_lo = req.r_off[lo], r_hi = req.r_off[hi];
+    std::vector<std::vector<int>> cls(kNumClass);
+    int max_lr_multistrip = 0;
+    int max_sum = 0, max_min = 0;
+    bool uniform = true;
+    int first_cls = -1;
+    long long first_cells = -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const int lq = pssm ? m.length : (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + i + 1] - req.q_off[lo + i]);
+        const int lr = (int)(req.r_off[lo + i + 1] - req.r_off[lo + i]);
+        if (lq <= 0 || lr <= 0) { set_error("empty sequence in batch (pair " + std::to_string(lo + i) + ")"); return PSB_EINVAL; }
+        const int cl = class_of_len(lq);
+        cls[cl].push_back((int)i);
+        if (lq > 32 * kClassK[cl]) max_lr_multistrip = std::max(max_lr_multistrip, lr);
+        max_sum = std::max(max_sum, lq + lr);
+        max_min = std::max(max_min, std::min(lq, lr));
+        const long long cells = (long long)lq * lr;
+        if (first_cls < 0) { first_cls = cl; first_cells = cells; }
+        else if (cl != first_cls || cells != first_cells) uniform = false;
+        b->cells += (double)cells;
+    }
+    const bool wide_stats = !(max_min < 1024 && max_sum < 4096);
+
+    // upload residues + offsets (relative to this range) and map them to matrix columns
+    DevMem d_q, d_r, d_qoff, d_roff, d_matrix;
+    const size_t qbytes = pssm ? (size_t)m.length : (size_t)(q_hi - q_lo);
+    PSB_TRY(d_q.alloc(qbytes, c.stream));
+    PSB_TRY(d_r.alloc((size_t)(r_hi - r_lo), c.stream));
+    std::vector<long long> qoff_rel(req.shared_query || pssm ? 2 : n + 1), roff_rel(n + 1);
+    if (req.shared_query || pssm) { qoff_rel[0] = 0; qoff_rel[1] = (long long)qbytes; }
+    else for (int64_t i = 0; i <= n; ++i) qoff_rel[i] = req.q_off[lo + i] - q_lo;
+    for (int64_t i = 0; i <= n; ++i) roff_rel[i] = req.r_off[lo + i] - r_lo;
+    PSB_TRY(d_qoff.alloc(qoff_rel.size() * sizeof(long long), c.stream));
+    PSB_TRY(d_roff.alloc(roff_rel.size() * sizeof(long long), c.stream));
+    PSB_TRY(d_matrix.alloc(m.table.size() * sizeof(int), c.stream));
+    if (pssm && m.query.size() == (size_t)m.length)
+        PSB_CUDA(cudaMemcpyAsync(d_q.p, m.query.data(), qbytes, cudaMemcpyHostToDevice, c.stream));
+    else if (pssm)
+        PSB_CUDA(cudaMemsetAsync(d_q.p, 0xff, qbytes, c.stream));  // no query residues: nothing "matches"
+    else
+        PSB_CUDA(cudaMemcpyAsync(d_q.p, req.q_cat + q_lo, qbytes, cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaMemcpyAsync(d_r.p, req.r_cat + r_lo, (size_t)(r_hi - r_lo), cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaMemcpyAsync(d_qoff.p, qoff_rel.data(), qoff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaMemcpyAsync(d_roff.p, roff_rel.data(), roff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaMemcpyAsync(d_matrix.p, m.table.data(), m.table.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaEventRecord(c.ev0, c.stream));
+    {
+        MapParams mp;
+        fill_lut(mp.lut, m.mapper);
+        const int blocks = c.sms * 8;
+        if (!(pssm && m.query.size() != (size_t)m.length)) {
+            mp.data = d_q.as<uint8_t>(); mp.n = (long long)qbytes;
+            map_residues_kernel<<<blocks, 256, 0, c.stream>>>(mp);
+            c.launches++;
+        }
+        mp.data = d_r.as<uint8_t>(); mp.n = (long long)(r_hi - r_lo);
+        map_residues_kernel<<<blocks, 256, 0, c.stream>>>(mp);
+        c.launches++;
+    }
+
+    // outputs
+    DevMem d_out[6], d_counter, d_bnd;
+    const int nout = cfg.stats || want_table ? 6 : 3;
+    for (int k = 0; k < nout; ++k) PSB_TRY(d_out[k].alloc((size_t)n * sizeof(int), c.stream));
+    PSB_TRY(d_counter.alloc(sizeof(int) * (kNumClass + 1), c.stream));
+    PSB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int) * (kNumClass + 1), c.stream));
+    const bool stats_kernel = cfg.stats || want_table;
+    const int bnd_words_per_col = 2 + (stats_kernel ? 2 * ((wide_stats || want_table) ? 2 : 1) : 0);
+    const long long bnd_stride = (long long)max_lr_multistrip * bnd_words_per_col;
+    if (bnd_stride > 0) PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps()) * sizeof(int), c.stream));
+
+    // trace / table blocks: [strip][step][lane][K] per pair
+    DevMem d_trace, d_traceoff, d_tab[4], d_rev, d_revoff, d_nops, d_beg[2];
+    std::vector<long long> trace_off, rev_off;
+    long long trace_total = 0, rev_total = 0;
+    if (want_trace || want_table) {
+        trace_off.resize(n);
+        rev_off.resize(n);
+        for (int cl = 0; cl < kNumClass; ++cl)
+            for (int id : cls[cl]) {
+                const int K = kClassK[cl];
+                const int lq = pssm ? m.length : (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + id + 1] - req.q_off[lo + id]);
+                const int lr = (int)(req.r_off[lo + id + 1] - req.r_off[lo + id]);
+                const long long strips = (lq + 32 * K - 1) / (32 * K);
+                trace_off[id] = trace_total;
+                trace_total += ((strips * (lr + 31) * 32 * K + 15) / 16) * 16;
+                rev_off[id] = rev_total;
+                rev_total += lq + lr + 2;
+            }
+        PSB_TRY(d_traceoff.alloc((size_t)n * sizeof(long long), c.stream));
+        PSB_CUDA(cudaMemcpyAsync(d_traceoff.p, trace_off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+        if (want_trace) PSB_TRY(d_trace.alloc((size_t)trace_total, c.stream));
+        if (want_table) for (int k = 0; k < 4; ++k) PSB_TRY(d_tab[k].alloc((size_t)trace_total * sizeof(int), c.stream));
+    }
+
+    Gotoh32Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.q = d_q.as<uint8_t>(); p.q_off = d_qoff.as<long long>();
+    p.r = d_r.as<uint8_t>(); p.r_off = d_roff.as<long long>();
+    p.shared_query = (req.shared_query || pssm) ? 1 : 0;
+    p.matrix = d_matrix.as<int>(); p.size = m.size; p.is_pssm = pssm ? 1 : 0;
+    p.open = req.open; p.gap = req.gap;
+    p.mode = cfg.mode; p.s1_beg = cfg.s1_beg; p.s1_end = cfg.s1_end; p.s2_beg = cfg.s2_beg; p.s2_end = cfg.s2_end;
+    p.score = d_out[0].as<int>(); p.end_query = d_out[1].as<int>(); p.end_ref = d_out[2].as<int>();
+    p.matches = d_out[3].as<int>(); p.similar = d_out[4].as<int>(); p.length = d_out[5].as<int>();
+    p.bnd = d_bnd.as<int>(); p.bnd_stride = bnd_stride;
+    p.trace = d_trace.as<uint8_t>(); p.trace_off = d_traceoff.as<long long>();
+    p.tabH = d_tab[0].as<int>(); p.tabM = d_tab[1].as<int>(); p.tabS = d_tab[2].as<int>(); p.tabL = d_tab[3].as<int>();
+    p.tab_off = d_traceoff.as<long long>();
+
+    std::vector<DevMem> d_orders(kNumClass);
+    for (int cl = 0; cl < kNumClass; ++cl) {
+        if (cls[cl].empty()) continue;
+        std::vector<int> &ids = cls[cl];
+        p.order = nullptr;
+        if (!uniform) {
+            // longest first so the dynamic queue ends on short pairs
+            std::stable_sort(ids.begin(), ids.end(), [&](int a, int bb) {
+                const long long la = req.r_off[lo + a + 1] - req.r_off[lo + a], lb = req.r_off[lo + bb + 1] - req.r_off[lo + bb];
+                return la > lb;
+            });
+            PSB_TRY(d_orders[cl].alloc(ids.size() * sizeof(int), c.stream));
+            PSB_CUDA(cudaMemcpyAsync(d_orders[cl].p, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+            p.order = d_orders[cl].as<int>();
+        }
+        p.n = (int)ids.size();
+        p.counter = d_counter.as<int>() + cl;
+        const Variant v = want_table ? V_TABLE : (want_trace ? V_TRACE : (cfg.stats ? (wide_stats ? V_STATS64 : V_STATS32) : V_SCORE));
+        PSB_TRY(launch_gotoh32(kClassK[cl], v, p, p.n));
+    }
+
+    // device-side trace walk -> CIGAR CSR
+    DevMem d_csroff, d_csr, d_scan_tmp;
+    if (want_trace) {
+        PSB_TRY(d_rev.alloc((size_t)rev_total * sizeof(unsigned), c.stream));
+        PSB_TRY(d_revoff.alloc((size_t)n * sizeof(long long), c.stream));
+        PSB_CUDA(cudaMemcpyAsync(d_revoff.p, rev_off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+        PSB_TRY(d_nops.alloc(((size_t)n + 1) * sizeof(int), c.stream));
+        PSB_CUDA(cudaMemsetAsync(d_nops.p, 0, ((size_t)n + 1) * sizeof(int), c.stream));
+        PSB_TRY(d_beg[0].alloc((size_t)n * sizeof(int), c.stream));
+        PSB_TRY(d_beg[1].alloc((size_t)n * sizeof(int), c.stream));
+        for (int cl = 0; cl < kNumClass; ++cl) {
+            if (cls[cl].empty()) continue;
+            if (!d_orders[cl].p) {
+                PSB_TRY(d_orders[cl].alloc(cls[cl].size() * sizeof(int), c.stream));
+                PSB_CUDA(cudaMemcpyAsync(d_orders[cl].p, cls[cl].data(), cls[cl].size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+            }
+            WalkParams w;
+            w.q = p.q; w.q_off = p.q_off; w.r = p.r; w.r_off = p.r_off; w.shared_query = p.shared_query;
+            w.ids = d_orders[cl].as<int>(); w.n = (int)cls[cl].size(); w.K = kClassK[cl];
+            w.trace = p.trace; w.trace_off = p.trace_off; w.end_query = p.end_query; w.end_ref = p.end_ref;
+            w.rev_ops = d_rev.as<unsigned>(); w.rev_off = d_revoff.as<long long>();
+            w.nops = d_nops.as<int>(); w.beg_query = d_beg[0].as<int>(); w.beg_ref = d_beg[1].as<int>();
+            walk_trace_kernel<<<(w.n + 127) / 128, 128, 0, c.stream>>>(w);
+            c.launches++;
+        }
+        // exclusive scan of nops[0..n] -> csr offsets (n+1)
+        PSB_TRY(d_csroff.alloc(((size_t)n + 1) * sizeof(long long), c.stream));
+        size_t tmp_bytes = 0;
+        auto in_it = d_nops.as<int>();
+        PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in_it, d_csroff.as<long long>(), (int)(n + 1), c.stream));
+        PSB_TRY(d_scan_tmp.alloc(tmp_bytes, c.stream));
+        PSB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, in_it, d_csroff.as<long long>(), (int)(n + 1), c.stream));
+        c.launches++;
+    }
+    PSB_CUDA(cudaEventRecord(c.ev1, c.stream));
+
+    // results back to the batch's pinned arrays
+    int *outs[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
+    const int ncopy = cfg.stats ? 6 : 3;
+    for (int k = 0; k < ncopy; ++k)
+        PSB_CUDA(cudaMemcpyAsync(outs[k] + lo, d_out[k].p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    if (want_trace) {
+        std::vector<long long> csr_off(n + 1);
+        PSB_CUDA(cudaMemcpyAsync(csr_off.data(), d_csroff.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+        PSB_CUDA(cudaStreamSynchronize(c.stream));
+        const long long total = csr_off[n];
+        PSB_TRY(d_csr.alloc((size_t)total * sizeof(unsigned), c.stream));
+        CompactParams cp;
+        cp.rev_ops = d_rev.as<unsigned>(); cp.rev_off = d_revoff.as<long long>();
+        cp.csr_off = d_csroff.as<long long>(); cp.csr_ops = d_csr.as<unsigned>(); cp.n = (int)n;
+        compact_cigar_kernel<<<c.sms * 8, 256, 0, c.stream>>>(cp);
+        c.launches++;
+        BatchImpl *impl = (BatchImpl *)b->impl;
+        // grow the CSR op array (pinned) to hold this range
+        uint32_t *ops = (uint32_t *)impl->take((size_t)(*csr_used + total + 1) * sizeof(uint32_t));
+        if (!ops) { set_error("pinned allocation failed"); return PSB_ENOMEM; }
+        if (*csr_used) std::memcpy(ops, b->cigar_ops, (size_t)*csr_used * sizeof(uint32_t));
+        b->cigar_ops = ops;
+        PSB_CUDA(cudaMemcpyAsync(ops + *csr_used, d_csr.p, (size_t)total * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream));
+        PSB_CUDA(cudaMemcpyAsync(b->beg_query + lo, d_beg[0].p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        PSB_CUDA(cudaMemcpyAsync(b->beg_ref + lo, d_beg[1].p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        for (int64_t i = 0; i <= n; ++i) b->cigar_off[lo + i] = *csr_used + csr_off[i];
+        *csr_used += total;
+    }
+
+    // single-pair extras: row-major trace bytes, tables, last row / column
+    if (req.extra && n == 1 && (want_trace || want_table)) {
+        psb_result_extra *x = req.extra;
+        const int cl = first_cls, K = kClassK[cl];
+        const int lq = x->qlen, lr = x->rlen, nsteps = lr + 31;
+        auto cell_index = [&](int i, int j) {
+            const int strip = i / (32 * K), rem = i % (32 * K), lane = rem / K, k = rem % K;
+            return (((size_t)strip * nsteps + (j + lane)) * 32 + lane) * K + k;
+        };
+        if (want_trace) {
+            std::vector<uint8_t> blob((size_t)trace_total);
+            PSB_CUDA(cudaMemcpyAsync(blob.data(), d_trace.p, blob.size(), cudaMemcpyDeviceToHost, c.stream));
+            PSB_CUDA(cudaStreamSynchronize(c.stream));
+            x->trace.resize((size_t)lq * lr);
+            for (int i = 0; i < lq; ++i)
+                for (int j = 0; j < lr; ++j) x->trace[(size_t)i * lr + j] = (int8_t)blob[cell_index(i, j)];
+        }
+        if (want_table) {
+            std::vector<int> planes[4];
+            const int np = cfg.stats ? 4 : 1;
+            for (int k = 0; k < np; ++k) {
+                planes[k].resize((size_t)trace_total);
+                PSB_CUDA(cudaMemcpyAsync(planes[k].data(), d_tab[k].p, planes[k].size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            }
+            PSB_CUDA(cudaStreamSynchronize(c.stream));
+            std::vector<int> *tabs[4] = {&x->score_table, &x->matches_table, &x->similar_table, &x->length_table};
+            std::vector<int> *rows[4] = {&x->score_row, &x->matches_row, &x->similar_row, &x->length_row};
+            std::vector<int> *cols[4] = {&x->score_col, &x->matches_col, &x->similar_col, &x->length_col};
+            for (int k = 0; k < np; ++k) {
+                if (cfg.table) {
+                    tabs[k]->resize((size_t)lq * lr);
+                    for (int i = 0; i < lq; ++i)
+                        for (int j = 0; j < lr; ++j) (*tabs[k])[(size_t)i * lr + j] = planes[k][cell_index(i, j)];
+                } else {
+                    rows[k]->resize(lr); cols[k]->resize(lq);
+                    for (int j = 0; j < lr; ++j) (*rows[k])[j] = planes[k][cell_index(lq - 1, j)];
+                    for (int i = 0; i < lq; ++i) (*cols[k])[i] = planes[k][cell_index(i, lr - 1)];
+                }
+            }
+        }
+    }
+    PSB_CUDA(cudaStreamSynchronize(c.stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_ms += ms;
+    return PSB_OK;
+}
+
+static psb_batch_t *new_batch(int64_t n, const FnConfig &cfg) {
+    psb_batch_t *b = new psb_batch_t();
+    std::memset(b, 0, sizeof(*b));
+    BatchImpl *impl = new BatchImpl();
+    b->impl = impl;
+    b->n = n;
+    b->flag = cfg.flag();
+    if (cfg.width == 0) b->flag |= PARASAIL_FLAG_BITS_32;
+    const size_t ib = (size_t)std::max<int64_t>(n, 1) * sizeof(int);
+    b->score = (int *)impl->take(ib); b->end_query = (int *)impl->take(ib); b->end_ref = (int *)impl->take(ib);
+    bool ok = b->score && b->end_query && b->end_ref;
+    if (cfg.stats) {
+        b->matches = (int *)impl->take(ib); b->similar = (int *)impl->take(ib); b->length = (int *)impl->take(ib);
+        ok = ok && b->matches && b->similar && b->length;
+    }
+    if (cfg.trace) {
+        b->cigar_off = (int64_t *)impl->take(((size_t)n + 1) * sizeof(int64_t));
+        b->beg_query = (int *)impl->take(ib); b->beg_ref = (int *)impl->take(ib);
+        ok = ok && b->cigar_off && b->beg_query && b->beg_ref;
+        if (ok) b->cigar_off[0] = 0;
+    }
+    b->saturated = (uint8_t *)impl->take((size_t)std::max<int64_t>(n, 1));
+    ok = ok && b->saturated;
+    if (!ok) { free_batch(b); return nullptr; }
+    std::memset(b->saturated, 0, (size_t)std::max<int64_t>(n, 1));
+    return b;
+}
+
+void free_batch(psb_batch_t *b) {
+    if (!b) return;
+    BatchImpl *impl = (BatchImpl *)b->impl;
+    if (impl) {
+        for (auto &blk : impl->blocks) pinned_free(blk.first, blk.second);
+        delete impl;
+    }
+    delete b;
+}
+
+int run_pairs(const PairsRequest &req, psb_batch_t **out) {
+    if (out) *out = nullptr;
+    if (!out || !req.matrix || !req.r_cat || !req.r_off || req.n <= 0 || (!req.q_cat && req.matrix->type != PARASAIL_MATRIX_TYPE_PSSM)) {
+        set_error("psb: NULL argument or empty batch");
+        return PSB_EINVAL;
+    }
+    if (req.n > 0x7fffffff) { set_error("psb: more than 2^31-1 pairs in one batch"); return PSB_EUNSUPPORTED; }
+    if (req.matrix->size > 96 && req.matrix->type != PARASAIL_MATRIX_TYPE_PSSM) { set_error("psb: alphabets above 96 letters are not supported"); return PSB_EUNSUPPORTED; }
+    if ((req.cfg.table || req.cfg.rowcol) && !(req.extra && req.n == 1)) {
+        set_error("psb: _table/_rowcol outputs exist only on the single-pair API");
+        return PSB_EUNSUPPORTED;
+    }
+    PSB_TRY(ensure_ctx());
+    Ctx &c = g_ctx;
+    c.last_ms = 0.0; c.launches = 0;
+    psb_batch_t *b = new_batch(req.n, req.cfg);
+    if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
+    // trace batches are cut so that a pass's trace + scratch stays within a fixed budget
+    const int64_t budget = (int64_t)24 << 30;
+    int64_t csr_used = 0;
+    int64_t lo = 0;
+    while (lo < req.n) {
+        int64_t hi = req.n;
+        if (req.cfg.trace) {
+            int64_t bytes = 0;
+            hi = lo;
+            while (hi < req.n) {
+                const int64_t lq = req.shared_query ? req.q_off[1] - req.q_off[0] : req.q_off[hi + 1] - req.q_off[hi];
+                const int64_t lr = req.r_off[hi + 1] - req.r_off[hi];
+                const int K = kClassK[class_of_len((int)std::min<int64_t>(lq, 1 << 20))];
+                const int64_t need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);
+                if (hi > lo && bytes + need > budget) break;
+                bytes += need; ++hi;
+            }
+        }
+        const int rc = run_pairs_range(req, lo, hi, b, &csr_used);
+        if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); free_batch(b); return rc; }
+        lo = hi;
+    }
+    *out = b;
+    return PSB_OK;
+}
+
+// ---- resident database ----------------------------------------------------------------------------
+}  // namespace psb
+
+struct psb_db {
+    int device = 0;
+    int64_t n = 0, residues = 0, words = 0;
+    int bits = 5;
+    int msize = 0;
+    uint8_t mapper[256];
+    std::vector<int> perm;          // sorted position -> caller's subject id (length descending)
+    std::vector<int> len_sorted;
+    unsigned *d_words = nullptr;
+    long long *d_word_off = nullptr;  // n+1
+    int *d_perm = nullptr;
+    int *d_len = nullptr;
+    // unpacked copy for the general 32-bit path, built on first use
+    uint8_t *d_bytes = nullptr;
+    long long *d_byte_off = nullptr;
+    std::mutex mu;
+};
+
+namespace psb {
+
+struct DevProfile {
+    uint8_t *d_query = nullptr;     // mapped residues
+    long long *d_qoff = nullptr;    // {0, Lq}
+    int *d_matrix = nullptr;
+    std::vector<uint8_t> mapped;    // host copy of the mapped query
+    Sw16Profile sw16;               // packed int8 profile (+open) for the 16-bit scan kernel
+};
+
+void release_profile_resident(parasail_profile *p) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    for (auto &kv : p->resident) {
+        DevProfile *d = (DevProfile *)kv.second;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(kv.first);
+        cudaFree(d->d_query); cudaFree(d->d_qoff); cudaFree(d->d_matrix); cudaFree(d->sw16.prof);
+        cudaSetDevice(cur);
+        delete d;
+    }
+    p->resident.clear();
+}
+
+static int get_dev_profile(const parasail_profile *prof, DevProfile **out) {
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(prof->mu);
+    auto it = prof->resident.find(c.device);
+    if (it != prof->resident.end()) { *out = (DevProfile *)it->second; return PSB_OK; }
+    DevProfile *d = new DevProfile();
+    const HostMatrix &m = prof->matrix;
+    const size_t lq = prof->query.size();
+    std::vector<uint8_t> mapped(lq);
+    for (size_t i = 0; i < lq; ++i) mapped[i] = m.mapper[prof->query[i]];
+    long long qoff[2] = {0, (long long)lq};
+    PSB_CUDA(cudaMalloc(&d->d_query, std::max<size_t>(lq, 16)));
+    PSB_CUDA(cudaMalloc(&d->d_qoff, sizeof(qoff)));
+    PSB_CUDA(cudaMalloc(&d->d_matrix, m.table.size() * sizeof(int)));
+    PSB_CUDA(cudaMemcpyAsync(d->d_query, mapped.data(), lq, cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaMemcpyAsync(d->d_qoff, qoff, sizeof(qoff), cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaMemcpyAsync(d->d_matrix, m.table.data(), m.table.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    d->mapped = mapped;
+    PSB_CUDA(cudaStreamSynchronize(c.stream));
+    prof->resident[c.device] = d;
+    *out = d;
+    return PSB_OK;
+}
+
+static int db_ensure_bytes(psb_db *db) {
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(db->mu);
+    if (db->d_bytes) return PSB_OK;
+    std::vector<long long> off(db->n + 1);
+    off[0] = 0;
+    for (int64_t i = 0; i < db->n; ++i) off[i + 1] = off[i] + db->len_sorted[i];
+    PSB_CUDA(cudaMalloc(&db->d_bytes, std::max<size_t>((size_t)db->residues, 16)));
+    PSB_CUDA(cudaMalloc(&db->d_byte_off, off.size() * sizeof(long long)));
+    PSB_CUDA(cudaMemcpyAsync(db->d_byte_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+    UnpackParams u;
+    u.words = db->d_words; u.word_off = db->d_word_off; u.ids = nullptr; u.out_off = db->d_byte_off;
+    u.out = db->d_bytes; u.n = db->n; u.bits = db->bits;
+    unpack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(u);
+    c.launches++;
+    PSB_CUDA(cudaStreamSynchronize(c.stream));
+    return PSB_OK;
+}
+
+// general 32-bit path over (a subset of) the resident database; results land in caller order
+static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, int open, int gap, psb_db *db,
+                        const int *d_subset, int nsubset, int *const d_out[6]) {
+    Ctx &c = g_ctx;
+    PSB_TRY(db_ensure_bytes(db));
+    const HostMatrix &m = prof->matrix;
+    const int lq = (int)prof->query.size();
+    const int cl = class_of_len(lq), K = kClassK[cl];
+    const bool pssm = m.type == PARASAIL_MATRIX_TYPE_PSSM;
+    DevMem d_counter, d_bnd;
+    PSB_TRY(d_counter.alloc(sizeof(int), c.stream));
+    PSB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int), c.stream));
+    const bool wide = !(std::min(lq, db->len_sorted[0]) < 1024 && lq + db->len_sorted[0] < 4096);
+    long long bnd_stride = 0;
+    if (lq > 32 * K) {
+        bnd_stride = (long long)db->len_sorted[0] * (2 + (cfg.stats ? (wide ? 4 : 2) : 0));
+        PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps()) * sizeof(int), c.stream));
+    }
+    Gotoh32Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.q = dp->d_query; p.q_off = dp->d_qoff; p.r = db->d_bytes; p.r_off = db->d_byte_off;
+    p.order = d_subset; p.n = d_subset ? nsubset : (int)db->n; p.shared_query = 1;
+    p.matrix = dp->d_matrix; p.size = m.size; p.is_pssm = pssm ? 1 : 0;
+    p.open = open; p.gap = gap;
+    p.mode = cfg.mode; p.s1_beg = cfg.s1_beg; p.s1_end = cfg.s1_end; p.s2_beg = cfg.s2_beg; p.s2_end = cfg.s2_end;
+    p.score = d_out[0]; p.end_query = d_out[1]; p.end_ref = d_out[2];
+    p.matches = d_out[3]; p.similar = d_out[4]; p.length = d_out[5];
+    p.bnd = d_bnd.as<int>(); p.bnd_stride = bnd_stride;
+    p.counter = d_counter.as<int>();
+    p.out_map = db->d_perm;
+    const Variant v = cfg.stats ? (wide ? V_STATS64 : V_STATS32) : V_SCORE;
+    PSB_TRY(launch_gotoh32(K, v, p, p.n));
+    return PSB_OK;
+}
+
+
+// (re)build the packed 16-bit profile when the gap-open penalty baked into it changes
+static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open, int gap) {
+    Ctx &c = g_ctx;
+    const HostMatrix &m = prof->matrix;
+    if (m.type != PARASAIL_MATRIX_TYPE_SQUARE) return false;
+    std::lock_guard<std::mutex> lk(prof->mu);
+    if (dp->sw16.prof && dp->sw16.open_baked == open) return sw16_supported(dp->sw16, open, gap);
+    Sw16Profile np_;
+    std::vector<int8_t> host;
+    if (!sw16_build_profile(dp->mapped.data(), (int)dp->mapped.size(), m.table.data(), m.size, open, &np_, &host)) return false;
+    if (!sw16_supported(np_, open, gap)) return false;
+    if (dp->sw16.prof) { cudaStreamSynchronize(c.stream); cudaFree(dp->sw16.prof); dp->sw16.prof = nullptr; }
+    if (cudaMalloc(&np_.prof, host.size()) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaMemcpyAsync(np_.prof, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return false;
+    cudaStreamSynchronize(c.stream);  // `host` goes out of scope
+    dp->sw16 = np_;
+    return true;
+}
+
+template <int K> static const void *sw16_fn_k() { return (const void *)sw16_scan_kernel<K>; }
+static const void *sw16_fn(int K) {
+    switch (K) {
+        case 2: return sw16_fn_k<2>();
+        case 4: return sw16_fn_k<4>();
+        case 6: return sw16_fn_k<6>();
+        case 8: return sw16_fn_k<8>();
+        case 10: return sw16_fn_k<10>();
+        case 12: return sw16_fn_k<12>();
+        case 13: return sw16_fn_k<13>();
+        case 14: return sw16_fn_k<14>();
+        case 16: return sw16_fn_k<16>();
+    }
+    return nullptr;
+}
+
+static constexpr int kSw16WarpsPerBlock = 8;
+
+// packed 16-bit local scan of the whole database; subjects that leave the 16-bit range (and
+// subjects too long for 16-bit column indices) are re-run by the 32-bit kernel
+static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, int open, int gap, psb_db *db,
+                     int *const d_out[6], int64_t *n_retried) {
+    Ctx &c = g_ctx;
+    const Sw16Profile &sp = dp->sw16;
+    // sorted by length descending: the first `nlong` subjects exceed the 16-bit column range
+    int64_t nlong = 0;
+    while (nlong < db->n && db->len_sorted[nlong] > 65535) ++nlong;
+    DevMem d_retry, d_cnt;
+    PSB_TRY(d_retry.alloc(((size_t)db->n + 2) * sizeof(int), c.stream));
+    PSB_TRY(d_cnt.alloc(2 * sizeof(int), c.stream));
+    PSB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(int), c.stream));
+    if (nlong > 0) {
+        std::vector<int> ids(nlong);
+        std::iota(ids.begin(), ids.end(), 0);
+        PSB_CUDA(cudaMemcpyAsync(d_retry.p, ids.data(), (size_t)nlong * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        const int nl = (int)nlong;
+        PSB_CUDA(cudaMemcpyAsync(d_cnt.as<int>(), &nl, sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        PSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    const int64_t nshort = db->n - nlong;
+    if (nshort > 0) {
+        Sw16Params p;
+        std::memset(&p, 0, sizeof(p));
+        p.prof = sp.prof; p.nletters = sp.nletters; p.lq = sp.lq; p.open = open; p.gap = gap; p.max_score = sp.max_score;
+        p.words = db->d_words; p.word_off = db->d_word_off + nlong; p.len = db->d_len + nlong; p.bits = db->bits;
+        p.n = nshort; p.out_map = db->d_perm + nlong;
+        p.score = d_out[0]; p.end_query = d_out[1]; p.end_ref = d_out[2];
+        p.retry = d_retry.as<int>(); p.retry_count = d_cnt.as<int>(); p.sid_base = (int)nlong;
+        p.counter = d_cnt.as<int>() + 1; p.mul_one = 1u; p.mul_16 = 16u;
+        const void *fn = sw16_fn(sp.K);
+        if (!fn) { set_error("sw16: no kernel for this query length"); return PSB_EUNSUPPORTED; }
+        const size_t smem = sw16_smem_bytes(sp.nletters, kSw16WarpsPerBlock);
+        if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSw16WarpsPerBlock * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        const long long items = (nshort + 1) / 2;
+        long long blocks = std::min<long long>((items + kSw16WarpsPerBlock - 1) / kSw16WarpsPerBlock, (long long)c.sms * per_sm);
+        if (blocks < 1) blocks = 1;
+        void *args[] = {&p};
+        PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kSw16WarpsPerBlock * 32), args, smem, c.stream));
+        c.launches++;
+    }
+    int nretry = 0;
+    PSB_CUDA(cudaMemcpyAsync(&nretry, d_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PSB_CUDA(cudaStreamSynchronize(c.stream));
+    *n_retried = nretry;
+    if (nretry > 0) PSB_TRY(scan_general(cfg, prof, dp, open, gap, db, d_retry.as<int>(), nretry, d_out));
+    return PSB_OK;
+}
+
+}  // namespace psb
+
+using namespace psb;
+
+extern "C" {
+
+int psb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int psb_set_device(int device) {
+    Ctx &c = g_ctx;
+    if (c.ready && c.device != device) {
+        // a host thread is bound to one device for its lifetime (one process per GPU is the model)
+        set_error("psb_set_device: this thread is already bound to another device");
+        return PSB_EINVAL;
+    }
+    c.device = device;
+    return ensure_ctx();
+}
+
+int psb_set_stream(void *cuda_stream) {
+    PSB_TRY(ensure_ctx());
+    g_ctx.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.own_stream;
+    return PSB_OK;
+}
+
+int psb_synchronize(void) {
+    PSB_TRY(ensure_ctx());
+    PSB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return PSB_OK;
+}
+
+double psb_last_kernel_ms(void) { return g_ctx.last_ms; }
+int psb_last_launches(void) { return g_ctx.launches; }
+
+void psb_batch_free(psb_batch_t *batch) { free_batch(batch); }
+
+int psb_align_pairs(const char *fn_name, const parasail_matrix_t *matrix, int open, int gap, const uint8_t *q_cat,
+                    const int64_t *q_off, const uint8_t *r_cat, const int64_t *r_off, int64_t n, psb_batch_t **out) {
+    FnConfig cfg;
+    if (!parse_fn_name(fn_name, &cfg) || cfg.profile) { set_error(std::string("psb_align_pairs: unknown function name: ") + (fn_name ? fn_name : "(null)")); return PSB_EINVAL; }
+    if (!matrix) { set_error("psb_align_pairs: NULL matrix"); return PSB_EINVAL; }
+    HostMatrix hm(matrix);
+    PairsRequest req;
+    req.cfg = cfg; req.matrix = &hm; req.open = open; req.gap = gap;
+    req.q_cat = q_cat; req.q_off = q_off; req.r_cat = r_cat; req.r_off = r_off; req.n = n;
+    const int rc = run_pairs(req, out);
+    if (rc == PSB_OK && (cfg.width == 8 || cfg.width == 16)) {
+        // explicit narrow widths: flag pairs whose optimum does not fit
+        psb_batch_t *b = *out;
+        const long long hi = cfg.width == 8 ? 127 : 32767;
+        for (int64_t i = 0; i < n; ++i)
+            if ((long long)b->score[i] + std::max(hm.max, 0) > hi || (long long)b->score[i] + std::min(hm.min, 0) < -hi - 1) {
+                b->saturated[i] = 1; b->score[i] = 0; b->end_query[i] = 0; b->end_ref[i] = 0;
+            }
+    }
+    return rc;
+}
+
+psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const parasail_matrix_t *matrix) {
+    if (!cat || !off || n <= 0 || !matrix) { set_error("psb_db_create: NULL argument or empty database"); return nullptr; }
+    if (n > 0x7fffffff) { set_error("psb_db_create: more than 2^31-1 subjects"); return nullptr; }
+    if (ensure_ctx() != PSB_OK) return nullptr;
+    Ctx &c = g_ctx;
+    HostMatrix hm(matrix);
+    psb_db *db = new psb_db();
+    db->device = c.device; db->n = n; db->msize = hm.size;
+    std::memcpy(db->mapper, hm.mapper, 256);
+    db->bits = hm.size <= 4 ? 2 : 5;
+    if (hm.size > 32) { set_error("psb_db_create: alphabets above 32 letters cannot be 5-bit packed"); delete db; return nullptr; }
+    const int rpw = db->bits == 2 ? 16 : 6;
+    db->perm.resize(n);
+    std::iota(db->perm.begin(), db->perm.end(), 0);
+    for (int64_t i = 0; i < n; ++i)
+        if (off[i + 1] <= off[i]) { set_error("psb_db_create: empty subject " + std::to_string(i)); delete db; return nullptr; }
+    {
+        // stable order by decreasing length: counting sort when the lengths are small integers
+        int64_t maxlen = 0;
+        for (int64_t i = 0; i < n; ++i) maxlen = std::max<int64_t>(maxlen, off[i + 1] - off[i]);
+        if (maxlen < (1 << 22)) {
+            std::vector<int64_t> start((size_t)maxlen + 2, 0);
+            for (int64_t i = 0; i < n; ++i) start[(size_t)(maxlen - (off[i + 1] - off[i])) + 1]++;
+            for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
+            for (int64_t i = 0; i < n; ++i) db->perm[(size_t)start[(size_t)(maxlen - (off[i + 1] - off[i]))]++] = (int)i;
+        } else {
+            std::stable_sort(db->perm.begin(), db->perm.end(), [&](int a, int b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
+        }
+    }
+    db->len_sorted.resize(n);
+    std::vector<long long> word_off(n + 1);
+    word_off[0] = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int len = (int)(off[db->perm[i] + 1] - off[db->perm[i]]);
+        db->len_sorted[i] = len;
+        word_off[i + 1] = word_off[i] + (len + rpw - 1) / rpw;
+    }
+    db->residues = off[n] - off[0];
+    db->words = word_off[n];
+    auto fail = [&](const char *what, cudaError_t e) {
+        set_error(std::string(what) + ": " + cudaGetErrorString(e));
+        psb_db_free(db);
+        return (psb_db_t *)nullptr;
+    };
+    cudaError_t e;
+    // staging copies of the raw residues and offsets are stream-ordered temporaries
+    DevMem d_raw, d_rawoff;
+    if (d_raw.alloc((size_t)db->residues, c.stream) != PSB_OK || d_rawoff.alloc(((size_t)n + 1) * sizeof(long long), c.stream) != PSB_OK) { psb_db_free(db); return nullptr; }
+    std::vector<long long> off_rel(n + 1);
+    for (int64_t i = 0; i <= n; ++i) off_rel[i] = off[i] - off[0];
+    if ((e = cudaMalloc(&db->d_words, std::max<size_t>((size_t)db->words * 4 + 64, 64))) != cudaSuccess) return fail("cudaMalloc(db words)", e);
+    if ((e = cudaMalloc(&db->d_word_off, word_off.size() * sizeof(long long))) != cudaSuccess) return fail("cudaMalloc(db offsets)", e);
+    if ((e = cudaMalloc(&db->d_perm, (size_t)n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc(db perm)", e);
+    if ((e = cudaMalloc(&db->d_len, (size_t)n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc(db lengths)", e);
+    cudaMemcpyAsync(db->d_len, db->len_sorted.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(d_raw.p, cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(d_rawoff.p, off_rel.data(), off_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(db->d_word_off, word_off.data(), word_off.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream);
+    cudaMemcpyAsync(db->d_perm, db->perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c.stream);
+    PackParams pp;
+    pp.raw = d_raw.as<uint8_t>(); pp.raw_off = d_rawoff.as<long long>(); pp.perm = db->d_perm;
+    pp.word_off = db->d_word_off; pp.words = db->d_words; pp.n = n; pp.bits = db->bits;
+    fill_lut(pp.lut, hm.mapper);
+    pack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(pp);
+    if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return fail("database packing", e);
+    return db;
+}
+
+int64_t psb_db_count(const psb_db_t *db) { return db ? db->n : 0; }
+int64_t psb_db_residues(const psb_db_t *db) { return db ? db->residues : 0; }
+int64_t psb_db_device_bytes(const psb_db_t *db) {
+    return db ? db->words * 4 + (db->n + 1) * 8 + db->n * 8 : 0;
+}
+
+void psb_db_free(psb_db_t *db) {
+    if (!db) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(db->device);
+    cudaFree(db->d_words); cudaFree(db->d_word_off); cudaFree(db->d_perm); cudaFree(db->d_len); cudaFree(db->d_bytes); cudaFree(db->d_byte_off);
+    cudaSetDevice(cur);
+    delete db;
+}
+
+int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const psb_db_t *db_c, psb_batch_t **out) {
+    if (out) *out = nullptr;
+    FnConfig cfg;
+    if (!parse_fn_name(fn_name, &cfg) || !cfg.profile) { set_error(std::string("psb_scan: not a profile function name: ") + (fn_name ? fn_name : "(null)")); return PSB_EINVAL; }
+    if (!profile || !db_c || !out) { set_error("psb_scan: NULL argument"); return PSB_EINVAL; }
+    if (cfg.trace || cfg.table || cfg.rowcol) { set_error("psb_scan: trace/table/rowcol outputs are not available for database scans"); return PSB_EUNSUPPORTED; }
+    psb_db *db = const_cast<psb_db *>(db_c);
+    PSB_TRY(ensure_ctx());
+    Ctx &c = g_ctx;
+    if (db->device != c.device) { set_error("psb_scan: database lives on another device"); return PSB_EINVAL; }
+    if (profile->matrix.size != db->msize || std::memcmp(profile->matrix.mapper, db->mapper, 256) != 0) {
+        set_error("psb_scan: profile and database were built with different alphabets");
+        return PSB_EINVAL;
+    }
+    c.last_ms = 0.0; c.launches = 0;
+    DevProfile *dp = nullptr;
+    PSB_TRY(get_dev_profile(profile, &dp));
+    psb_batch_t *b = new_batch(db->n, cfg);
+    if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
+    const int lq = (int)profile->query.size();
+    for (int64_t i = 0; i < db->n; ++i) b->cells += (double)lq * db->len_sorted[i];
+    DevMem d_out[6];
+    int *outp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const int nout = cfg.stats ? 6 : 3;
+    int rc = PSB_OK;
+    for (int k = 0; k < nout && rc == PSB_OK; ++k) { rc = d_out[k].alloc((size_t)db->n * sizeof(int), c.stream); outp[k] = d_out[k].as<int>(); }
+    if (rc == PSB_OK) rc = cudaEventRecord(c.ev0, c.stream) == cudaSuccess ? PSB_OK : PSB_ECUDA;
+    if (rc == PSB_OK) {
+        const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 &&
+                          sw16_prepare(profile, dp, open, gap);
+        if (fast) {
+            int64_t retried = 0;
+            rc = scan_sw16(cfg, profile, dp, open, gap, db, outp, &retried);
+            b->n_retried = retried;
+        } else {
+            rc = scan_general(cfg, profile, dp, open, gap, db, nullptr, 0, outp);
+        }
+    }
+    if (rc == PSB_OK && cudaEventRecord(c.ev1, c.stream) != cudaSuccess) rc = PSB_ECUDA;
+    int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
+    for (int k = 0; k < nout && rc == PSB_OK; ++k)
+        if (cudaMemcpyAsync(hosts[k], d_out[k].p, (size_t)db->n * sizeof(int), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) rc = PSB_ECUDA;
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (rc == PSB_OK && e != cudaSuccess) { set_error(std::string("psb_scan: ") + cudaGetErrorString(e)); rc = PSB_ECUDA; }
+    if (rc != PSB_OK) { free_batch(b); return rc; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_ms = ms;
+    *out = b;
+    return PSB_OK;
+}
+
+int psb_batch_topk(const psb_batch_t *batch, int k, int64_t *idx_out, int *score_out) {
+    if (!batch || k <= 0 || !idx_out) { set_error("psb_batch_topk: bad argument"); return PSB_EINVAL; }
+    const int64_t n = batch->n;
+    std::vector<int64_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    const int64_t kk = std::min<int64_t>(k, n);
+    auto better = [&](int64_t a, int64_t b) { return batch->score[a] != batch->score[b] ? batch->score[a] > batch->score[b] : a < b; };
+    std::partial_sort(idx.begin(), idx.begin() + kk, idx.end(), better);
+    for (int64_t i = 0; i < kk; ++i) { idx_out[i] = idx[i]; if (score_out) score_out[i] = batch->score[idx[i]]; }
+    return (int)kk;
+}
+
+int psb_shard_plan(const int64_t *off, int64_t n, int n_shards, int *shard_of) {
+    if (!off || !shard_of || n <= 0 || n_shards <= 0) { set_error("psb_shard_plan: bad argument"); return PSB_EINVAL; }
+    // longest-processing-time first on residue counts: sort by length, give each subject to
+    // the currently lightest shard
+    std::vector<int64_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
+    std::vector<int64_t> load(n_shards, 0);
+    for (int64_t t = 0; t < n; ++t) {
+        const int64_t i = order[t];
+        int best = 0;
+        for (int s = 1; s < n_shards; ++s) if (load[s] < load[best]) best = s;
+        shard_of[i] = best;
+        load[best] += off[i + 1] - off[i];
+    }
+    return PSB_OK;
+}
+
+}  // extern "C"

@@ -21,16 +21,10 @@
 //     are merged once per pair with parasail's tie-break (score, then smaller end_ref,
 //     then smaller end_query; the last column only beats the last row when strictly better).
 #pragma once
+#include "psb_defs.h"
 #include "psb_simt.h"
 
 namespace psb {
-
-enum { MODE_NW = 0, MODE_SG = 1, MODE_SW = 2 };
-static constexpr int NEG_INF32 = -(1 << 30);
-static constexpr int PAD_SCORE = -(1 << 28);  // substitution score of rows beyond the query
-
-// TraceFlags bytes [REF src/alignment/table.rs:127-142]
-enum { TR_INS = 1, TR_DEL = 2, TR_DIAG = 4, TR_DIAG_E = 8, TR_INS_E = 16, TR_DIAG_F = 32, TR_DEL_F = 64 };
 
 struct Gotoh32Params {
     const uint8_t *q;           // residues already mapped to matrix column indices
@@ -52,6 +46,9 @@ struct Gotoh32Params {
     uint8_t *trace;             // TRACE only: per pair [strip][step][lane][K] bytes
     const long long *trace_off; // byte offset of each pair's trace block (indexed by pair id)
     int *counter;               // dynamic work queue
+    const int *out_map;         // results are written at out_map[pair id] (NULL: pair id)
+    int *tabH, *tabM, *tabS, *tabL;  // TABLE only: per-cell planes, same indexing as the trace
+    const long long *tab_off;   // element offset of each pair's table block (indexed by pair id)
 };
 
 // statistics word: matches | similar | length packed so that one add updates all three
@@ -71,7 +68,7 @@ inline size_t gotoh32_smem_bytes(int size, int warps, bool stats, int statw) {
     return ((m + 15) & ~(size_t)15) + (size_t)warps * ((ring + 15) & ~(size_t)15);
 }
 
-template <int K, bool STATS, bool TRACE, typename SW_>
+template <int K, bool STATS, bool TRACE, bool TABLE, typename SW_>
 PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
     typedef SW_ SWord;
     typedef StatPack<SWord> SP;
@@ -204,7 +201,7 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                         else So = ld_ro(p.matrix + rowbase[k] + letter) + o;
                         const int Tl = T[k];
                         int H, Fn, En;
-                        if (!STATS && !TRACE) {
+                        if (!STATS && !TRACE && !TABLE) {
                             En = viaddmax(E[k], -e, Tl);
                             Fn = viaddmax(Fu, -e, Tu);
                             const int h = viaddmax(Td, So, En);
@@ -232,6 +229,15 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                                 Hsd = Hs[k];   // becomes the diagonal of the row below
                                 Hs[k] = hs; Es[k] = es;
                                 Hsu = hs; Fsu = fs;
+                            }
+                            if (TABLE) {
+                                const size_t idx = (size_t)p.tab_off[pid] + (((size_t)strip * nsteps + s) * 32 + lane) * K + k;
+                                p.tabH[idx] = H;
+                                if (STATS) {
+                                    p.tabM[idx] = (int)(Hs[k] & SP::MM);
+                                    p.tabS[idx] = (int)((Hs[k] >> SP::SS) & SP::SM);
+                                    p.tabL[idx] = (int)((Hs[k] >> SP::LS) & SP::LM);
+                                }
                             }
                             if (TRACE) {
                                 unsigned t = (eopen ? TR_DIAG_E : TR_INS_E) | (fopen ? TR_DIAG_F : TR_DEL_F);
@@ -312,11 +318,12 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
         if (col_ends && (!row_ends || colH > bestH)) { bestH = colH; bestJ = Lr - 1; bestI = colI; bestS = colS; }
         if (lane == 0) {
             if (is_sw && bestH <= 0) { bestH = 0; bestJ = 0; bestI = 0; bestS = 0; }
-            p.score[pid] = bestH; p.end_query[pid] = bestI; p.end_ref[pid] = bestJ;
+            const int oid = p.out_map ? p.out_map[pid] : pid;
+            p.score[oid] = bestH; p.end_query[oid] = bestI; p.end_ref[oid] = bestJ;
             if (STATS) {
-                p.matches[pid] = (int)(bestS & SP::MM);
-                p.similar[pid] = (int)((bestS >> SP::SS) & SP::SM);
-                p.length[pid] = (int)((bestS >> SP::LS) & SP::LM);
+                p.matches[oid] = (int)(bestS & SP::MM);
+                p.similar[oid] = (int)((bestS >> SP::SS) & SP::SM);
+                p.length[oid] = (int)((bestS >> SP::LS) & SP::LM);
             }
         }
     }

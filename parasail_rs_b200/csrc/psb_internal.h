@@ -1,0 +1,92 @@
+// psb_internal.h -- declarations shared by the host side of libparasail_b200.so.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/parasail_b200.h"
+
+namespace psb {
+
+// ---- function-name grammar [REF src/aligner/mod.rs:289-331] --------------------------------
+struct FnConfig {
+    int mode = 0;  // 0 nw, 1 sg, 2 sw (kern_gotoh32.cuh MODE_*)
+    int s1_beg = 0, s1_end = 0, s2_beg = 0, s2_end = 0;
+    bool trace = false, stats = false, table = false, rowcol = false;
+    int strategy = 0;  // 0 striped, 1 scan, 2 diag: echoed in the result flags only
+    bool profile = false;
+    int width = 0;  // 8, 16, 32, 64, or 0 for "sat"
+    int flag() const;
+};
+// true iff `name` (with or without "parasail_") is a function upstream parasail defines
+bool parse_fn_name(const char *name, FnConfig *cfg);
+int encode_fn(const FnConfig &c);       // dense id for the thunk tables
+FnConfig decode_fn(int id);
+int fn_id_count();
+
+void set_error(const std::string &msg);
+
+// ---- matrices ------------------------------------------------------------------------------
+// value-type snapshot of a parasail_matrix_t, safe to keep after the caller frees the original
+struct HostMatrix {
+    std::vector<int> table;   // length x size
+    uint8_t mapper[256];
+    int size = 0, length = 0, type = 0, max = 0, min = 0;
+    std::vector<uint8_t> query;  // pssm: the query it was converted from (may be empty)
+    explicit HostMatrix(const parasail_matrix_t *m);
+    HostMatrix() = default;
+};
+
+// ---- results -------------------------------------------------------------------------------
+}  // namespace psb
+
+struct psb_result_extra {
+    int matches = 0, similar = 0, length = 0;
+    int qlen = 0, rlen = 0;
+    std::vector<int> score_table, matches_table, similar_table, length_table;
+    std::vector<int> score_row, matches_row, similar_row, length_row;
+    std::vector<int> score_col, matches_col, similar_col, length_col;
+    std::vector<int8_t> trace;  // row-major TraceFlags bytes (qlen x rlen)
+};
+
+struct parasail_profile {
+    std::vector<uint8_t> query;  // raw residues (deep copy)
+    psb::HostMatrix matrix;      // deep copy
+    bool stats = false;
+    int width = 0;
+    // device-resident state, created on first use per device and then immutable
+    mutable std::mutex mu;
+    mutable std::map<int, void *> resident;
+};
+
+namespace psb {
+
+// ---- engine (engine.cu) --------------------------------------------------------------------
+struct PairsRequest {
+    FnConfig cfg;
+    const HostMatrix *matrix = nullptr;
+    int open = 0, gap = 0;
+    const uint8_t *q_cat = nullptr;
+    const int64_t *q_off = nullptr;   // n+1 entries; shared_query: 2 entries
+    bool shared_query = false;
+    const uint8_t *r_cat = nullptr;
+    const int64_t *r_off = nullptr;
+    int64_t n = 0;
+    // single-pair API extras (n == 1): full tables / last row+col / row-major trace bytes
+    psb_result_extra *extra = nullptr;
+};
+int run_pairs(const PairsRequest &req, psb_batch_t **out);
+void free_batch(psb_batch_t *b);
+void release_profile_resident(parasail_profile *p);
+
+// one pair through the batch path, wrapped as a parasail_result_t (never NULL)
+parasail_result_t *align_one(const FnConfig &cfg, const HostMatrix &m, const uint8_t *q, int qlen, const uint8_t *r,
+                             int rlen, int open, int gap);
+
+// host-side trace walk shared by parasail_result_get_cigar / get_traceback (result.cpp)
+int walk_cigar(const int8_t *trace, const uint8_t *q, const uint8_t *r, int rlen, const uint8_t *mapper,
+               int end_query, int end_ref, std::vector<uint32_t> *ops, int *beg_query, int *beg_ref);
+
+}  // namespace psb

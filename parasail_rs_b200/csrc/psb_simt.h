@@ -24,16 +24,9 @@ PSB_DEV int thread_in_block() { return (int)threadIdx.x; }
 PSB_DEV int threads_per_block() { return (int)blockDim.x; }
 PSB_DEV void sync_warp() { __syncwarp(); }
 PSB_DEV void sync_block() { __syncthreads(); }
-PSB_DEV int shfl_up(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-PSB_DEV unsigned shfl_up(unsigned v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-PSB_DEV unsigned long long shfl_up(unsigned long long v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-PSB_DEV int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-PSB_DEV unsigned shfl(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-PSB_DEV long long shfl(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-PSB_DEV unsigned long long shfl(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-PSB_DEV int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-PSB_DEV unsigned shfl_xor(unsigned v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-PSB_DEV long long shfl_xor(long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <typename T> PSB_DEV T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+template <typename T> PSB_DEV T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <typename T> PSB_DEV T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 PSB_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 PSB_DEV unsigned long long atomic_add(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 PSB_DEV int atomic_add(int *p, int v) { return atomicAdd(p, v); }
@@ -68,6 +61,7 @@ PSB_DEV unsigned prmt(unsigned a, unsigned b, unsigned sel) {
 #define PSB_KERNEL
 #define PSB_SHARED_DECL(name) unsigned char *name = psb::emu::tls().smem
 
+struct uint4 { unsigned x, y, z, w; };
 namespace psb {
 namespace emu {
 struct Block {

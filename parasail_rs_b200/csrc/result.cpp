@@ -1,0 +1,304 @@
+// result.cpp -- parasail_result_t and its getters, CIGAR and traceback strings, as used by
+// parasail-rs's Alignment [REF src/alignment/mod.rs:54-504].  Single-pair results are n = 1
+// batches of the GPU path (engine.cu); this file only reads what the device produced.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "psb_internal.h"
+
+namespace psb {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+
+// an explicit 8/16-bit request whose true optimum does not fit that width is
+// reported saturated (score/ends zeroed); "sat" and 32/64 return the exact result.
+static bool saturates(const FnConfig &cfg, const HostMatrix &m, int score, int qlen, int rlen, int open, int gap) {
+    if (cfg.width != 8 && cfg.width != 16) return false;
+    const long long hi = cfg.width == 8 ? 127 : 32767, lo = -hi - 1;
+    if ((long long)score + std::max(m.max, 0) > hi) return true;
+    if (cfg.mode != 2) {
+        // global-style boundaries reach -(open + (L-1)*gap) along the first row/column
+        long long worst = -(long long)open - (long long)(std::max(qlen, rlen) - 1) * gap + std::min(m.min, 0);
+        bool bounded_rows = cfg.mode == 0 || !cfg.s1_beg || !cfg.s2_beg;
+        if (bounded_rows && worst < lo) return true;
+        if ((long long)score + std::min(m.min, 0) < lo) return true;
+    }
+    return false;
+}
+
+parasail_result_t *align_one(const FnConfig &cfg, const HostMatrix &m, const uint8_t *q, int qlen, const uint8_t *r,
+                             int rlen, int open, int gap) {
+    parasail_result_t *res = (parasail_result_t *)std::calloc(1, sizeof(parasail_result_t));
+    if (!res) std::abort();
+    res->extra = new psb_result_extra();
+    res->flag = cfg.flag();
+    if (cfg.width == 0) res->flag |= PARASAIL_FLAG_BITS_32;
+    if (m.type == PARASAIL_MATRIX_TYPE_PSSM) qlen = m.length;
+    res->extra->qlen = qlen; res->extra->rlen = rlen;
+    if (m.size == 0 || !r || rlen <= 0 || qlen <= 0 || (m.type != PARASAIL_MATRIX_TYPE_PSSM && !q)) {
+        if (g_error.empty()) set_error("alignment called with an empty sequence");
+        res->flag |= PARASAIL_FLAG_SATURATED;
+        return res;
+    }
+    int64_t qoff[2] = {0, qlen}, roff[2] = {0, rlen};
+    std::vector<uint8_t> fake_q;
+    if (!q) { fake_q.assign((size_t)qlen, 0); q = fake_q.data(); }
+    PairsRequest req;
+    req.cfg = cfg; req.matrix = &m; req.open = open; req.gap = gap;
+    req.q_cat = q; req.q_off = qoff; req.r_cat = r; req.r_off = roff; req.n = 1;
+    req.extra = res->extra;
+    psb_batch_t *b = nullptr;
+    const int rc = run_pairs(req, &b);
+    if (rc != PSB_OK || !b) {
+        // no CPU fallback: the failure is visible as a saturated, zeroed result + psb_last_error()
+        res->flag |= PARASAIL_FLAG_SATURATED;
+        std::fprintf(stderr, "libparasail_b200: alignment failed: %s\n", psb_last_error());
+        if (b) free_batch(b);
+        return res;
+    }
+    res->score = b->score[0]; res->end_query = b->end_query[0]; res->end_ref = b->end_ref[0];
+    if (cfg.stats) { res->extra->matches = b->matches[0]; res->extra->similar = b->similar[0]; res->extra->length = b->length[0]; }
+    free_batch(b);
+    if (saturates(cfg, m, res->score, qlen, rlen, open, gap)) {
+        res->flag |= PARASAIL_FLAG_SATURATED;
+        res->score = 0; res->end_query = 0; res->end_ref = 0;
+    }
+    return res;
+}
+
+// SURVEY A.7 / upstream src/cigar.c: walk the row-major trace bytes from the end cell
+int walk_cigar(const int8_t *trace, const uint8_t *q, const uint8_t *r, int rlen, const uint8_t *mapper,
+               int end_query, int end_ref, std::vector<uint32_t> *ops, int *beg_query, int *beg_ref) {
+    long long i = end_query, j = end_ref;
+    int where = 4;  // DIAG
+    std::vector<uint32_t> rev;
+    int cur = -1;
+    uint32_t len = 0;
+    auto emit = [&](int op) {
+        if (cur == op) { ++len; return; }
+        if (cur >= 0) rev.push_back((len << 4) | (uint32_t)cur);
+        cur = op; len = 1;
+    };
+    while (i >= 0 || j >= 0) {
+        if (i < 0) { emit(2); --j; continue; }
+        if (j < 0) { emit(1); --i; continue; }
+        const int t = trace[(size_t)i * (size_t)rlen + (size_t)j];
+        if (where == 4) {
+            if (t & 4) { emit(mapper[q[i]] == mapper[r[j]] ? 7 : 8); --i; --j; }
+            else if (t & 1) where = 1;
+            else if (t & 2) where = 2;
+            else break;
+        } else if (where == 1) { emit(2); where = (t & 8) ? 4 : 1; --j; }
+        else { emit(1); where = (t & 32) ? 4 : 2; --i; }
+    }
+    if (cur >= 0) rev.push_back((len << 4) | (uint32_t)cur);
+    ops->assign(rev.rbegin(), rev.rend());
+    *beg_query = (int)(i + 1); *beg_ref = (int)(j + 1);
+    return (int)ops->size();
+}
+
+}  // namespace psb
+
+extern "C" {
+
+const char *psb_last_error(void) { return psb::g_error.c_str(); }
+const char *psb_version(void) { return "parasail_b200 0.1 (sm_100a)"; }
+
+void parasail_result_free(parasail_result_t *result) {
+    if (!result) return;
+    delete result->extra;
+    result->extra = nullptr;
+    std::free(result);
+}
+
+int parasail_result_get_score(const parasail_result_t *r) { return r->score; }
+int parasail_result_get_end_query(const parasail_result_t *r) { return r->end_query; }
+int parasail_result_get_end_ref(const parasail_result_t *r) { return r->end_ref; }
+int parasail_result_get_matches(const parasail_result_t *r) { return r->extra ? r->extra->matches : 0; }
+int parasail_result_get_similar(const parasail_result_t *r) { return r->extra ? r->extra->similar : 0; }
+int parasail_result_get_length(const parasail_result_t *r) { return r->extra ? r->extra->length : 0; }
+
+#define PSB_ARRAY_GETTER(NAME)                                                   \
+    int *parasail_result_get_##NAME(const parasail_result_t *r) {                \
+        return (r->extra && !r->extra->NAME.empty()) ? r->extra->NAME.data() : nullptr; \
+    }
+PSB_ARRAY_GETTER(score_table) PSB_ARRAY_GETTER(matches_table) PSB_ARRAY_GETTER(similar_table) PSB_ARRAY_GETTER(length_table)
+PSB_ARRAY_GETTER(score_row) PSB_ARRAY_GETTER(matches_row) PSB_ARRAY_GETTER(similar_row) PSB_ARRAY_GETTER(length_row)
+PSB_ARRAY_GETTER(score_col) PSB_ARRAY_GETTER(matches_col) PSB_ARRAY_GETTER(similar_col) PSB_ARRAY_GETTER(length_col)
+#undef PSB_ARRAY_GETTER
+
+// row-major int8 TraceFlags, the layout parasail-rs's TracebackTable reads [REF src/alignment/mod.rs:291-303]
+int *parasail_result_get_trace_table(const parasail_result_t *r) {
+    return (r->extra && !r->extra->trace.empty()) ? (int *)r->extra->trace.data() : nullptr;
+}
+
+int parasail_result_is_nw(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_NW) != 0; }
+int parasail_result_is_sg(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_SG) != 0; }
+int parasail_result_is_sw(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_SW) != 0; }
+int parasail_result_is_saturated(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_SATURATED) != 0; }
+int parasail_result_is_banded(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_BANDED) != 0; }
+int parasail_result_is_scan(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_SCAN) != 0; }
+int parasail_result_is_striped(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_STRIPED) != 0; }
+int parasail_result_is_diag(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_DIAG) != 0; }
+int parasail_result_is_blocked(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_BLOCKED) != 0; }
+int parasail_result_is_stats(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_STATS) != 0; }
+int parasail_result_is_table(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_TABLE) != 0; }
+int parasail_result_is_rowcol(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_ROWCOL) != 0; }
+int parasail_result_is_trace(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_TRACE) != 0; }
+int parasail_result_is_stats_table(const parasail_result_t *r) {
+    return (r->flag & PARASAIL_FLAG_STATS) && (r->flag & PARASAIL_FLAG_TABLE);
+}
+int parasail_result_is_stats_rowcol(const parasail_result_t *r) {
+    return (r->flag & PARASAIL_FLAG_STATS) && (r->flag & PARASAIL_FLAG_ROWCOL);
+}
+
+// [REF src/alignment/mod.rs:400-407]
+parasail_cigar_t *parasail_result_get_cigar(parasail_result_t *result, const char *seqA, int lena, const char *seqB,
+                                            int lenb, const parasail_matrix_t *matrix) {
+    if (!result || !result->extra || result->extra->trace.empty() || !seqA || !seqB || !matrix) {
+        psb::set_error("parasail_result_get_cigar: result has no trace");
+        return nullptr;
+    }
+    if (lena != result->extra->qlen || lenb != result->extra->rlen) {
+        psb::set_error("parasail_result_get_cigar: sequence lengths differ from the aligned pair");
+        return nullptr;
+    }
+    psb::HostMatrix hm(matrix);
+    std::vector<uint32_t> ops;
+    int bq = 0, br = 0;
+    psb::walk_cigar(result->extra->trace.data(), (const uint8_t *)seqA, (const uint8_t *)seqB, lenb, hm.mapper,
+                    result->end_query, result->end_ref, &ops, &bq, &br);
+    parasail_cigar_t *c = (parasail_cigar_t *)std::calloc(1, sizeof(parasail_cigar_t));
+    c->seq = (uint32_t *)std::malloc(sizeof(uint32_t) * std::max<size_t>(ops.size(), 1));
+    std::memcpy(c->seq, ops.data(), sizeof(uint32_t) * ops.size());
+    c->len = (int)ops.size();
+    c->beg_query = bq; c->beg_ref = br;
+    return c;
+}
+
+// [REF src/alignment/mod.rs:410] malloc'd: parasail-rs adopts it with CString::from_raw
+char *parasail_cigar_decode(parasail_cigar_t *cigar) {
+    static const char tab[] = "MIDNSHP=X";
+    if (!cigar) return nullptr;
+    std::string s;
+    for (int k = 0; k < cigar->len; ++k) {
+        const uint32_t op = cigar->seq[k] & 0xf;
+        s += std::to_string(cigar->seq[k] >> 4);
+        s.push_back(op > 8 ? 'M' : tab[op]);
+    }
+    char *out = (char *)std::malloc(s.size() + 1);
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return out;
+}
+
+void parasail_cigar_free(parasail_cigar_t *cigar) {
+    if (!cigar) return;
+    std::free(cigar->seq);
+    std::free(cigar);
+}
+
+// [REF src/alignment/mod.rs:356-366] three malloc'd strings, adopted by the Rust side
+parasail_traceback_t *parasail_result_get_traceback(parasail_result_t *result, const char *seqA, int lena,
+                                                    const char *seqB, int lenb, const parasail_matrix_t *matrix,
+                                                    char match, char pos, char neg) {
+    if (!result || !result->extra || result->extra->trace.empty() || !seqA || !seqB || !matrix) {
+        psb::set_error("parasail_result_get_traceback: result has no trace");
+        return nullptr;
+    }
+    if (lena != result->extra->qlen || lenb != result->extra->rlen) return nullptr;
+    psb::HostMatrix hm(matrix);
+    const int8_t *tr = result->extra->trace.data();
+    std::string qs, cs, rs;
+    long long i = result->end_query, j = result->end_ref;
+    int where = 4;
+    while (i >= 0 || j >= 0) {
+        if (i < 0) { qs.push_back('-'); rs.push_back(seqB[j]); cs.push_back(' '); --j; continue; }
+        if (j < 0) { qs.push_back(seqA[i]); rs.push_back('-'); cs.push_back(' '); --i; continue; }
+        const int t = tr[(size_t)i * lenb + j];
+        if (where == 4) {
+            if (t & 4) {
+                const int a = hm.mapper[(uint8_t)seqA[i]], b = hm.mapper[(uint8_t)seqB[j]];
+                const int sub = hm.table[(size_t)hm.size * (hm.type == PARASAIL_MATRIX_TYPE_PSSM ? (int)i : a) + b];
+                qs.push_back(seqA[i]); rs.push_back(seqB[j]);
+                cs.push_back(a == b ? match : (sub > 0 ? pos : neg));
+                --i; --j;
+            } else if (t & 1) where = 1;
+            else if (t & 2) where = 2;
+            else break;
+        } else if (where == 1) { qs.push_back('-'); rs.push_back(seqB[j]); cs.push_back(' '); where = (t & 8) ? 4 : 1; --j; }
+        else { qs.push_back(seqA[i]); rs.push_back('-'); cs.push_back(' '); where = (t & 32) ? 4 : 2; --i; }
+    }
+    std::reverse(qs.begin(), qs.end()); std::reverse(cs.begin(), cs.end()); std::reverse(rs.begin(), rs.end());
+    auto dup = [](const std::string &s) { char *p = (char *)std::malloc(s.size() + 1); std::memcpy(p, s.c_str(), s.size() + 1); return p; };
+    parasail_traceback_t *tb = (parasail_traceback_t *)std::calloc(1, sizeof(parasail_traceback_t));
+    tb->query = dup(qs); tb->comp = dup(cs); tb->ref = dup(rs);
+    return tb;
+}
+
+void parasail_traceback_free(parasail_traceback_t *tb) {
+    if (!tb) return;
+    std::free(tb->query); std::free(tb->comp); std::free(tb->ref);
+    std::free(tb);
+}
+
+// [REF src/alignment/mod.rs:324-339] prints the alignment in blocks of `width` columns
+void parasail_traceback_generic(const char *seqA, int lena, const char *seqB, int lenb, const char *nameA,
+                                const char *nameB, const parasail_matrix_t *matrix, parasail_result_t *result,
+                                char match, char pos, char neg, int width, int name_width, int use_stats) {
+    parasail_traceback_t *tb = parasail_result_get_traceback(result, seqA, lena, seqB, lenb, matrix, match, pos, neg);
+    if (!tb) return;
+    parasail_cigar_t *cig = parasail_result_get_cigar(result, seqA, lena, seqB, lenb, matrix);
+    const int n = (int)std::strlen(tb->query);
+    int qi = cig ? cig->beg_query : 0, ri = cig ? cig->beg_ref : 0;
+    int matches = 0, gaps = 0;
+    if (width <= 0) width = 80;
+    for (int a = 0; a < n; a += width) {
+        const int b = std::min(n, a + width);
+        int qn = 0, rn = 0;
+        for (int k = a; k < b; ++k) { qn += tb->query[k] != '-'; rn += tb->ref[k] != '-'; }
+        std::printf("\n%*.*s %8d %.*s %8d\n", name_width, name_width, nameB ? nameB : "", ri + (rn ? 1 : 0), b - a, tb->ref + a, ri + rn);
+        std::printf("%*s %8s %.*s\n", name_width, "", "", b - a, tb->comp + a);
+        std::printf("%*.*s %8d %.*s %8d\n", name_width, name_width, nameA ? nameA : "", qi + (qn ? 1 : 0), b - a, tb->query + a, qi + qn);
+        qi += qn; ri += rn;
+    }
+    for (int k = 0; k < n; ++k) { matches += tb->comp[k] == match && tb->query[k] != '-' && tb->ref[k] != '-'; gaps += tb->query[k] == '-' || tb->ref[k] == '-'; }
+    if (use_stats) {
+        std::printf("\nLength: %d\nIdentity: %d/%d\nGaps: %d/%d\nScore: %d\n", n, matches, n, gaps, n, result->score);
+    }
+    parasail_cigar_free(cig);
+    parasail_traceback_free(tb);
+}
+
+// ---- side APIs outside the accelerated path ----------------------------
+parasail_result_t *parasail_nw_banded(const char *s1, int s1Len, const char *s2, int s2Len, int open, int gap, int k,
+                                      const parasail_matrix_t *matrix) {
+    (void)k;  // the band only prunes work upstream; the full fill is its k = max(len) limit
+    psb::FnConfig cfg;
+    cfg.mode = 0; cfg.width = 32; cfg.strategy = 0;
+    psb::HostMatrix hm;
+    if (matrix) hm = psb::HostMatrix(matrix);
+    parasail_result_t *r = psb::align_one(cfg, hm, (const uint8_t *)s1, s1Len, (const uint8_t *)s2, s2Len, open, gap);
+    r->flag &= ~PARASAIL_FLAG_STRIPED;
+    r->flag |= PARASAIL_FLAG_BANDED | PARASAIL_FLAG_NOVEC;
+    return r;
+}
+
+parasail_result_ssw_t *parasail_ssw(const char *, int, const char *, int, int, int, const parasail_matrix_t *) {
+    psb::set_error("parasail_ssw: the SSW emulation is outside the accelerated path (not implemented)");
+    return nullptr;
+}
+parasail_profile_t *parasail_ssw_init(const char *, int, const parasail_matrix_t *, int8_t) {
+    psb::set_error("parasail_ssw_init: the SSW emulation is outside the accelerated path (not implemented)");
+    return nullptr;
+}
+void parasail_result_ssw_free(parasail_result_ssw_t *r) {
+    if (!r) return;
+    std::free(r->cigar);
+    std::free(r);
+}
+
+}  // extern "C"

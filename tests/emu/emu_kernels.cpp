@@ -10,7 +10,8 @@ using namespace psb;
 template <int K, bool STATS, bool TRACE, typename W>
 static void run32(const Gotoh32Params &p, int nblocks) {
     size_t smem = gotoh32_smem_bytes(p.size, 1, STATS, sizeof(W));
-    emu::launch(nblocks, smem, [&]() { gotoh32_kernel<K, STATS, TRACE, W>(p); });
+    if (p.tabH) emu::launch(nblocks, smem, [&]() { gotoh32_kernel<K, STATS, TRACE, true, W>(p); });
+    else emu::launch(nblocks, smem, [&]() { gotoh32_kernel<K, STATS, TRACE, false, W>(p); });
 }
 
 extern "C" int emu_gotoh32(int K, int stats, int trace, int wide_stats, const Gotoh32Params *pp, int nblocks) {
@@ -28,3 +29,26 @@ extern "C" int emu_gotoh32(int K, int stats, int trace, int wide_stats, const Go
     return -1;
 }
 extern "C" int emu_sizeof_params() { return (int)sizeof(Gotoh32Params); }
+
+// ---- packed 16-bit scan kernel ------------------------------------------------------------------
+#include "../../parasail_rs_b200/csrc/kern_sw16.cuh"
+
+extern "C" int emu_sw16_build(const uint8_t *mapped_query, int lq, const int *table, int size, int open,
+                              int8_t *out, int cap, int *K, int *max_score) {
+    Sw16Profile pr;
+    std::vector<int8_t> host;
+    if (!sw16_build_profile(mapped_query, lq, table, size, open, &pr, &host)) return -1;
+    if ((int)host.size() > cap) return -2;
+    std::memcpy(out, host.data(), host.size());
+    *K = pr.K; *max_score = pr.max_score;
+    return (int)host.size();
+}
+
+extern "C" int emu_sw16(int K, const Sw16Params *pp, int nblocks) {
+    Sw16Params p = *pp;
+    size_t smem = sw16_smem_bytes(p.nletters, 1);
+#define SCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { sw16_scan_kernel<KK>(p); }); return 0;
+    switch (K) { SCASE(2) SCASE(4) SCASE(6) SCASE(8) SCASE(13) SCASE(16) }
+    return -1;
+}
+extern "C" int emu_sizeof_sw16() { return (int)sizeof(Sw16Params); }

@@ -31,7 +31,8 @@ class Gotoh32Params(C.Structure):
                 ("s2_end", C.c_int), ("score", C.c_void_p), ("end_query", C.c_void_p), ("end_ref", C.c_void_p),
                 ("matches", C.c_void_p), ("similar", C.c_void_p), ("length", C.c_void_p), ("bnd", C.c_void_p),
                 ("bnd_stride", C.c_longlong), ("trace", C.c_void_p), ("trace_off", C.c_void_p),
-                ("counter", C.c_void_p)]
+                ("counter", C.c_void_p), ("out_map", C.c_void_p), ("tabH", C.c_void_p), ("tabM", C.c_void_p),
+                ("tabS", C.c_void_p), ("tabL", C.c_void_p), ("tab_off", C.c_void_p)]
 
 
 def trace_to_rowmajor(blob, off, K, lq, lr):
@@ -79,10 +80,67 @@ def gotoh32(qs, rs, mat, K, mode, open, gap, flags=(1, 1, 1, 1), stats=False, tr
                       mat.size, int(mat.is_pssm), open, gap, mode, flags[0], flags[1], flags[2], flags[3],
                       ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(outs["matches"]),
                       ptr(outs["similar"]), ptr(outs["length"]), ptr(bnd), per_col * maxlr, ptr(blob),
-                      ptr(trace_off), ptr(counter))
+                      ptr(trace_off), ptr(counter), None, None, None, None, None, None)
     rc = lib().emu_gotoh32(K, int(stats), int(trace), int(wide), C.byref(p), nblocks)
     assert rc == 0
     if trace:
         outs["trace"] = [trace_to_rowmajor(blob, int(trace_off[i]), K, len(qm[0]) if shared_query else len(qm[i]), len(rm[i]))
                          for i in range(n)]
     return outs
+
+
+class Sw16Params(C.Structure):
+    _fields_ = [("prof", C.c_void_p), ("nletters", C.c_int), ("lq", C.c_int), ("open", C.c_int), ("gap", C.c_int),
+                ("max_score", C.c_int), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
+                ("bits", C.c_int), ("n", C.c_longlong), ("out_map", C.c_void_p), ("score", C.c_void_p),
+                ("end_query", C.c_void_p), ("end_ref", C.c_void_p), ("retry", C.c_void_p),
+                ("retry_count", C.c_void_p), ("sid_base", C.c_int), ("counter", C.c_void_p), ("mul_one", C.c_uint), ("mul_16", C.c_uint)]
+
+
+def pack_db(subjects_mapped, bits):
+    """host mirror of pack_db_kernel: sorted by length (descending, stable), rpw residues per word"""
+    rpw = 16 if bits == 2 else 6
+    n = len(subjects_mapped)
+    perm = sorted(range(n), key=lambda i: -len(subjects_mapped[i]))
+    word_off = np.zeros(n + 1, dtype=np.int64)
+    lens = np.zeros(n, dtype=np.int32)
+    words = []
+    for s, i in enumerate(perm):
+        seq = subjects_mapped[i]
+        lens[s] = len(seq)
+        nw = (len(seq) + rpw - 1) // rpw
+        for w in range(nw):
+            v = 0
+            for t in range(rpw):
+                idx = w * rpw + t
+                if idx < len(seq):
+                    v |= int(seq[idx]) << (bits * t)
+            words.append(v)
+        word_off[s + 1] = word_off[s] + nw
+    return np.array(words + [0], dtype=np.uint32), word_off, lens, np.array(perm, dtype=np.int32)
+
+
+def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1):
+    """Run the emulated packed scan kernel: one query vs subjects.  Returns (outs, retry list)."""
+    assert lib().emu_sizeof_sw16() == C.sizeof(Sw16Params)
+    mapper = mat.mapper.astype(np.uint8)
+    qm = np.ascontiguousarray(mapper[np.asarray(query, dtype=np.uint8)])
+    sm = [mapper[np.asarray(s, dtype=np.uint8)] for s in subjects]
+    table = np.ascontiguousarray(mat.table, dtype=np.int32)
+    prof = np.zeros(33 * 512, dtype=np.int8)
+    K, mx = C.c_int(), C.c_int()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    nb = lib().emu_sw16_build(ptr(qm), len(qm), ptr(table), mat.size, open, ptr(prof), prof.size, C.byref(K), C.byref(mx))
+    assert nb > 0, nb
+    words, word_off, lens, perm = pack_db(sm, bits)
+    n = len(sm)
+    outs = {k: np.full(n, -777, dtype=np.int32) for k in ("score", "end_query", "end_ref")}
+    retry = np.full(n + 2, -1, dtype=np.int32)
+    retry_count = np.zeros(1, dtype=np.int32)
+    counter = np.zeros(1, dtype=np.int32)
+    p = Sw16Params(ptr(prof), mat.size + 1, len(qm), open, gap, mx.value, ptr(words), ptr(word_off), ptr(lens), bits, n,
+                   ptr(perm), ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(retry),
+                   ptr(retry_count), 0, ptr(counter), 1, 16)
+    rc = lib().emu_sw16(K.value, C.byref(p), nblocks)
+    assert rc == 0, (rc, K.value)
+    return outs, sorted(int(perm[i]) for i in retry[: retry_count[0]])

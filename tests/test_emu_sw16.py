@@ -1,0 +1,51 @@
+"""The packed 16-bit scan kernel source (csrc/kern_sw16.cuh) on the CPU SIMT emulation vs the
+oracle: score, end_query, end_ref bit-exact; overflowing subjects must land on the retry list."""
+import numpy as np
+import pytest
+
+import emu_harness
+import psb_data
+
+
+def check(oracle, mat, query, subjects, o, e, bits=5):
+    outs, retry = emu_harness.sw16(query, subjects, mat, o, e, bits)
+    for i, s in enumerate(subjects):
+        if i in retry:
+            continue
+        exp = oracle.align(query, s, mat, mode=2, open=o, gap=e)
+        got = (outs["score"][i], outs["end_query"][i], outs["end_ref"][i])
+        assert got == (exp["score"], exp["end_query"], exp["end_ref"]), (i, len(query), len(s))
+    return outs, retry
+
+
+@pytest.mark.parametrize("lq", [40, 100, 400])
+def test_protein_scan(oracle, blosum62, lq):
+    q = psb_data.random_seq(7, 0, lq)
+    subs = []
+    for i in range(7):
+        L = [35, 90, 91, 150, 17, 64, 33][i]
+        if i % 2 == 0:
+            seg = psb_data.mutate(q[: min(lq, L)], 7, 100 + i, 0.2, 0.05)[:L]
+            s = np.concatenate([seg, psb_data.random_seq(8, i, max(0, L - len(seg)))])[:L]
+        else:
+            s = psb_data.random_seq(8, i, L)
+        subs.append(s)
+    _, retry = check(oracle, blosum62, q, subs, 10, 1)
+    assert retry == []
+
+
+def test_ties_and_zero(oracle):
+    mat = oracle.Matrix.create(b"ACGT", 2, -3)
+    q = np.frombuffer(b"ACTACGGG", dtype=np.uint8)
+    subs = [np.frombuffer(s, dtype=np.uint8) for s in (b"ACTTAC", b"AC", b"TTTT", b"ACGGGACGGG", b"GG")]
+    check(oracle, mat, q, subs, 5, 2)
+    check(oracle, mat, q, subs, 0, 0)
+    check(oracle, mat, q, subs, 5, 2, bits=5)
+
+
+def test_overflow_goes_to_retry(oracle, blosum62):
+    # identical 400-aa sequences score far above 2048 - 11: both subjects of that item are re-run
+    q = psb_data.random_seq(9, 0, 400)
+    subs = [q.copy(), psb_data.random_seq(9, 1, 380), psb_data.random_seq(9, 2, 60), psb_data.random_seq(9, 3, 50)]
+    _, retry = check(oracle, blosum62, q, subs, 10, 1)
+    assert retry == [0, 1]

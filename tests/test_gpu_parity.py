@@ -1,0 +1,275 @@
+"""GPU parity proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs -- bit-exact score, end_query, end_ref, matches/similar/length, CIGAR, beg_*."""
+import numpy as np
+import pytest
+
+import psb_data
+from test_oracle_properties import SG_FLAGS, cigar_rescore
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ps():
+    import __graft_entry__ as g
+    g.build()
+    import parasail_rs_b200 as ps
+    return ps
+
+
+MODE_NAME = {0: "global_", 1: "semi_global", 2: "local"}
+KEYS3 = ("score", "end_query", "end_ref")
+KEYS6 = KEYS3 + ("matches", "similar", "length")
+
+
+def builder(ps, mode, mat, o, e):
+    return getattr(ps.Aligner.new(), MODE_NAME[mode])().matrix(mat).gap_open(o).gap_extend(e)
+
+
+def mixed_pairs(seed, n, lq_rng, lr_rng, protein):
+    rng = np.random.default_rng(seed)
+    qs, rs = [], []
+    for i in range(n):
+        lq, lr = int(rng.integers(*lq_rng)), int(rng.integers(*lr_rng))
+        q = psb_data.random_seq(seed, 2 * i, lq, protein)
+        if i % 3 == 0:
+            r = psb_data.mutate(q, seed, 2 * i + 1, 0.15, 0.06, protein)
+            r = r[:lr] if len(r) >= lr else np.concatenate([r, psb_data.random_seq(seed + 7, i, lr - len(r), protein)])
+        else:
+            r = psb_data.random_seq(seed, 2 * i + 1, lr, protein)
+        qs.append(q); rs.append(r)
+    return qs, rs
+
+
+def oracle_batch(oracle, qs, rs, omat, mode, o, e, flags=(1, 1, 1, 1), **kw):
+    qc, qo = psb_data.concat(qs)
+    rc, ro = psb_data.concat(rs)
+    return oracle.align_batch(qc, qo, rc, ro, omat, mode=mode, open=o, gap=e, s1_beg=flags[0], s1_end=flags[1],
+                              s2_beg=flags[2], s2_end=flags[3], **kw)
+
+
+def assert_same(got, exp, keys, tag=""):
+    for k in keys:
+        g, x = getattr(got, k), exp[k]
+        if not np.array_equal(g, x):
+            bad = np.nonzero(g != x)[0]
+            raise AssertionError(f"{tag} {k}: {len(bad)} mismatches, first at {bad[0]}: got {g[bad[0]]} expected {x[bad[0]]}")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pairs_protein_all_length_classes(ps, oracle, blosum62, mode):
+    # query lengths 1..700 exercise every K class and the multi-strip path
+    qs, rs = mixed_pairs(101, 160, (1, 700), (1, 500), True)
+    got = builder(ps, mode, ps.Matrix.from_name("blosum62"), 10, 1).build().align_batch(qs, rs)
+    assert_same(got, oracle_batch(oracle, qs, rs, blosum62, mode, 10, 1), KEYS3, f"mode {mode}")
+
+
+@pytest.mark.parametrize("flags", SG_FLAGS)
+def test_pairs_sg_flags(ps, oracle, flags):
+    qs, rs = mixed_pairs(102, 60, (1, 200), (1, 200), False)
+    b = ps.Aligner.new().semi_global().matrix(ps.Matrix.create(b"ACGT", 2, -3)).gap_open(5).gap_extend(2)
+    qg = [g for g, f in (("prefix", flags[0]), ("suffix", flags[1])) if f]
+    dg = [g for g, f in (("prefix", flags[2]), ("suffix", flags[3])) if f]
+    got = b.allow_query_gaps(qg).allow_ref_gaps(dg).build().align_batch(qs, rs)
+    exp = oracle_batch(oracle, qs, rs, oracle.Matrix.create(b"ACGT", 2, -3), 1, 5, 2, flags)
+    assert_same(got, exp, KEYS3, str(flags))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("gaps", [(0, 0), (5, 2), (1, 4)])
+def test_pairs_stats(ps, oracle, mode, gaps):
+    qs, rs = mixed_pairs(103, 80, (1, 400), (1, 400), False)
+    got = builder(ps, mode, ps.Matrix.create(b"ACGT", 2, -3), *gaps).use_stats().build().align_batch(qs, rs)
+    exp = oracle_batch(oracle, qs, rs, oracle.Matrix.create(b"ACGT", 2, -3), mode, *gaps, stats=True)
+    assert_same(got, exp, KEYS6, f"mode {mode} gaps {gaps}")
+
+
+def test_pairs_stats_wide_counters(ps, oracle, blosum62):
+    # lengths beyond the 10/10/12-bit packed counters switch to the 64-bit statistics word
+    qs, rs = mixed_pairs(104, 6, (1100, 1300), (2900, 3100), True)
+    got = builder(ps, 2, ps.Matrix.from_name("blosum62"), 10, 1).use_stats().build().align_batch(qs, rs)
+    assert_same(got, oracle_batch(oracle, qs, rs, blosum62, 2, 10, 1, stats=True), KEYS6)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pairs_trace_cigar(ps, oracle, blosum62, mode):
+    qs, rs = mixed_pairs(105, 90, (1, 420), (1, 300), True)
+    got = builder(ps, mode, ps.Matrix.from_name("blosum62"), 10, 1).use_trace().build().align_batch(qs, rs)
+    exp = oracle_batch(oracle, qs, rs, blosum62, mode, 10, 1, cigar=True)
+    assert_same(got, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"), f"mode {mode}")
+
+
+def test_single_pair_api_matches_batch(ps, oracle, blosum62):
+    # the per-pair C entry points (what parasail-rs calls) against the oracle, incl. tables and trace bytes
+    b62 = ps.Matrix.from_name("blosum62")
+    qs, rs = mixed_pairs(106, 6, (1, 150), (1, 150), True)
+    for q, r in zip(qs, rs):
+        for mode in (0, 1, 2):
+            exp = oracle.align(q, r, blosum62, mode=mode, open=10, gap=1, tables=True, rowcol=True, trace=True)
+            a = builder(ps, mode, b62, 10, 1).use_stats().use_table().build().align(q, r)
+            assert (a.get_score(), a.get_end_query(), a.get_end_ref()) == (exp["score"], exp["end_query"], exp["end_ref"])
+            assert (a.get_matches(), a.get_similar(), a.get_length()) == (exp["matches"], exp["similar"], exp["length"])
+            for nm in ("score_table", "matches_table", "similar_table", "length_table"):
+                assert np.array_equal(getattr(a, "get_" + nm)(), exp[nm]), nm
+            a = builder(ps, mode, b62, 10, 1).use_stats().use_last_rowcol().build().align(q, r)
+            for nm in ("score_row", "matches_row", "similar_row", "length_row", "score_col", "matches_col", "similar_col", "length_col"):
+                assert np.array_equal(getattr(a, "get_" + nm)(), exp[nm]), nm
+            a = builder(ps, mode, b62, 10, 1).use_trace().build().align(q, r)
+            assert np.array_equal(a.get_trace_table(), exp["trace"])
+            assert a.get_cigar(q, r) == exp["cigar"] and a.cigar_beg == (exp["beg_query"], exp["beg_ref"])
+            tb = a.get_traceback_strings(q, r)
+            assert (tb.query, tb.comparison, tb.reference) == exp["traceback"]
+
+
+def test_pssm_matrix(ps, oracle, blosum62):
+    q = psb_data.random_seq(107, 0, 60)
+    pssm = ps.Matrix.from_name("blosum62").to_pssm(q)
+    rs = [psb_data.random_seq(107, i + 1, 40 + 3 * i) for i in range(8)]
+    for mode in (0, 2):
+        a = builder(ps, mode, pssm, 10, 1).build()
+        for r in rs:
+            exp = oracle.align(q, r, blosum62, mode=mode, open=10, gap=1)
+            got = a.align(q, r)
+            assert (got.get_score(), got.get_end_query(), got.get_end_ref()) == (exp["score"], exp["end_query"], exp["end_ref"])
+
+
+# ---- database scan (config C2, reduced) ------------------------------------------------------------
+def scan_case(ps, oracle, blosum62, query, cat, off, o=10, e=1, mode="local", stats=False):
+    b62 = ps.Matrix.from_name("blosum62")
+    db = ps.Database((cat, off), b62)
+    prof = ps.Profile.new(query, stats, b62)
+    a = getattr(ps.Aligner.new(), mode)().gap_open(o).gap_extend(e).profile(prof).build()
+    got = a.scan(db)
+    omode = {"local": 2, "global_": 0, "semi_global": 1}[mode]
+    exp = oracle.align_batch(query, np.array([0, len(query)]), cat, off, blosum62, mode=omode, open=o, gap=e,
+                             shared_query=True, stats=stats)
+    assert_same(got, exp, KEYS6 if stats else KEYS3, f"scan {mode}")
+    return got
+
+
+def test_scan_c2_reduced(ps, oracle, blosum62):
+    query = psb_data.random_seq(2001, 0, 400)
+    cat, off = psb_data.protein_db(2002, 2003, 6000, query=query, planted_frac=0.02)
+    got = scan_case(ps, oracle, blosum62, query, cat, off)
+    assert got.score.max() > 200  # planted segments are found
+    idx, sc = got.topk(10)
+    order = np.lexsort((np.arange(got.n), -got.score))[:10]
+    assert np.array_equal(idx, order) and np.array_equal(sc, got.score[order])
+
+
+@pytest.mark.parametrize("lq", [17, 64, 129, 300, 512])
+def test_scan_query_lengths(ps, oracle, blosum62, lq):
+    query = psb_data.random_seq(2101, 0, lq)
+    cat, off = psb_data.protein_db(2102, 2103, 700, query=query if lq >= 60 else None, planted_frac=0.05)
+    scan_case(ps, oracle, blosum62, query, cat, off)
+
+
+def test_scan_overflow_and_long_subjects(ps, oracle, blosum62):
+    # identical copies of the query overflow 16 bit; a 70 kb subject exceeds 16-bit columns;
+    # a 700-aa query takes the multi-strip 32-bit path
+    query = psb_data.random_seq(2201, 0, 400)
+    subs = [psb_data.random_seq(2202, i, 30 + 11 * i) for i in range(40)]
+    subs[3] = query.copy()
+    subs[17] = np.concatenate([psb_data.random_seq(2203, 0, 100), query, psb_data.random_seq(2203, 1, 50)])
+    subs.append(psb_data.random_seq(2204, 0, 70000))
+    cat, off = psb_data.concat(subs)
+    got = scan_case(ps, oracle, blosum62, query, cat, off)
+    assert got.n_retried >= 3 and got.score[3] > 2048
+    long_q = psb_data.random_seq(2205, 0, 700)
+    scan_case(ps, oracle, blosum62, long_q, *psb_data.concat(subs[:20]))
+
+
+@pytest.mark.parametrize("mode", ["global_", "semi_global"])
+def test_scan_other_modes_and_stats(ps, oracle, blosum62, mode):
+    query = psb_data.random_seq(2301, 0, 120)
+    cat, off = psb_data.protein_db(2302, 2303, 300, query=query, planted_frac=0.1)
+    scan_case(ps, oracle, blosum62, query, cat, off, mode=mode)
+    scan_case(ps, oracle, blosum62, query, cat, off, mode=mode, stats=True)
+    scan_case(ps, oracle, blosum62, query, cat, off, mode="local", stats=True)
+
+
+def test_scan_permutation_invariance_large(ps):
+    # size-independent property at a size the scalar oracle would need minutes for: shuffling the
+    # database permutes the results and nothing else
+    query = psb_data.random_seq(2401, 0, 400)
+    cat, off = psb_data.protein_db(2402, 2403, 100000, query=query, planted_frac=0.01)
+    b62 = ps.Matrix.from_name("blosum62")
+    prof = ps.Profile.new(query, False, b62)
+    a = ps.Aligner.new().local().gap_open(10).gap_extend(1).profile(prof).build()
+    base = a.scan(ps.Database((cat, off), b62))
+    perm = np.random.default_rng(5).permutation(len(off) - 1)
+    lens = np.diff(off)
+    off2 = np.zeros_like(off); off2[1:] = np.cumsum(lens[perm])
+    cat2 = np.concatenate([cat[off[i]:off[i + 1]] for i in perm])
+    shuf = a.scan(ps.Database((cat2, off2), b62))
+    for k in KEYS3:
+        assert np.array_equal(getattr(shuf, k), getattr(base, k)[perm]), k
+    assert np.all(base.end_ref < lens) and np.all(base.end_query < 400) and np.all(base.score >= 0)
+
+
+# ---- the other BASELINE configs, reduced ---------------------------------------------------------------
+def test_config_c1_reduced(ps, oracle, blosum62):
+    qs, rs = psb_data.protein_pairs(1001, 400, 300, related_frac=0.1)
+    got = ps.Aligner.new().matrix(ps.Matrix.from_name("blosum62")).gap_open(10).gap_extend(1).build().align_batch(qs, rs)
+    exp = oracle_batch(oracle, qs, rs, blosum62, 0, 10, 1)
+    assert_same(got, exp, KEYS3)
+    assert np.all(got.end_query == 299) and np.all(got.end_ref == 299)
+
+
+def test_config_c3_reduced(ps, oracle):
+    qs, rs = psb_data.dna_read_pairs(3001, 600)
+    a = ps.Aligner.new().semi_global().matrix(ps.Matrix.create(b"ACGT", 2, -3)).gap_open(5).gap_extend(2).use_stats().build()
+    assert a.fn_name == "sg_stats_striped_sat"
+    got = a.align_batch(qs, rs)
+    exp = oracle_batch(oracle, qs, rs, oracle.Matrix.create(b"ACGT", 2, -3), 1, 5, 2, stats=True)
+    assert_same(got, exp, KEYS6)
+
+
+def test_config_c4_reduced(ps, oracle, blosum62):
+    qs, rs = psb_data.protein_pairs(4001, 300, 250, related_frac=0.8, p_sub=0.2, p_indel=0.02, geometric_mean=2.0)
+    a = ps.Aligner.new().local().matrix(ps.Matrix.from_name("blosum62")).gap_open(10).gap_extend(1).use_trace().build()
+    assert a.fn_name == "sw_trace_striped_sat"
+    got = a.align_batch(qs, rs)
+    exp = oracle_batch(oracle, qs, rs, blosum62, 2, 10, 1, cigar=True)
+    assert_same(got, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"))
+    # oracle-free: re-scoring each CIGAR reproduces the score
+    for i in range(0, 300, 17):
+        ops = got.cigar_ops[got.cigar_off[i]: got.cigar_off[i + 1]]
+        if got.score[i] == 0:
+            continue
+        sc, ei, ej, *_ = cigar_rescore(ops, qs[i], rs[i], got.beg_query[i], got.beg_ref[i], blosum62, 10, 1)
+        first = int(ops[0])
+        if (first & 15) in (1, 2):
+            sc += 10 + ((first >> 4) - 1)
+        assert (sc, ei, ej) == (got.score[i], got.end_query[i], got.end_ref[i])
+
+
+def test_config_c5_reduced(ps, oracle):
+    # long DNA pair through the 32-bit path (multi-strip): 6 kb x 6 kb against the oracle
+    r = psb_data.random_seq(5001, 0, 6000, protein=False)
+    q = psb_data.mutate(r, 5001, 1, 0.10, 0.01, protein=False)[:6000]
+    a = ps.Aligner.new().local().matrix(ps.Matrix.create(b"ACGT", 2, -3)).gap_open(5).gap_extend(2).solution_width(32).build()
+    got = a.align(q, r)
+    exp = oracle.align(q, r, oracle.Matrix.create(b"ACGT", 2, -3), mode=2, open=5, gap=2)
+    assert (got.get_score(), got.get_end_query(), got.get_end_ref()) == (exp["score"], exp["end_query"], exp["end_ref"])
+    assert got.get_score() > 3000
+
+
+def test_edge_cases(ps, oracle, blosum62):
+    b62 = ps.Matrix.from_name("blosum62")
+    # single residues, unknown letters (mapped to '*'), lower case
+    qs = [b"A", b"W", b"acgt", b"XXXX", b"ARNDJOU", b"M" * 33]
+    rs = [b"A", b"A", b"ACGT", b"ARND", b"ARND??", b"M"]
+    for mode in (0, 1, 2):
+        got = builder(ps, mode, b62, 10, 1).use_stats().build().align_batch(qs, rs)
+        exp = oracle_batch(oracle, [np.frombuffer(x, dtype=np.uint8) for x in qs], [np.frombuffer(x, dtype=np.uint8) for x in rs],
+                           blosum62, mode, 10, 1, stats=True)
+        assert_same(got, exp, KEYS6, f"edge mode {mode}")
+    with pytest.raises(ps.DeviceError):
+        builder(ps, 0, b62, 10, 1).build().align_batch([b"ACGT", b""], [b"ACGT", b"ACGT"])
+    # explicit narrow width that cannot hold the result is reported saturated, not wrong
+    q = psb_data.random_seq(9, 0, 400)
+    res = builder(ps, 2, b62, 10, 1).solution_width(8).build().align(q, q)
+    assert res.is_saturated()
+    res = builder(ps, 2, b62, 10, 1).build().align(q, q)
+    assert not res.is_saturated() and res.get_score() > 2000
