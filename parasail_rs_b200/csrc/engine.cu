@@ -699,15 +699,14 @@ static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open,
 template <int K> static const void *sw16_fn_k() { return (const void *)sw16_scan_kernel<K>; }
 static const void *sw16_fn(int K) {
     switch (K) {
-        case 2: return sw16_fn_k<2>();
         case 4: return sw16_fn_k<4>();
-        case 6: return sw16_fn_k<6>();
         case 8: return sw16_fn_k<8>();
-        case 10: return sw16_fn_k<10>();
         case 12: return sw16_fn_k<12>();
-        case 13: return sw16_fn_k<13>();
-        case 14: return sw16_fn_k<14>();
         case 16: return sw16_fn_k<16>();
+        case 20: return sw16_fn_k<20>();
+        case 25: return sw16_fn_k<25>();
+        case 28: return sw16_fn_k<28>();
+        case 32: return sw16_fn_k<32>();
     }
     return nullptr;
 }
@@ -747,13 +746,13 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         p.counter = d_cnt.as<int>() + 1; p.mul_one = 1u; p.mul_16 = 16u;
         const void *fn = sw16_fn(sp.K);
         if (!fn) { set_error("sw16: no kernel for this query length"); return PSB_EUNSUPPORTED; }
-        const size_t smem = sw16_smem_bytes(sp.nletters, kSw16WarpsPerBlock);
+        const size_t smem = sw16_smem_bytes(sp.nletters, sp.chunks, kSw16WarpsPerBlock);
         if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSw16WarpsPerBlock * 32, smem));
         if (per_sm < 1) per_sm = 1;
-        const long long items = (nshort + 1) / 2;
-        long long blocks = std::min<long long>((items + kSw16WarpsPerBlock - 1) / kSw16WarpsPerBlock, (long long)c.sms * per_sm);
+        const long long slots = ((nshort + 1) / 2 + 1) / 2;  // a warp takes two items (four subjects) at a time
+        long long blocks = std::min<long long>((slots + kSw16WarpsPerBlock - 1) / kSw16WarpsPerBlock, (long long)c.sms * per_sm);
         if (blocks < 1) blocks = 1;
         void *args[] = {&p};
         PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kSw16WarpsPerBlock * 32), args, smem, c.stream));

@@ -34,21 +34,21 @@ extern "C" int emu_sizeof_params() { return (int)sizeof(Gotoh32Params); }
 #include "../../parasail_rs_b200/csrc/kern_sw16.cuh"
 
 extern "C" int emu_sw16_build(const uint8_t *mapped_query, int lq, const int *table, int size, int open,
-                              int8_t *out, int cap, int *K, int *max_score) {
+                              int8_t *out, int cap, int *K, int *max_score, int *chunks) {
     Sw16Profile pr;
     std::vector<int8_t> host;
     if (!sw16_build_profile(mapped_query, lq, table, size, open, &pr, &host)) return -1;
     if ((int)host.size() > cap) return -2;
     std::memcpy(out, host.data(), host.size());
-    *K = pr.K; *max_score = pr.max_score;
+    *K = pr.K; *max_score = pr.max_score; *chunks = pr.chunks;
     return (int)host.size();
 }
 
 extern "C" int emu_sw16(int K, const Sw16Params *pp, int nblocks) {
     Sw16Params p = *pp;
-    size_t smem = sw16_smem_bytes(p.nletters, 1);
+    size_t smem = sw16_smem_bytes(p.nletters, (K + 15) / 16, 1);
 #define SCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { sw16_scan_kernel<KK>(p); }); return 0;
-    switch (K) { SCASE(2) SCASE(4) SCASE(6) SCASE(8) SCASE(13) SCASE(16) }
+    switch (K) { SCASE(4) SCASE(8) SCASE(12) SCASE(16) SCASE(20) SCASE(25) SCASE(28) SCASE(32) }
     return -1;
 }
 extern "C" int emu_sizeof_sw16() { return (int)sizeof(Sw16Params); }

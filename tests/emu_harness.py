@@ -128,9 +128,10 @@ def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1):
     sm = [mapper[np.asarray(s, dtype=np.uint8)] for s in subjects]
     table = np.ascontiguousarray(mat.table, dtype=np.int32)
     prof = np.zeros(33 * 512, dtype=np.int8)
-    K, mx = C.c_int(), C.c_int()
+    K, mx, ch = C.c_int(), C.c_int(), C.c_int()
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-    nb = lib().emu_sw16_build(ptr(qm), len(qm), ptr(table), mat.size, open, ptr(prof), prof.size, C.byref(K), C.byref(mx))
+    nb = lib().emu_sw16_build(ptr(qm), len(qm), ptr(table), mat.size, open, ptr(prof), prof.size, C.byref(K), C.byref(mx),
+                              C.byref(ch))
     assert nb > 0, nb
     words, word_off, lens, perm = pack_db(sm, bits)
     n = len(sm)

@@ -43,9 +43,20 @@ def test_ties_and_zero(oracle):
     check(oracle, mat, q, subs, 5, 2, bits=5)
 
 
-def test_overflow_goes_to_retry(oracle, blosum62):
-    # identical 400-aa sequences score far above 2048 - 11: both subjects of that item are re-run
-    q = psb_data.random_seq(9, 0, 400)
-    subs = [q.copy(), psb_data.random_seq(9, 1, 380), psb_data.random_seq(9, 2, 60), psb_data.random_seq(9, 3, 50)]
-    _, retry = check(oracle, blosum62, q, subs, 10, 1)
+def test_overflow_goes_to_retry(oracle):
+    # 400 matches at +100 exceed the 16-bit range: both subjects of that item are re-run at 32 bit,
+    # everything else stays exact
+    mat = oracle.Matrix.create(b"ACGT", 100, -90)
+    q = psb_data.random_seq(9, 0, 400, protein=False)
+    subs = [q.copy(), psb_data.random_seq(9, 1, 380, protein=False), psb_data.random_seq(9, 2, 60, protein=False),
+            psb_data.random_seq(9, 3, 50, protein=False)]
+    _, retry = check(oracle, mat, q, subs, 5, 2)
     assert retry == [0, 1]
+
+
+def test_high_scores_stay_in_16_bit(oracle, blosum62):
+    # an identical 400-aa protein scores ~2100: no re-run needed any more
+    q = psb_data.random_seq(9, 0, 400)
+    subs = [q.copy(), psb_data.random_seq(9, 1, 380), np.concatenate([psb_data.random_seq(9, 2, 60), q[50:300]])]
+    outs, retry = check(oracle, blosum62, q, subs, 10, 1)
+    assert retry == [] and outs["score"][0] > 2000
