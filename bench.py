@@ -175,17 +175,9 @@ def main():
     lens = np.diff(off)
     total_cells = float(QUERY_LEN) * float(off[-1])
     if world > 1:
+        from parasail_rs_b200 import sharding
         shard = ps.shard_plan(off, world)
-        mine = np.nonzero(shard == rank)[0]
-        my_off = np.zeros(len(mine) + 1, dtype=np.int64)
-        my_off[1:] = np.cumsum(lens[mine])
-        idx = np.concatenate([np.arange(off[i], off[i + 1]) for i in mine]) if len(mine) < 50000 else None
-        if idx is None:
-            my_cat = np.empty(int(my_off[-1]), dtype=np.uint8)
-            for t, i in enumerate(mine):
-                my_cat[my_off[t]: my_off[t + 1]] = cat[off[i]: off[i + 1]]
-        else:
-            my_cat = cat[idx]
+        my_cat, my_off, mine = sharding.local_shard(cat, off, shard, rank)
     else:
         mine, my_cat, my_off = np.arange(len(lens)), cat, off
     my_cells = float(QUERY_LEN) * float(my_off[-1])
