@@ -271,7 +271,7 @@ def main():
     roofline = {
         "bound": "int_alu_dpx", "achieved": achieved, "peak": peak_s16, "unit": "GCUPS", "frac": achieved / peak_s16,
         "traffic": None,
-        "kernel": "sw16_scan_kernel<13> (packed s16x2 DPX)", "kernel_ms_per_launch": float(kms.item()),
+        "kernel": "sw16_scan_kernel<25> (packed s16x2 DPX, 16-lane groups)", "kernel_ms_per_launch": float(kms.item()),
         "peak_basis": f"148 SM x {LANE_OPS_PER_CLK_SM} lane-ops/clk x {sm_mhz:.0f} MHz (sampled) / {OPS_PER_CELL} ops per cell x 2 cells per s16x2 op",
         "peak_at_max_clock": 148 * LANE_OPS_PER_CLK_SM * 1.965 / OPS_PER_CELL * 2,
         "hbm": {"algorithmic_bytes_per_launch": packed_bytes, "achieved_gbs": packed_bytes / (float(kms.item()) * 1e-3) / 1e9,
