@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <map>
 #include <mutex>
@@ -20,6 +21,7 @@
 #include "kern_gotoh32.cuh"
 #include "kern_sw16.cuh"
 #include "kern_util.cuh"
+#include "kern_wave32.cuh"
 #include "psb_internal.h"
 
 namespace psb {
@@ -212,6 +214,45 @@ static int launch_gotoh32(int K, Variant v, Gotoh32Params &p, int nwork, long lo
 
 static long long max_grid_warps() { return (long long)g_ctx.sms * 16 * kWarpsPerBlock; }
 
+// ---- one long pair over the whole GPU (kern_wave32.cuh) -------------------------------------------
+static constexpr int kWaveMinLq = 2048;   // below this the per-pair kernel is used
+
+template <int K> static const void *wave32_fn_k() { return (const void *)wave32_kernel<K>; }
+
+static int launch_wave32(const Gotoh32Params &g, long long q_byte_off, int lq, long long r_byte_off, int lr, int out_index) {
+    Ctx &c = g_ctx;
+    // strips of 32*K rows: enough strips to occupy the chip, as few as possible beyond that
+    const int K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4);
+    const void *fn = K == 16 ? wave32_fn_k<16>() : (K == 8 ? wave32_fn_k<8>() : wave32_fn_k<4>());
+    const int nstrips = (lq + 32 * K - 1) / (32 * K);
+    DevMem d_bnd, d_ctl, d_cand;
+    PSB_TRY(d_bnd.alloc((size_t)nstrips * 2 * (size_t)lr * sizeof(int), c.stream));
+    PSB_TRY(d_ctl.alloc(((size_t)nstrips + 2) * sizeof(int), c.stream));
+    PSB_TRY(d_cand.alloc((size_t)nstrips * 8 * sizeof(int), c.stream));
+    PSB_CUDA(cudaMemsetAsync(d_ctl.p, 0, ((size_t)nstrips + 2) * sizeof(int), c.stream));
+    Wave32Params p;
+    p.q = g.q + q_byte_off; p.r = g.r + r_byte_off; p.Lq = lq; p.Lr = lr;
+    p.matrix = g.matrix; p.size = g.size; p.open = g.open; p.gap = g.gap;
+    p.mode = g.mode; p.s1_beg = g.s1_beg; p.s1_end = g.s1_end; p.s2_beg = g.s2_beg; p.s2_end = g.s2_end;
+    p.bnd = d_bnd.as<int>(); p.progress = d_ctl.as<int>() + 1; p.next_strip = d_ctl.as<int>(); p.cand = d_cand.as<int>();
+    const size_t smem = wave32_smem_bytes(g.size, kWarpsPerBlock);
+    if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    // every launched warp must be resident at once: the strips wait on one another
+    long long blocks = std::min<long long>((nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock, (long long)c.sms * per_sm);
+    if (blocks < 1) blocks = 1;
+    void *args[] = {&p};
+    PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kWarpsPerBlock * 32), args, smem, c.stream));
+    WaveReduceParams r;
+    r.cand = d_cand.as<int>(); r.nstrips = nstrips; r.mode = g.mode; r.s1_end = g.s1_end; r.s2_end = g.s2_end; r.Lr = lr;
+    r.score = g.score + out_index; r.end_query = g.end_query + out_index; r.end_ref = g.end_ref + out_index;
+    wave32_reduce_kernel<<<1, 32, 0, c.stream>>>(r);
+    c.launches += 2;
+    return PSB_OK;
+}
+
 // ---- many pairs ---------------------------------------------------------------------------------
 struct PairChunk {
     int64_t lo, hi;  // pair range of the caller's batch handled by this pass
@@ -231,6 +272,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     const int64_t q_hi = req.shared_query ? req.q_off[1] : req.q_off[hi];
     const int64_t r_lo = req.r_off[lo], r_hi = req.r_off[hi];
     std::vector<std::vector<int>> cls(kNumClass);
+    std::vector<int> wave_ids;   // long score-only pairs: spread over the whole GPU one at a time
     int max_lr_multistrip = 0;
     int max_sum = 0, max_min = 0;
     bool uniform = true;
@@ -241,8 +283,10 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         const int lr = (int)(req.r_off[lo + i + 1] - req.r_off[lo + i]);
         if (lq <= 0 || lr <= 0) { set_error("empty sequence in batch (pair " + std::to_string(lo + i) + ")"); return PSB_EINVAL; }
         const int cl = class_of_len(lq);
-        cls[cl].push_back((int)i);
-        if (lq > 32 * kClassK[cl]) max_lr_multistrip = std::max(max_lr_multistrip, lr);
+        const bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !cfg.stats && !cfg.trace && !(req.extra && (cfg.table || cfg.rowcol));
+        if (wave) { wave_ids.push_back((int)i); uniform = false; }
+        else cls[cl].push_back((int)i);
+        if (!wave && lq > 32 * kClassK[cl]) max_lr_multistrip = std::max(max_lr_multistrip, lr);
         max_sum = std::max(max_sum, lq + lr);
         max_min = std::max(max_min, std::min(lq, lr));
         const long long cells = (long long)lq * lr;
@@ -358,6 +402,13 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         p.counter = d_counter.as<int>() + cl;
         const Variant v = want_table ? V_TABLE : (want_trace ? V_TRACE : (cfg.stats ? (wide_stats ? V_STATS64 : V_STATS32) : V_SCORE));
         PSB_TRY(launch_gotoh32(kClassK[cl], v, p, p.n));
+    }
+
+    for (int id : wave_ids) {
+        const long long qb = (req.shared_query ? 0 : qoff_rel[id]), rb = roff_rel[id];
+        const int lq = (int)(req.shared_query ? qoff_rel[1] : qoff_rel[id + 1] - qoff_rel[id]);
+        const int lr = (int)(roff_rel[id + 1] - roff_rel[id]);
+        PSB_TRY(launch_wave32(p, qb, lq, rb, lr, id));
     }
 
     // device-side trace walk -> CIGAR CSR
@@ -558,16 +609,17 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
 
 struct psb_db {
     int device = 0;
+    cudaStream_t stream = nullptr;  // stream the buffers were allocated on (stream-ordered pool)
     int64_t n = 0, residues = 0, words = 0;
     int bits = 5;
     int msize = 0;
+    int maxlen = 0;                 // longest subject
+    int nlong = 0;                  // subjects longer than 65535 (sorted first)
     uint8_t mapper[256];
-    std::vector<int> perm;          // sorted position -> caller's subject id (length descending)
-    std::vector<int> len_sorted;
     unsigned *d_words = nullptr;
-    long long *d_word_off = nullptr;  // n+1
-    int *d_perm = nullptr;
-    int *d_len = nullptr;
+    long long *d_word_off = nullptr;  // n+1, sorted order (length descending, stable)
+    int *d_perm = nullptr;            // sorted position -> caller's subject id
+    int *d_len = nullptr;             // sorted order
     // unpacked copy for the general 32-bit path, built on first use
     uint8_t *d_bytes = nullptr;
     long long *d_byte_off = nullptr;
@@ -580,6 +632,7 @@ struct DevProfile {
     uint8_t *d_query = nullptr;     // mapped residues
     long long *d_qoff = nullptr;    // {0, Lq}
     int *d_matrix = nullptr;
+    cudaStream_t stream = nullptr;  // allocation stream (stream-ordered pool)
     std::vector<uint8_t> mapped;    // host copy of the mapped query
     Sw16Profile sw16;               // packed int8 profile (+open) for the 16-bit scan kernel
 };
@@ -591,7 +644,8 @@ void release_profile_resident(parasail_profile *p) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(kv.first);
-        cudaFree(d->d_query); cudaFree(d->d_qoff); cudaFree(d->d_matrix); cudaFree(d->sw16.prof);
+        void *ptrs[] = {d->d_query, d->d_qoff, d->d_matrix, d->sw16.prof};
+        for (void *q : ptrs) if (q) cudaFreeAsync(q, d->stream);
         cudaSetDevice(cur);
         delete d;
     }
@@ -609,9 +663,10 @@ static int get_dev_profile(const parasail_profile *prof, DevProfile **out) {
     std::vector<uint8_t> mapped(lq);
     for (size_t i = 0; i < lq; ++i) mapped[i] = m.mapper[prof->query[i]];
     long long qoff[2] = {0, (long long)lq};
-    PSB_CUDA(cudaMalloc(&d->d_query, std::max<size_t>(lq, 16)));
-    PSB_CUDA(cudaMalloc(&d->d_qoff, sizeof(qoff)));
-    PSB_CUDA(cudaMalloc(&d->d_matrix, m.table.size() * sizeof(int)));
+    d->stream = c.stream;
+    PSB_CUDA(cudaMallocAsync(&d->d_query, std::max<size_t>(lq, 16), c.stream));
+    PSB_CUDA(cudaMallocAsync(&d->d_qoff, sizeof(qoff), c.stream));
+    PSB_CUDA(cudaMallocAsync(&d->d_matrix, m.table.size() * sizeof(int), c.stream));
     PSB_CUDA(cudaMemcpyAsync(d->d_query, mapped.data(), lq, cudaMemcpyHostToDevice, c.stream));
     PSB_CUDA(cudaMemcpyAsync(d->d_qoff, qoff, sizeof(qoff), cudaMemcpyHostToDevice, c.stream));
     PSB_CUDA(cudaMemcpyAsync(d->d_matrix, m.table.data(), m.table.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
@@ -622,21 +677,46 @@ static int get_dev_profile(const parasail_profile *prof, DevProfile **out) {
     return PSB_OK;
 }
 
+__global__ void db_lengths_kernel(const long long *off, long long n, int rpw, int *len, int *idx, long long *wcount, int *stats) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        if (i == n) { wcount[n] = 0; break; }
+        const long long l = off[i + 1] - off[i];
+        len[i] = (int)l; idx[i] = (int)i;
+        wcount[i] = (l + rpw - 1) / rpw;
+        if (l <= 0 || l > 0x7fffffff) atomicAdd(&stats[0], 1);   // empty / absurd subjects
+        atomicMax(&stats[1], (int)(l > 0x7fffffff ? 0x7fffffff : l));
+        if (l > 65535) atomicAdd(&stats[2], 1);
+    }
+}
+__global__ void db_wcount_sorted_kernel(const int *len_sorted, long long n, int rpw, long long *wcount) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride)
+        wcount[i] = i < n ? (len_sorted[i] + rpw - 1) / rpw : 0;
+}
+__global__ void db_len64_kernel(const int *len_sorted, long long n, long long *out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) out[i] = i < n ? len_sorted[i] : 0;
+}
+
 static int db_ensure_bytes(psb_db *db) {
     Ctx &c = g_ctx;
     std::lock_guard<std::mutex> lk(db->mu);
     if (db->d_bytes) return PSB_OK;
-    std::vector<long long> off(db->n + 1);
-    off[0] = 0;
-    for (int64_t i = 0; i < db->n; ++i) off[i + 1] = off[i] + db->len_sorted[i];
-    PSB_CUDA(cudaMalloc(&db->d_bytes, std::max<size_t>((size_t)db->residues, 16)));
-    PSB_CUDA(cudaMalloc(&db->d_byte_off, off.size() * sizeof(long long)));
-    PSB_CUDA(cudaMemcpyAsync(db->d_byte_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+    PSB_CUDA(cudaMallocAsync(&db->d_bytes, std::max<size_t>((size_t)db->residues, 16), c.stream));
+    PSB_CUDA(cudaMallocAsync(&db->d_byte_off, ((size_t)db->n + 1) * sizeof(long long), c.stream));
+    DevMem tmp64, scan_tmp;
+    PSB_TRY(tmp64.alloc(((size_t)db->n + 1) * sizeof(long long), c.stream));
+    db_len64_kernel<<<c.sms * 4, 256, 0, c.stream>>>(db->d_len, db->n, tmp64.as<long long>());
+    size_t tb = 0;
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, tmp64.as<long long>(), db->d_byte_off, (int)(db->n + 1), c.stream));
+    PSB_TRY(scan_tmp.alloc(tb, c.stream));
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tb, tmp64.as<long long>(), db->d_byte_off, (int)(db->n + 1), c.stream));
     UnpackParams u;
     u.words = db->d_words; u.word_off = db->d_word_off; u.ids = nullptr; u.out_off = db->d_byte_off;
     u.out = db->d_bytes; u.n = db->n; u.bits = db->bits;
     unpack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(u);
-    c.launches++;
+    c.launches += 3;
     PSB_CUDA(cudaStreamSynchronize(c.stream));
     return PSB_OK;
 }
@@ -653,10 +733,10 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     DevMem d_counter, d_bnd;
     PSB_TRY(d_counter.alloc(sizeof(int), c.stream));
     PSB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int), c.stream));
-    const bool wide = !(std::min(lq, db->len_sorted[0]) < 1024 && lq + db->len_sorted[0] < 4096);
+    const bool wide = !(std::min(lq, db->maxlen) < 1024 && lq + db->maxlen < 4096);
     long long bnd_stride = 0;
     if (lq > 32 * K) {
-        bnd_stride = (long long)db->len_sorted[0] * (2 + (cfg.stats ? (wide ? 4 : 2) : 0));
+        bnd_stride = (long long)db->maxlen * (2 + (cfg.stats ? (wide ? 4 : 2) : 0));
         PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps()) * sizeof(int), c.stream));
     }
     Gotoh32Params p;
@@ -688,8 +768,8 @@ static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open,
     std::vector<int8_t> host;
     if (!sw16_build_profile(dp->mapped.data(), (int)dp->mapped.size(), m.table.data(), m.size, open, &np_, &host)) return false;
     if (!sw16_supported(np_, open, gap)) return false;
-    if (dp->sw16.prof) { cudaStreamSynchronize(c.stream); cudaFree(dp->sw16.prof); dp->sw16.prof = nullptr; }
-    if (cudaMalloc(&np_.prof, host.size()) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (dp->sw16.prof) { cudaFreeAsync(dp->sw16.prof, dp->stream); dp->sw16.prof = nullptr; }
+    if (cudaMallocAsync(&np_.prof, host.size(), c.stream) != cudaSuccess) { cudaGetLastError(); return false; }
     if (cudaMemcpyAsync(np_.prof, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return false;
     cudaStreamSynchronize(c.stream);  // `host` goes out of scope
     dp->sw16 = np_;
@@ -720,8 +800,7 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
     Ctx &c = g_ctx;
     const Sw16Profile &sp = dp->sw16;
     // sorted by length descending: the first `nlong` subjects exceed the 16-bit column range
-    int64_t nlong = 0;
-    while (nlong < db->n && db->len_sorted[nlong] > 65535) ++nlong;
+    const int64_t nlong = db->nlong;
     DevMem d_retry, d_cnt;
     PSB_TRY(d_retry.alloc(((size_t)db->n + 2) * sizeof(int), c.stream));
     PSB_TRY(d_cnt.alloc(2 * sizeof(int), c.stream));
@@ -830,69 +909,69 @@ int psb_align_pairs(const char *fn_name, const parasail_matrix_t *matrix, int op
 
 psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const parasail_matrix_t *matrix) {
     if (!cat || !off || n <= 0 || !matrix) { set_error("psb_db_create: NULL argument or empty database"); return nullptr; }
-    if (n > 0x7fffffff) { set_error("psb_db_create: more than 2^31-1 subjects"); return nullptr; }
+    if (n > 0x7ffffffe) { set_error("psb_db_create: more than 2^31-2 subjects"); return nullptr; }
     if (ensure_ctx() != PSB_OK) return nullptr;
     Ctx &c = g_ctx;
     HostMatrix hm(matrix);
+    if (hm.size > 32) { set_error("psb_db_create: alphabets above 32 letters cannot be 5-bit packed"); return nullptr; }
     psb_db *db = new psb_db();
-    db->device = c.device; db->n = n; db->msize = hm.size;
+    db->device = c.device; db->stream = c.stream; db->n = n; db->msize = hm.size;
     std::memcpy(db->mapper, hm.mapper, 256);
     db->bits = hm.size <= 4 ? 2 : 5;
-    if (hm.size > 32) { set_error("psb_db_create: alphabets above 32 letters cannot be 5-bit packed"); delete db; return nullptr; }
     const int rpw = db->bits == 2 ? 16 : 6;
-    db->perm.resize(n);
-    std::iota(db->perm.begin(), db->perm.end(), 0);
-    for (int64_t i = 0; i < n; ++i)
-        if (off[i + 1] <= off[i]) { set_error("psb_db_create: empty subject " + std::to_string(i)); delete db; return nullptr; }
-    {
-        // stable order by decreasing length: counting sort when the lengths are small integers
-        int64_t maxlen = 0;
-        for (int64_t i = 0; i < n; ++i) maxlen = std::max<int64_t>(maxlen, off[i + 1] - off[i]);
-        if (maxlen < (1 << 22)) {
-            std::vector<int64_t> start((size_t)maxlen + 2, 0);
-            for (int64_t i = 0; i < n; ++i) start[(size_t)(maxlen - (off[i + 1] - off[i])) + 1]++;
-            for (size_t k = 1; k < start.size(); ++k) start[k] += start[k - 1];
-            for (int64_t i = 0; i < n; ++i) db->perm[(size_t)start[(size_t)(maxlen - (off[i + 1] - off[i]))]++] = (int)i;
-        } else {
-            std::stable_sort(db->perm.begin(), db->perm.end(), [&](int a, int b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
-        }
-    }
-    db->len_sorted.resize(n);
-    std::vector<long long> word_off(n + 1);
-    word_off[0] = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        const int len = (int)(off[db->perm[i] + 1] - off[db->perm[i]]);
-        db->len_sorted[i] = len;
-        word_off[i + 1] = word_off[i] + (len + rpw - 1) / rpw;
-    }
     db->residues = off[n] - off[0];
-    db->words = word_off[n];
-    auto fail = [&](const char *what, cudaError_t e) {
-        set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    auto fail = [&](const std::string &what) {
+        set_error(what);
+        cudaStreamSynchronize(c.stream);
         psb_db_free(db);
         return (psb_db_t *)nullptr;
     };
-    cudaError_t e;
-    // staging copies of the raw residues and offsets are stream-ordered temporaries
-    DevMem d_raw, d_rawoff;
-    if (d_raw.alloc((size_t)db->residues, c.stream) != PSB_OK || d_rawoff.alloc(((size_t)n + 1) * sizeof(long long), c.stream) != PSB_OK) { psb_db_free(db); return nullptr; }
-    std::vector<long long> off_rel(n + 1);
-    for (int64_t i = 0; i <= n; ++i) off_rel[i] = off[i] - off[0];
-    if ((e = cudaMalloc(&db->d_words, std::max<size_t>((size_t)db->words * 4 + 64, 64))) != cudaSuccess) return fail("cudaMalloc(db words)", e);
-    if ((e = cudaMalloc(&db->d_word_off, word_off.size() * sizeof(long long))) != cudaSuccess) return fail("cudaMalloc(db offsets)", e);
-    if ((e = cudaMalloc(&db->d_perm, (size_t)n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc(db perm)", e);
-    if ((e = cudaMalloc(&db->d_len, (size_t)n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc(db lengths)", e);
-    cudaMemcpyAsync(db->d_len, db->len_sorted.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c.stream);
-    cudaMemcpyAsync(d_raw.p, cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, c.stream);
-    cudaMemcpyAsync(d_rawoff.p, off_rel.data(), off_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream);
-    cudaMemcpyAsync(db->d_word_off, word_off.data(), word_off.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream);
-    cudaMemcpyAsync(db->d_perm, db->perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c.stream);
+    if (db->residues <= 0) return fail("psb_db_create: offsets are not increasing");
+    // everything below runs on the device: lengths, stable sort by decreasing length (radix sort),
+    // word offsets (scan), residue mapping + bit packing.  The host only touches off[0] and off[n].
+    DevMem d_raw, d_off, d_len0, d_idx0, d_wcount, d_stats, d_tmp;
+    const size_t n1 = (size_t)n + 1;
+    if (d_raw.alloc((size_t)db->residues, c.stream) != PSB_OK || d_off.alloc(n1 * 8, c.stream) != PSB_OK ||
+        d_len0.alloc((size_t)n * 4, c.stream) != PSB_OK || d_idx0.alloc((size_t)n * 4, c.stream) != PSB_OK ||
+        d_wcount.alloc(n1 * 8, c.stream) != PSB_OK || d_stats.alloc(16, c.stream) != PSB_OK)
+        return fail(psb_last_error());
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ck(cudaMallocAsync(&db->d_word_off, n1 * 8, c.stream));
+    ck(cudaMallocAsync(&db->d_perm, (size_t)n * 4, c.stream));
+    ck(cudaMallocAsync(&db->d_len, (size_t)n * 4, c.stream));
+    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
+    ck(cudaMemcpyAsync(d_off.p, off, n1 * 8, cudaMemcpyHostToDevice, c.stream));
+    ck(cudaMemcpyAsync(d_raw.p, cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, c.stream));
+    ck(cudaMemsetAsync(d_stats.p, 0, 16, c.stream));
+    db_lengths_kernel<<<c.sms * 4, 256, 0, c.stream>>>(d_off.as<long long>(), n, rpw, d_len0.as<int>(), d_idx0.as<int>(),
+                                                      d_wcount.as<long long>(), d_stats.as<int>());
+    size_t tb = 0, tb2 = 0;
+    ck(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, d_len0.as<int>(), db->d_len, d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
+    ck(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
+    if (d_tmp.alloc(std::max(tb, tb2), c.stream) != PSB_OK) return fail(psb_last_error());
+    ck(cub::DeviceRadixSort::SortPairsDescending(d_tmp.p, tb, d_len0.as<int>(), db->d_len, d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
+    db_wcount_sorted_kernel<<<c.sms * 4, 256, 0, c.stream>>>(db->d_len, n, rpw, d_wcount.as<long long>());
+    ck(cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
+    int stats[4] = {0, 0, 0, 0};
+    long long total_words = 0;
+    ck(cudaMemcpyAsync(stats, d_stats.p, 16, cudaMemcpyDeviceToHost, c.stream));
+    ck(cudaMemcpyAsync(&total_words, db->d_word_off + n, 8, cudaMemcpyDeviceToHost, c.stream));
+    ck(cudaStreamSynchronize(c.stream));
+    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
+    if (stats[0] != 0) return fail("psb_db_create: " + std::to_string(stats[0]) + " empty or oversized subject(s)");
+    db->maxlen = stats[1]; db->nlong = stats[2]; db->words = total_words;
+    ck(cudaMallocAsync(&db->d_words, (size_t)db->words * 4 + 64, c.stream));
+    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
     PackParams pp;
-    pp.raw = d_raw.as<uint8_t>(); pp.raw_off = d_rawoff.as<long long>(); pp.perm = db->d_perm;
+    pp.raw = d_raw.as<uint8_t>(); pp.raw_off = d_off.as<long long>(); pp.raw_base = off[0]; pp.perm = db->d_perm;
     pp.word_off = db->d_word_off; pp.words = db->d_words; pp.n = n; pp.bits = db->bits;
     fill_lut(pp.lut, hm.mapper);
     pack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(pp);
-    if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return fail("database packing", e);
+    c.launches += 6;
+    // no synchronisation: later work on this stream is ordered after the packing kernel, and the
+    // staging buffers are returned to the pool in stream order
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(std::string("database packing: ") + cudaGetErrorString(e));
     return db;
 }
 
@@ -907,7 +986,8 @@ void psb_db_free(psb_db_t *db) {
     int cur = 0;
     cudaGetDevice(&cur);
     cudaSetDevice(db->device);
-    cudaFree(db->d_words); cudaFree(db->d_word_off); cudaFree(db->d_perm); cudaFree(db->d_len); cudaFree(db->d_bytes); cudaFree(db->d_byte_off);
+    void *ptrs[] = {db->d_words, db->d_word_off, db->d_perm, db->d_len, db->d_bytes, db->d_byte_off};
+    for (void *p : ptrs) if (p) cudaFreeAsync(p, db->stream);
     cudaSetDevice(cur);
     delete db;
 }
@@ -932,7 +1012,7 @@ int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, i
     psb_batch_t *b = new_batch(db->n, cfg);
     if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
     const int lq = (int)profile->query.size();
-    for (int64_t i = 0; i < db->n; ++i) b->cells += (double)lq * db->len_sorted[i];
+    b->cells = (double)lq * (double)db->residues;
     DevMem d_out[6];
     int *outp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int nout = cfg.stats ? 6 : 3;

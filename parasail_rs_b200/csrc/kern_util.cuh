@@ -27,7 +27,8 @@ PSB_DEV constexpr int residues_per_word(int bits) { return bits == 2 ? 16 : 6; }
 
 struct PackParams {
     const uint8_t *raw;          // original residues (caller order), unmapped
-    const long long *raw_off;    // n+1
+    const long long *raw_off;    // n+1, as given by the caller
+    long long raw_base;          // raw_off[0]: `raw` starts at that residue
     const int *perm;             // sorted position -> original subject id
     const long long *word_off;   // n+1, in words, sorted order
     unsigned *words;
@@ -42,8 +43,8 @@ PSB_KERNEL void pack_db_kernel(PackParams p) {
     const long long nwarps = ((long long)grid_blocks() * threads_per_block()) >> 5;
     const int lane = lane_id();
     for (long long s = warp; s < p.n; s += nwarps) {
-        const long long src = p.raw_off[p.perm[s]];
-        const int len = (int)(p.raw_off[p.perm[s] + 1] - src);
+        const long long src = p.raw_off[p.perm[s]] - p.raw_base;
+        const int len = (int)(p.raw_off[p.perm[s] + 1] - p.raw_off[p.perm[s]]);
         const long long w0 = p.word_off[s];
         const int nw = (int)(p.word_off[s + 1] - w0);
         for (int w = lane; w < nw; w += 32) {

@@ -1,0 +1,212 @@
+// kern_wave32.cuh -- one LONG pair spread over the whole GPU: the anti-diagonal wavefront of the
+// north star ("long-pair Smith-Waterman: 100 kb x 100 kb ... 32-bit scores, single-GPU intra-sequence
+// parallelism", BASELINE config C5).  Replaces the same upstream kernels as kern_gotoh32.cuh
+// (parasail_{nw,sg*,sw}_{striped,scan,diag}_{32,64,sat}, score + end cell) for pairs whose query is
+// thousands of residues long; results follow SURVEY.md Appendix A.
+//
+// The table is cut into horizontal strips of 32*K query rows.  A strip is swept left to right by
+// one warp exactly as in gotoh32_kernel (lane t owns K rows, column j = s - t, bottom row handed
+// down by __shfl_up: the in-warp anti-diagonal).  Strips are claimed in order from an atomic
+// counter by persistent warps that are all resident at once; strip b may start column chunk c as
+// soon as strip b-1 has published the bottom row (T, F) of that chunk to its boundary line in
+// global memory -- so the strips themselves form a second, coarser anti-diagonal wavefront across
+// the SMs.  Publication is a release-store of a column counter after a __threadfence; the consumer
+// polls it with an acquire-load.  Waiting is deadlock-free because a warp only ever waits for the
+// strip claimed immediately before its own, which belongs to a warp that is running or finished.
+#pragma once
+#include "psb_defs.h"
+#include "psb_simt.h"
+
+namespace psb {
+
+struct Wave32Params {
+    const uint8_t *q;        // mapped residues of the pair
+    const uint8_t *r;
+    int Lq, Lr;
+    const int *matrix;       // square, size*size
+    int size;
+    int open, gap;
+    int mode, s1_beg, s1_end, s2_beg, s2_end;
+    int *bnd;                // nstrips lines of 2*Lr ints: T (= H - open) then F of the strip's bottom row
+    int *progress;           // per strip: number of bottom-row columns published
+    int *next_strip;         // work counter
+    int *cand;               // per strip 8 ints: bestH, bestJ, bestI, colH, colI
+};
+
+inline size_t wave32_smem_bytes(int size, int warps) {
+    return (((size_t)size * size * sizeof(int) + 15) & ~(size_t)15) + (size_t)warps * (64 + 64 * 2 * sizeof(int));
+}
+
+#if !defined(PSB_EMULATE)
+PSB_DEV int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+PSB_DEV void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+PSB_DEV void backoff() { __nanosleep(64); }
+#else
+inline int ld_acquire(const int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release(int *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void backoff() {}
+#endif
+
+template <int K>
+PSB_KERNEL void wave32_kernel(Wave32Params p) {
+    PSB_SHARED_DECL(smem_raw);
+    const int lane = lane_id();
+    const int size = p.size, o = p.open, e = p.gap;
+    int *smat = (int *)smem_raw;
+    const size_t mat_bytes = (((size_t)size * size * sizeof(int)) + 15) & ~(size_t)15;
+    unsigned char *ring = smem_raw + mat_bytes + (size_t)warp_in_block() * (64 + 64 * 2 * sizeof(int));
+    int *ringT = (int *)ring, *ringF = ringT + 64;
+    uint8_t *ringL = (uint8_t *)(ringF + 64);
+    for (int x = thread_in_block(); x < size * size; x += threads_per_block()) smat[x] = p.matrix[x] + o;
+    sync_block();
+
+    const int mode = p.mode;
+    const bool is_sw = mode == MODE_SW;
+    const bool top_free = is_sw || (mode == MODE_SG && p.s1_beg);
+    const bool left_free = is_sw || (mode == MODE_SG && p.s2_beg);
+    const bool row_ends = mode == MODE_SG && p.s1_end;
+    const bool col_ends = mode == MODE_SG && p.s2_end;
+    const int Lq = p.Lq, Lr = p.Lr;
+    const int rows_per_strip = 32 * K;
+    const int nstrips = (Lq + rows_per_strip - 1) / rows_per_strip;
+    const int nsteps = Lr + 31;
+
+    for (;;) {
+        int strip = 0;
+        if (lane == 0) strip = atomic_add(p.next_strip, 1);
+        strip = shfl(strip, 0);
+        if (strip >= nstrips) break;
+        const bool last_strip = strip == nstrips - 1;
+        const int i0 = strip * rows_per_strip + lane * K;
+        int *bndT_in = p.bnd + (long long)(strip - 1) * 2 * Lr, *bndF_in = bndT_in + Lr;   // written by strip-1
+        int *bndT_out = p.bnd + (long long)strip * 2 * Lr, *bndF_out = bndT_out + Lr;
+        int T[K], E[K], rowbase[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = i0 + k;
+            rowbase[k] = i < Lq ? (int)p.q[i] * size : -1;
+            T[k] = (left_free ? 0 : -o - i * e) - o;
+            E[k] = NEG_INF32;
+        }
+        int Tdiag_in = (i0 == 0) ? -o : ((left_free ? 0 : -o - (i0 - 1) * e) - o);
+        int Tout = 0, Fout = NEG_INF32;
+        int bestH = NEG_INF32, bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
+        const int klast = (Lq - 1) - i0;
+
+        for (int s = 0; s < nsteps; ++s) {
+            if ((s & 31) == 0) {
+                // publish what lane 31 has finished (columns < s - 31), then wait for the strip above
+                sync_warp();
+                if (!last_strip && lane == 31 && s >= 32) {
+#if !defined(PSB_EMULATE)
+                    __threadfence();
+#endif
+                    st_release(p.progress + strip, s - 31);
+                }
+                const int need = (s + 32 < Lr) ? s + 32 : Lr;   // columns [s, need) are staged now
+                if (strip > 0 && s < Lr) {
+                    if (lane == 0) while (ld_acquire(p.progress + strip - 1) < need) backoff();
+                    sync_warp();
+                }
+                const int c = s + lane;
+                if (c < Lr) {
+                    ringL[c & 63] = p.r[c];
+                    if (strip > 0) { ringT[c & 63] = ld_cg(bndT_in + c); ringF[c & 63] = ld_cg(bndF_in + c); }
+                }
+                sync_warp();
+            }
+            const int j = s - lane;
+            int Tup = shfl_up(Tout, 1);
+            int Fup = shfl_up(Fout, 1);
+            const bool active = j >= 0 && j < Lr;
+            if (lane == 0 && active) {
+                if (strip == 0) { Tup = (top_free ? 0 : -o - j * e) - o; Fup = NEG_INF32; }
+                else { Tup = ringT[j & 63]; Fup = ringF[j & 63]; }
+            }
+            if (active) {
+                const int letter = (int)ringL[j & 63];
+                int Tu = Tup, Fu = Fup, Td = Tdiag_in;
+                int cmax = -0x7fffffff - 1;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int So = rowbase[k] < 0 ? PAD_SCORE : smat[rowbase[k] + letter];
+                    const int Tl = T[k];
+                    const int En = viaddmax(E[k], -e, Tl);
+                    const int Fn = viaddmax(Fu, -e, Tu);
+                    const int h = viaddmax(Td, So, En);
+                    const int H = is_sw ? vimax3(h, Fn, 0) : (h > Fn ? h : Fn);
+                    Td = Tl;
+                    const int Tn = H - o;
+                    T[k] = Tn; E[k] = En; Tu = Tn; Fu = Fn;
+                    if (is_sw) { const int key = H * 16 + (15 - k); cmax = cmax > key ? cmax : key; }
+                }
+                Tdiag_in = Tup; Tout = Tu; Fout = Fu;
+                if (lane == 31 && !last_strip) { st_cg(bndT_out + j, Tu); st_cg(bndF_out + j, Fu); }
+                if (is_sw) {
+                    const int ch = cmax >> 4;
+                    if (ch > bestH) { bestH = ch; bestJ = j; bestI = i0 + 15 - (cmax & 15); }
+                } else if (last_strip && klast >= 0 && klast < K && (row_ends || (j == Lr - 1 && !col_ends))) {
+                    int hv = 0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) if (k == klast) hv = T[k] + o;
+                    if (hv > bestH) { bestH = hv; bestJ = j; bestI = Lq - 1; }
+                }
+                if (col_ends && j == Lr - 1) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int hv = T[k] + o;
+                        if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
+                    }
+                }
+            }
+        }
+        // the whole bottom row is out
+        sync_warp();
+        if (!last_strip && lane == 31) {
+#if !defined(PSB_EMULATE)
+            __threadfence();
+#endif
+            st_release(p.progress + strip, Lr);
+        }
+        // merge the strip's lanes: (score desc, end_ref asc, end_query asc)
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const int oH = shfl_xor(bestH, m), oJ = shfl_xor(bestJ, m), oI = shfl_xor(bestI, m);
+            if (oH > bestH || (oH == bestH && (oJ < bestJ || (oJ == bestJ && oI < bestI)))) { bestH = oH; bestJ = oJ; bestI = oI; }
+            const int cH = shfl_xor(colH, m), cI = shfl_xor(colI, m);
+            if (cH > colH || (cH == colH && cI < colI)) { colH = cH; colI = cI; }
+        }
+        if (lane == 0) {
+            int *c = p.cand + strip * 8;
+            c[0] = bestH; c[1] = bestJ; c[2] = bestI; c[3] = colH; c[4] = colI;
+        }
+    }
+}
+
+// final pick over the per-strip candidates, same tie-breaks as the in-warp merge
+struct WaveReduceParams {
+    const int *cand;
+    int nstrips;
+    int mode, s1_end, s2_end;
+    int Lr;
+    int *score, *end_query, *end_ref;   // single outputs (already offset to the pair)
+};
+PSB_KERNEL void wave32_reduce_kernel(WaveReduceParams p) {
+    if (thread_in_block() != 0 || block_id() != 0) return;
+    int bestH = NEG_INF32, bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
+    for (int s = 0; s < p.nstrips; ++s) {
+        const int *c = p.cand + s * 8;
+        if (c[0] > bestH || (c[0] == bestH && (c[1] < bestJ || (c[1] == bestJ && c[2] < bestI)))) { bestH = c[0]; bestJ = c[1]; bestI = c[2]; }
+        if (c[3] > colH || (c[3] == colH && c[4] < colI)) { colH = c[3]; colI = c[4]; }
+    }
+    const bool row_ends = p.mode == MODE_SG && p.s1_end, col_ends = p.mode == MODE_SG && p.s2_end;
+    if (col_ends && (!row_ends || colH > bestH)) { bestH = colH; bestJ = p.Lr - 1; bestI = colI; }
+    if (p.mode == MODE_SW && bestH <= 0) { bestH = 0; bestJ = 0; bestI = 0; }
+    *p.score = bestH; *p.end_query = bestI; *p.end_ref = bestJ;
+}
+
+}  // namespace psb

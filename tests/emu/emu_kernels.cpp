@@ -52,3 +52,18 @@ extern "C" int emu_sw16(int K, const Sw16Params *pp, int nblocks) {
     return -1;
 }
 extern "C" int emu_sizeof_sw16() { return (int)sizeof(Sw16Params); }
+
+// ---- long-pair wavefront kernel -------------------------------------------------------------------
+#include "../../parasail_rs_b200/csrc/kern_wave32.cuh"
+
+extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams *rp, int nblocks) {
+    Wave32Params p = *pp;
+    size_t smem = wave32_smem_bytes(p.size, 1);
+#define WCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { wave32_kernel<KK>(p); }); break;
+    switch (K) { WCASE(1) WCASE(2) WCASE(4) WCASE(8) default: return -1; }
+    WaveReduceParams r = *rp;
+    emu::launch(1, 64, [&]() { wave32_reduce_kernel(r); });
+    return 0;
+}
+extern "C" int emu_sizeof_wave32() { return (int)sizeof(Wave32Params); }
+extern "C" int emu_sizeof_wavereduce() { return (int)sizeof(WaveReduceParams); }

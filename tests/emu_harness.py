@@ -145,3 +145,38 @@ def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1):
     rc = lib().emu_sw16(K.value, C.byref(p), nblocks)
     assert rc == 0, (rc, K.value)
     return outs, sorted(int(perm[i]) for i in retry[: retry_count[0]])
+
+
+class Wave32Params(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("r", C.c_void_p), ("Lq", C.c_int), ("Lr", C.c_int), ("matrix", C.c_void_p),
+                ("size", C.c_int), ("open", C.c_int), ("gap", C.c_int), ("mode", C.c_int), ("s1_beg", C.c_int),
+                ("s1_end", C.c_int), ("s2_beg", C.c_int), ("s2_end", C.c_int), ("bnd", C.c_void_p),
+                ("progress", C.c_void_p), ("next_strip", C.c_void_p), ("cand", C.c_void_p)]
+
+
+class WaveReduceParams(C.Structure):
+    _fields_ = [("cand", C.c_void_p), ("nstrips", C.c_int), ("mode", C.c_int), ("s1_end", C.c_int), ("s2_end", C.c_int),
+                ("Lr", C.c_int), ("score", C.c_void_p), ("end_query", C.c_void_p), ("end_ref", C.c_void_p)]
+
+
+def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1):
+    """Run the emulated long-pair wavefront kernel on one pair; returns (score, end_query, end_ref)."""
+    assert lib().emu_sizeof_wave32() == C.sizeof(Wave32Params) and lib().emu_sizeof_wavereduce() == C.sizeof(WaveReduceParams)
+    mapper = mat.mapper.astype(np.uint8)
+    qm = np.ascontiguousarray(mapper[np.asarray(q, dtype=np.uint8)])
+    rm = np.ascontiguousarray(mapper[np.asarray(r, dtype=np.uint8)])
+    table = np.ascontiguousarray(mat.table, dtype=np.int32)
+    nstrips = (len(qm) + 32 * K - 1) // (32 * K)
+    bnd = np.zeros(nstrips * 2 * len(rm) + 16, dtype=np.int32)
+    progress = np.zeros(nstrips + 1, dtype=np.int32)
+    nxt = np.zeros(1, dtype=np.int32)
+    cand = np.zeros(nstrips * 8 + 8, dtype=np.int32)
+    out = np.zeros(3, dtype=np.int32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    p = Wave32Params(ptr(qm), ptr(rm), len(qm), len(rm), ptr(table), mat.size, open, gap, mode, flags[0], flags[1], flags[2],
+                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand))
+    rp = WaveReduceParams(ptr(cand), nstrips, mode, flags[1], flags[3], len(rm), out.ctypes.data, out.ctypes.data + 4,
+                          out.ctypes.data + 8)
+    rc = lib().emu_wave32(K, C.byref(p), C.byref(rp), nblocks)
+    assert rc == 0
+    return int(out[0]), int(out[1]), int(out[2])

@@ -273,6 +273,23 @@ def test_config_c5_reduced(ps, oracle):
     assert got.get_score() > 3000
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_long_pair_wavefront(ps, oracle, mode):
+    # queries >= 2048 rows go to the multi-warp wavefront kernel: strips run concurrently on
+    # different SMs and hand their bottom rows over through global memory
+    m = oracle.Matrix.create(b"ACGT", 2, -3)
+    r = psb_data.random_seq(5101, 0, 9000, protein=False)
+    q = psb_data.mutate(r, 5101, 1, 0.10, 0.01, protein=False)[:8000]
+    got = builder(ps, mode, ps.Matrix.create(b"ACGT", 2, -3), 5, 2).solution_width(32).build().align(q, r)
+    exp = oracle.align(q, r, m, mode=mode, open=5, gap=2)
+    assert (got.get_score(), got.get_end_query(), got.get_end_ref()) == (exp["score"], exp["end_query"], exp["end_ref"])
+    # mixed batch: long pairs next to short ones
+    qs = [q, q[:100], q[:3000]]
+    rs = [r[:500], r[:300], r[:2500]]
+    gb = builder(ps, mode, ps.Matrix.create(b"ACGT", 2, -3), 5, 2).build().align_batch(qs, rs)
+    assert_same(gb, oracle_batch(oracle, qs, rs, m, mode, 5, 2), KEYS3, f"wave batch mode {mode}")
+
+
 def test_edge_cases(ps, oracle, blosum62):
     b62 = ps.Matrix.from_name("blosum62")
     # single residues, unknown letters (mapped to '*'), lower case
