@@ -166,7 +166,16 @@ static int class_of_len(int lq) {
 
 enum Variant { V_SCORE = 0, V_STATS32, V_STATS64, V_TRACE, V_TABLE };
 
-template <int K> static const void *gotoh32_fn_k(Variant v) {
+template <int K> static const void *gotoh32_fn_k(Variant v, bool prof) {
+    if (prof) {
+        switch (v) {
+            case V_SCORE: return (const void *)gotoh32_kernel<K, false, false, false, unsigned, true>;
+            case V_STATS32: return (const void *)gotoh32_kernel<K, true, false, false, unsigned, true>;
+            case V_STATS64: return (const void *)gotoh32_kernel<K, true, false, false, unsigned long long, true>;
+            case V_TRACE: return (const void *)gotoh32_kernel<K, false, true, false, unsigned, true>;
+            default: break;
+        }
+    }
     switch (v) {
         case V_SCORE: return (const void *)gotoh32_kernel<K, false, false, false, unsigned>;
         case V_STATS32: return (const void *)gotoh32_kernel<K, true, false, false, unsigned>;
@@ -176,28 +185,29 @@ template <int K> static const void *gotoh32_fn_k(Variant v) {
     }
     return nullptr;
 }
-static const void *gotoh32_fn(int K, Variant v) {
+static const void *gotoh32_fn(int K, Variant v, bool prof) {
     switch (K) {
-        case 1: return gotoh32_fn_k<1>(v);
-        case 2: return gotoh32_fn_k<2>(v);
-        case 4: return gotoh32_fn_k<4>(v);
-        case 6: return gotoh32_fn_k<6>(v);
-        case 8: return gotoh32_fn_k<8>(v);
-        case 10: return gotoh32_fn_k<10>(v);
-        case 12: return gotoh32_fn_k<12>(v);
-        case 16: return gotoh32_fn_k<16>(v);
+        case 1: return gotoh32_fn_k<1>(v, prof);
+        case 2: return gotoh32_fn_k<2>(v, prof);
+        case 4: return gotoh32_fn_k<4>(v, prof);
+        case 6: return gotoh32_fn_k<6>(v, prof);
+        case 8: return gotoh32_fn_k<8>(v, prof);
+        case 10: return gotoh32_fn_k<10>(v, prof);
+        case 12: return gotoh32_fn_k<12>(v, prof);
+        case 16: return gotoh32_fn_k<16>(v, prof);
     }
     return nullptr;
 }
 
 static constexpr int kWarpsPerBlock = 4;
 
-static int launch_gotoh32(int K, Variant v, Gotoh32Params &p, int nwork, long long *grid_warps_out = nullptr) {
+static int launch_gotoh32(int K, Variant v, Gotoh32Params &p, int nwork, bool prof, long long *grid_warps_out = nullptr) {
     Ctx &c = g_ctx;
-    const void *fn = gotoh32_fn(K, v);
+    if (v == V_TABLE) prof = false;
+    const void *fn = gotoh32_fn(K, v, prof);
     const bool stats = v == V_STATS32 || v == V_STATS64 || v == V_TABLE;
     const int statw = v == V_STATS32 ? 4 : 8;
-    const size_t smem = gotoh32_smem_bytes(p.is_pssm ? 0 : p.size, kWarpsPerBlock, stats, statw);
+    const size_t smem = gotoh32_smem_bytes(p.is_pssm ? 0 : p.size, kWarpsPerBlock, stats, statw, prof);
     if (smem > 200 * 1024) { set_error("substitution matrix too large for shared memory"); return PSB_EUNSUPPORTED; }
     if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -401,7 +411,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         p.n = (int)ids.size();
         p.counter = d_counter.as<int>() + cl;
         const Variant v = want_table ? V_TABLE : (want_trace ? V_TRACE : (cfg.stats ? (wide_stats ? V_STATS64 : V_STATS32) : V_SCORE));
-        PSB_TRY(launch_gotoh32(kClassK[cl], v, p, p.n));
+        PSB_TRY(launch_gotoh32(kClassK[cl], v, p, p.n, gotoh32_profile_ok(m.size, m.min, m.max, req.open, pssm)));
     }
 
     for (int id : wave_ids) {
@@ -752,7 +762,7 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     p.counter = d_counter.as<int>();
     p.out_map = db->d_perm;
     const Variant v = cfg.stats ? (wide ? V_STATS64 : V_STATS32) : V_SCORE;
-    PSB_TRY(launch_gotoh32(K, v, p, p.n));
+    PSB_TRY(launch_gotoh32(K, v, p, p.n, gotoh32_profile_ok(m.size, m.min, m.max, open, pssm)));
     return PSB_OK;
 }
 

@@ -62,13 +62,18 @@ template <> struct StatPack<unsigned long long> {  // 21 | 21 | 22 bits
     static constexpr unsigned long long MM = 0x1fffffull, SM = 0x1fffffull, LM = 0x3fffffull;
 };
 
-inline size_t gotoh32_smem_bytes(int size, int warps, bool stats, int statw) {
+// prof: each warp additionally keeps an int8 query profile [letter][lane][16 rows] of (S + open)
+inline size_t gotoh32_smem_bytes(int size, int warps, bool stats, int statw, bool prof = false) {
     size_t m = (size_t)size * (size_t)size * sizeof(int);
     size_t ring = 64 /*letters*/ + 64 * 2 * sizeof(int) + (stats ? 64 * 2 * (size_t)statw : 0);
-    return ((m + 15) & ~(size_t)15) + (size_t)warps * ((ring + 15) & ~(size_t)15);
+    return ((m + 15) & ~(size_t)15) + (size_t)warps * (((ring + 15) & ~(size_t)15) + (prof ? (size_t)size * 512 : 0));
+}
+// the per-warp profile needs S + open to fit a signed byte
+inline bool gotoh32_profile_ok(int size, int mat_min, int mat_max, int open, bool pssm) {
+    return !pssm && size <= 32 && open >= 0 && mat_max + open <= 127 && mat_min + open >= -127;
 }
 
-template <int K, bool STATS, bool TRACE, bool TABLE, typename SW_>
+template <int K, bool STATS, bool TRACE, bool TABLE, typename SW_, bool PROF = false>
 PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
     typedef SW_ SWord;
     typedef StatPack<SWord> SP;
@@ -82,7 +87,11 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
     int *smat = (int *)smem_raw;
     const size_t mat_bytes = square_in_smem ? ((((size_t)size * size * sizeof(int)) + 15) & ~(size_t)15) : 0;
     const size_t ring_bytes = ((64 + 64 * 2 * sizeof(int) + (STATS ? 64 * 2 * sizeof(SWord) : 0)) + 15) & ~(size_t)15;
-    unsigned char *ring = smem_raw + mat_bytes + (size_t)warp_in_block() * ring_bytes;
+    const size_t prof_bytes = PROF ? (size_t)size * 512 : 0;
+    unsigned char *ring = smem_raw + mat_bytes + (size_t)warp_in_block() * (ring_bytes + prof_bytes);
+    // PROF: int8 (S + open) of this lane's K rows for every reference letter, one 16-byte slot per
+    // (letter, lane): one conflict-free LDS.128 per step replaces K scattered matrix reads
+    unsigned char *wprof = ring + ring_bytes;
     int *ringT = (int *)ring;                 // boundary T (= H - o) of the strip above
     int *ringF = ringT + 64;                  // boundary F
     SWord *ringHs = (SWord *)(ringF + 64);    // boundary H stats
@@ -147,6 +156,22 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                 E[k] = NEG_INF32;
                 Hs[k] = 0; Es[k] = 0;
             }
+            if (PROF) {
+                sync_warp();
+                for (int a = 0; a < size; ++a) {
+                    unsigned wv[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};  // pad rows: -128
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (rowq[k] >= 0) {
+                            const unsigned b = (unsigned)smat[rowq[k] * size + a] & 0xffu;
+                            wv[k >> 2] = (wv[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (b << (8 * (k & 3)));
+                        }
+                    }
+                    uint4 v; v.x = wv[0]; v.y = wv[1]; v.z = wv[2]; v.w = wv[3];
+                    *(uint4 *)(wprof + ((size_t)a * 32 + lane) * 16) = v;
+                }
+                sync_warp();
+            }
             // H[i0-1][-1]: corner of the whole table for i0 == 0, else the left boundary above
             int Tdiag_in = (i0 == 0) ? -o : ((left_free ? 0 : -o - (i0 - 1) * e) - o);
             SWord Hsdiag_in = 0;
@@ -189,6 +214,11 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                 }
                 if (active) {
                     const int letter = (int)ringL[j & 63];
+                    unsigned pw[4] = {0, 0, 0, 0};
+                    if (PROF) {
+                        const uint4 v = *(const uint4 *)(wprof + ((size_t)letter * 32 + lane) * 16);
+                        pw[0] = v.x; pw[1] = v.y; pw[2] = v.z; pw[3] = v.w;
+                    }
                     int Tu = Tup, Fu = Fup, Td = Tdiag_in;
                     SWord Hsu = Hsup, Fsu = Fsup, Hsd = Hsdiag_in;
                     int cmax = -0x7fffffff - 1;  // sw: column max of H*16 + (15-k)
@@ -196,7 +226,12 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         int So;
-                        if (rowbase[k] < 0) So = PAD_SCORE;
+                        if (PROF) {
+                            // sign-extend byte k of the 16-byte profile slot
+                            const unsigned SEL = (unsigned)(k & 3) * 0x1111u + 0x8880u;
+                            So = (int)prmt(pw[k >> 2], 0u, SEL);
+                        }
+                        else if (rowbase[k] < 0) So = PAD_SCORE;
                         else if (square_in_smem) So = smat[rowbase[k] + letter];
                         else So = ld_ro(p.matrix + rowbase[k] + letter) + o;
                         const int Tl = T[k];

@@ -7,12 +7,16 @@
 
 using namespace psb;
 
+static bool g_prof = false;
 template <int K, bool STATS, bool TRACE, typename W>
 static void run32(const Gotoh32Params &p, int nblocks) {
-    size_t smem = gotoh32_smem_bytes(p.size, 1, STATS, sizeof(W));
+    size_t smem = gotoh32_smem_bytes(p.size, 1, STATS, sizeof(W), g_prof);
     if (p.tabH) emu::launch(nblocks, smem, [&]() { gotoh32_kernel<K, STATS, TRACE, true, W>(p); });
+    else if (g_prof) emu::launch(nblocks, smem, [&]() { gotoh32_kernel<K, STATS, TRACE, false, W, true>(p); });
     else emu::launch(nblocks, smem, [&]() { gotoh32_kernel<K, STATS, TRACE, false, W>(p); });
 }
+
+extern "C" void emu_gotoh32_use_profile(int on) { g_prof = on != 0; }
 
 extern "C" int emu_gotoh32(int K, int stats, int trace, int wide_stats, const Gotoh32Params *pp, int nblocks) {
     Gotoh32Params p = *pp;

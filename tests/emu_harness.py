@@ -50,7 +50,7 @@ def trace_to_rowmajor(blob, off, K, lq, lr):
 
 
 def gotoh32(qs, rs, mat, K, mode, open, gap, flags=(1, 1, 1, 1), stats=False, trace=False, wide=False,
-            shared_query=False, nblocks=1):
+            shared_query=False, nblocks=1, profile=False):
     """Run the emulated general kernel on pairs (lists of uint8 arrays of raw residues)."""
     assert lib().emu_sizeof_params() == C.sizeof(Gotoh32Params)
     mapper = mat.mapper.astype(np.uint8)
@@ -81,7 +81,9 @@ def gotoh32(qs, rs, mat, K, mode, open, gap, flags=(1, 1, 1, 1), stats=False, tr
                       ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(outs["matches"]),
                       ptr(outs["similar"]), ptr(outs["length"]), ptr(bnd), per_col * maxlr, ptr(blob),
                       ptr(trace_off), ptr(counter), None, None, None, None, None, None)
+    lib().emu_gotoh32_use_profile(int(profile))
     rc = lib().emu_gotoh32(K, int(stats), int(trace), int(wide), C.byref(p), nblocks)
+    lib().emu_gotoh32_use_profile(0)
     assert rc == 0
     if trace:
         outs["trace"] = [trace_to_rowmajor(blob, int(trace_off[i]), K, len(qm[0]) if shared_query else len(qm[i]), len(rm[i]))

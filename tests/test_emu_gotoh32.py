@@ -8,8 +8,8 @@ import psb_data
 from test_oracle_properties import SG_FLAGS, rand_pair
 
 
-def compare(oracle, mat, qs, rs, K, mode, o, e, flags=(1, 1, 1, 1), stats=False, trace=False, wide=False):
-    got = emu_harness.gotoh32(qs, rs, mat, K, mode, o, e, flags, stats, trace, wide)
+def compare(oracle, mat, qs, rs, K, mode, o, e, flags=(1, 1, 1, 1), stats=False, trace=False, wide=False, profile=False):
+    got = emu_harness.gotoh32(qs, rs, mat, K, mode, o, e, flags, stats, trace, wide, profile=profile)
     for i, (q, r) in enumerate(zip(qs, rs)):
         exp = oracle.align(q, r, mat, mode=mode, open=o, gap=e, s1_beg=flags[0], s1_end=flags[1],
                            s2_beg=flags[2], s2_end=flags[3], trace=trace)
@@ -74,3 +74,14 @@ def test_planted_ties(oracle):
     for mode in (0, 1, 2):
         compare(oracle, mat, qs, rs, 1, mode, 5, 2, stats=True)
         compare(oracle, mat, qs, rs, 2, mode, 0, 0)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("variant", ["score", "stats", "trace"])
+def test_per_warp_profile_variant(oracle, blosum62, mode, variant):
+    # the PROF=true instantiation (int8 per-warp query profile instead of matrix reads)
+    qs, rs = pairs(61, 3, (1, 150), (1, 80), True)
+    compare(oracle, blosum62, qs, rs, 3, mode, 10, 1, stats=variant == "stats", trace=variant == "trace", profile=True)
+    mat = oracle.Matrix.create(b"ACGT", 2, -3)
+    qs, rs = pairs(62, 3, (1, 90), (1, 90), False)
+    compare(oracle, mat, qs, rs, 2, mode, 0, 0, stats=variant == "stats", trace=variant == "trace", profile=True)
