@@ -157,44 +157,64 @@ static void fill_lut(unsigned *lut, const uint8_t *mapper) {
 }
 
 // ---- kernel dispatch --------------------------------------------------------------------------
-static const int kClassK[] = {1, 2, 4, 6, 8, 10, 12, 16};
-static constexpr int kNumClass = 8;
-static int class_of_len(int lq) {
-    for (int c = 0; c < kNumClass; ++c) if (lq <= 32 * kClassK[c]) return c;
-    return kNumClass - 1;
+// Two kernel families.  "fine": per-warp int8 profile, mode-specialised, 13 row-per-lane classes
+// (the many-pairs fast path).  "coarse": substitution matrix read directly (values that do not fit
+// a byte, PSSMs, table outputs), mode read at run time, 3 classes.
+static const int kFineK[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16};
+static const int kCoarseK[] = {4, 8, 16};
+static constexpr int kNumClass = 13;   // upper bound on classes of either family
+struct ClassTable { const int *k; int n; };
+static ClassTable class_table(bool fine) { return fine ? ClassTable{kFineK, 13} : ClassTable{kCoarseK, 3}; }
+static int class_of_len(const ClassTable &t, int lq) {
+    for (int c = 0; c < t.n; ++c) if (lq <= 32 * t.k[c]) return c;
+    return t.n - 1;
 }
 
 enum Variant { V_SCORE = 0, V_STATS32, V_STATS64, V_TRACE, V_TABLE };
 
-template <int K> static const void *gotoh32_fn_k(Variant v, bool prof) {
-    if (prof) {
-        switch (v) {
-            case V_SCORE: return (const void *)gotoh32_kernel<K, false, false, false, unsigned, true>;
-            case V_STATS32: return (const void *)gotoh32_kernel<K, true, false, false, unsigned, true>;
-            case V_STATS64: return (const void *)gotoh32_kernel<K, true, false, false, unsigned long long, true>;
-            case V_TRACE: return (const void *)gotoh32_kernel<K, false, true, false, unsigned, true>;
-            default: break;
-        }
+template <int K, int MS> static const void *gotoh32_fine_km(Variant v) {
+    switch (v) {
+        case V_SCORE: return (const void *)gotoh32_kernel<K, false, false, false, unsigned, true, MS>;
+        case V_STATS32: return (const void *)gotoh32_kernel<K, true, false, false, unsigned, true, MS>;
+        case V_STATS64: return (const void *)gotoh32_kernel<K, true, false, false, unsigned long long, true, MS>;
+        case V_TRACE: return (const void *)gotoh32_kernel<K, false, true, false, unsigned, true, MS>;
+        default: return nullptr;
     }
+}
+template <int K> static const void *gotoh32_fine_k(Variant v, bool sw) { return sw ? gotoh32_fine_km<K, 1>(v) : gotoh32_fine_km<K, 2>(v); }
+template <int K> static const void *gotoh32_coarse_k(Variant v) {
     switch (v) {
         case V_SCORE: return (const void *)gotoh32_kernel<K, false, false, false, unsigned>;
-        case V_STATS32: return (const void *)gotoh32_kernel<K, true, false, false, unsigned>;
+        case V_STATS32:
         case V_STATS64: return (const void *)gotoh32_kernel<K, true, false, false, unsigned long long>;
         case V_TRACE: return (const void *)gotoh32_kernel<K, false, true, false, unsigned>;
         case V_TABLE: return (const void *)gotoh32_kernel<K, true, false, true, unsigned long long>;
     }
     return nullptr;
 }
-static const void *gotoh32_fn(int K, Variant v, bool prof) {
+static const void *gotoh32_fn(int K, Variant v, bool fine, bool sw) {
+    if (!fine) {
+        switch (K) {
+            case 4: return gotoh32_coarse_k<4>(v);
+            case 8: return gotoh32_coarse_k<8>(v);
+            case 16: return gotoh32_coarse_k<16>(v);
+        }
+        return nullptr;
+    }
     switch (K) {
-        case 1: return gotoh32_fn_k<1>(v, prof);
-        case 2: return gotoh32_fn_k<2>(v, prof);
-        case 4: return gotoh32_fn_k<4>(v, prof);
-        case 6: return gotoh32_fn_k<6>(v, prof);
-        case 8: return gotoh32_fn_k<8>(v, prof);
-        case 10: return gotoh32_fn_k<10>(v, prof);
-        case 12: return gotoh32_fn_k<12>(v, prof);
-        case 16: return gotoh32_fn_k<16>(v, prof);
+        case 1: return gotoh32_fine_k<1>(v, sw);
+        case 2: return gotoh32_fine_k<2>(v, sw);
+        case 3: return gotoh32_fine_k<3>(v, sw);
+        case 4: return gotoh32_fine_k<4>(v, sw);
+        case 5: return gotoh32_fine_k<5>(v, sw);
+        case 6: return gotoh32_fine_k<6>(v, sw);
+        case 7: return gotoh32_fine_k<7>(v, sw);
+        case 8: return gotoh32_fine_k<8>(v, sw);
+        case 9: return gotoh32_fine_k<9>(v, sw);
+        case 10: return gotoh32_fine_k<10>(v, sw);
+        case 12: return gotoh32_fine_k<12>(v, sw);
+        case 14: return gotoh32_fine_k<14>(v, sw);
+        case 16: return gotoh32_fine_k<16>(v, sw);
     }
     return nullptr;
 }
@@ -203,8 +223,9 @@ static constexpr int kWarpsPerBlock = 4;
 
 static int launch_gotoh32(int K, Variant v, Gotoh32Params &p, int nwork, bool prof, long long *grid_warps_out = nullptr) {
     Ctx &c = g_ctx;
-    if (v == V_TABLE) prof = false;
-    const void *fn = gotoh32_fn(K, v, prof);
+    if (!prof && v == V_STATS32) v = V_STATS64;   // the coarse family carries only the wide statistics word
+    const void *fn = gotoh32_fn(K, v, prof, p.mode == MODE_SW);
+    if (!fn) { set_error("internal: no kernel for this class"); return PSB_EUNSUPPORTED; }
     const bool stats = v == V_STATS32 || v == V_STATS64 || v == V_TABLE;
     const int statw = v == V_STATS32 ? 4 : 8;
     const size_t smem = gotoh32_smem_bytes(p.is_pssm ? 0 : p.size, kWarpsPerBlock, stats, statw, prof);
@@ -281,6 +302,8 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     const int64_t q_lo = req.shared_query ? req.q_off[0] : req.q_off[lo];
     const int64_t q_hi = req.shared_query ? req.q_off[1] : req.q_off[hi];
     const int64_t r_lo = req.r_off[lo], r_hi = req.r_off[hi];
+    const bool fine = gotoh32_profile_ok(m.size, m.min, m.max, req.open, pssm) && !want_table;
+    const ClassTable ct = class_table(fine);
     std::vector<std::vector<int>> cls(kNumClass);
     std::vector<int> wave_ids;   // long score-only pairs: spread over the whole GPU one at a time
     int max_lr_multistrip = 0;
@@ -292,11 +315,11 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         const int lq = pssm ? m.length : (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + i + 1] - req.q_off[lo + i]);
         const int lr = (int)(req.r_off[lo + i + 1] - req.r_off[lo + i]);
         if (lq <= 0 || lr <= 0) { set_error("empty sequence in batch (pair " + std::to_string(lo + i) + ")"); return PSB_EINVAL; }
-        const int cl = class_of_len(lq);
+        const int cl = class_of_len(ct, lq);
         const bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !cfg.stats && !cfg.trace && !(req.extra && (cfg.table || cfg.rowcol));
         if (wave) { wave_ids.push_back((int)i); uniform = false; }
         else cls[cl].push_back((int)i);
-        if (!wave && lq > 32 * kClassK[cl]) max_lr_multistrip = std::max(max_lr_multistrip, lr);
+        if (!wave && lq > 32 * ct.k[cl]) max_lr_multistrip = std::max(max_lr_multistrip, lr);
         max_sum = std::max(max_sum, lq + lr);
         max_min = std::max(max_min, std::min(lq, lr));
         const long long cells = (long long)lq * lr;
@@ -363,7 +386,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         rev_off.resize(n);
         for (int cl = 0; cl < kNumClass; ++cl)
             for (int id : cls[cl]) {
-                const int K = kClassK[cl];
+                const int K = ct.k[cl];
                 const int lq = pssm ? m.length : (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + id + 1] - req.q_off[lo + id]);
                 const int lr = (int)(req.r_off[lo + id + 1] - req.r_off[lo + id]);
                 const long long strips = (lq + 32 * K - 1) / (32 * K);
@@ -411,7 +434,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         p.n = (int)ids.size();
         p.counter = d_counter.as<int>() + cl;
         const Variant v = want_table ? V_TABLE : (want_trace ? V_TRACE : (cfg.stats ? (wide_stats ? V_STATS64 : V_STATS32) : V_SCORE));
-        PSB_TRY(launch_gotoh32(kClassK[cl], v, p, p.n, gotoh32_profile_ok(m.size, m.min, m.max, req.open, pssm)));
+        PSB_TRY(launch_gotoh32(ct.k[cl], v, p, p.n, fine));
     }
 
     for (int id : wave_ids) {
@@ -439,7 +462,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             }
             WalkParams w;
             w.q = p.q; w.q_off = p.q_off; w.r = p.r; w.r_off = p.r_off; w.shared_query = p.shared_query;
-            w.ids = d_orders[cl].as<int>(); w.n = (int)cls[cl].size(); w.K = kClassK[cl];
+            w.ids = d_orders[cl].as<int>(); w.n = (int)cls[cl].size(); w.K = ct.k[cl];
             w.trace = p.trace; w.trace_off = p.trace_off; w.end_query = p.end_query; w.end_ref = p.end_ref;
             w.rev_ops = d_rev.as<unsigned>(); w.rev_off = d_revoff.as<long long>();
             w.nops = d_nops.as<int>(); w.beg_query = d_beg[0].as<int>(); w.beg_ref = d_beg[1].as<int>();
@@ -489,7 +512,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     // single-pair extras: row-major trace bytes, tables, last row / column
     if (req.extra && n == 1 && (want_trace || want_table)) {
         psb_result_extra *x = req.extra;
-        const int cl = first_cls, K = kClassK[cl];
+        const int cl = first_cls, K = ct.k[cl];
         const int lq = x->qlen, lr = x->rlen, nsteps = lr + 31;
         auto cell_index = [&](int i, int j) {
             const int strip = i / (32 * K), rem = i % (32 * K), lane = rem / K, k = rem % K;
@@ -600,7 +623,7 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
             while (hi < req.n) {
                 const int64_t lq = req.shared_query ? req.q_off[1] - req.q_off[0] : req.q_off[hi + 1] - req.q_off[hi];
                 const int64_t lr = req.r_off[hi + 1] - req.r_off[hi];
-                const int K = kClassK[class_of_len((int)std::min<int64_t>(lq, 1 << 20))];
+                const int K = 16;  // upper bound on rows per lane of any class
                 const int64_t need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);
                 if (hi > lo && bytes + need > budget) break;
                 bytes += need; ++hi;
@@ -738,8 +761,10 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     PSB_TRY(db_ensure_bytes(db));
     const HostMatrix &m = prof->matrix;
     const int lq = (int)prof->query.size();
-    const int cl = class_of_len(lq), K = kClassK[cl];
     const bool pssm = m.type == PARASAIL_MATRIX_TYPE_PSSM;
+    const bool fine = gotoh32_profile_ok(m.size, m.min, m.max, open, pssm);
+    const ClassTable ct = class_table(fine);
+    const int K = ct.k[class_of_len(ct, lq)];
     DevMem d_counter, d_bnd;
     PSB_TRY(d_counter.alloc(sizeof(int), c.stream));
     PSB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int), c.stream));
@@ -762,7 +787,7 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     p.counter = d_counter.as<int>();
     p.out_map = db->d_perm;
     const Variant v = cfg.stats ? (wide ? V_STATS64 : V_STATS32) : V_SCORE;
-    PSB_TRY(launch_gotoh32(K, v, p, p.n, gotoh32_profile_ok(m.size, m.min, m.max, open, pssm)));
+    PSB_TRY(launch_gotoh32(K, v, p, p.n, fine));
     return PSB_OK;
 }
 

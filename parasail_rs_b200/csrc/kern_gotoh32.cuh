@@ -73,7 +73,9 @@ inline bool gotoh32_profile_ok(int size, int mat_min, int mat_max, int open, boo
     return !pssm && size <= 32 && open >= 0 && mat_max + open <= 127 && mat_min + open >= -127;
 }
 
-template <int K, bool STATS, bool TRACE, bool TABLE, typename SW_, bool PROF = false>
+// MODESEL: 0 = alignment mode read at run time, 1 = local only, 2 = global / semi-global only
+// (the specialised forms drop the other mode's bookkeeping from the inner loop)
+template <int K, bool STATS, bool TRACE, bool TABLE, typename SW_, bool PROF = false, int MODESEL = 0>
 PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
     typedef SW_ SWord;
     typedef StatPack<SWord> SP;
@@ -103,7 +105,7 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
     sync_block();
 
     const int mode = p.mode;
-    const bool is_sw = mode == MODE_SW;
+    const bool is_sw = MODESEL == 1 ? true : (MODESEL == 2 ? false : mode == MODE_SW);
     const bool top_free = is_sw || (mode == MODE_SG && p.s1_beg);   // H[-1][j] = 0
     const bool left_free = is_sw || (mode == MODE_SG && p.s2_beg);  // H[i][-1] = 0
     const bool row_ends = mode == MODE_SG && p.s1_end;               // last row holds candidates
