@@ -33,6 +33,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side = nullptr;          // long subjects of a scan run here, beside the main kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sms = 0;
     double last_ms = 0.0;
     int launches = 0;
@@ -78,6 +80,11 @@ static int ensure_ctx() {
     if (!c.stream) c.stream = c.own_stream;
     PSB_CUDA(cudaEventCreate(&c.ev0));
     PSB_CUDA(cudaEventCreate(&c.ev1));
+    int lo_pri = 0, hi_pri = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+    PSB_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi_pri));
+    PSB_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    PSB_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     // keep freed stream-ordered allocations cached so repeated batches do not hit the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
@@ -249,6 +256,16 @@ static long long max_grid_warps() { return (long long)g_ctx.sms * 16 * kWarpsPer
 static constexpr int kWaveMinLq = 2048;   // below this the per-pair kernel is used
 
 template <int K> static const void *wave32_fn_k() { return (const void *)wave32_kernel<K>; }
+static const void *wave32_fn(int K) {
+    switch (K) {
+        case 1: return wave32_fn_k<1>();
+        case 2: return wave32_fn_k<2>();
+        case 4: return wave32_fn_k<4>();
+        case 8: return wave32_fn_k<8>();
+        case 16: return wave32_fn_k<16>();
+    }
+    return nullptr;
+}
 
 static int launch_wave32(const Gotoh32Params &g, long long q_byte_off, int lq, long long r_byte_off, int lr, int out_index) {
     Ctx &c = g_ctx;
@@ -266,6 +283,7 @@ static int launch_wave32(const Gotoh32Params &g, long long q_byte_off, int lq, l
     p.matrix = g.matrix; p.size = g.size; p.open = g.open; p.gap = g.gap;
     p.mode = g.mode; p.s1_beg = g.s1_beg; p.s1_end = g.s1_end; p.s2_beg = g.s2_beg; p.s2_end = g.s2_end;
     p.bnd = d_bnd.as<int>(); p.progress = d_ctl.as<int>() + 1; p.next_strip = d_ctl.as<int>(); p.cand = d_cand.as<int>();
+    p.multi_n = 0; p.r_off = nullptr;
     const size_t smem = wave32_smem_bytes(g.size, kWarpsPerBlock);
     if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -279,6 +297,7 @@ static int launch_wave32(const Gotoh32Params &g, long long q_byte_off, int lq, l
     WaveReduceParams r;
     r.cand = d_cand.as<int>(); r.nstrips = nstrips; r.mode = g.mode; r.s1_end = g.s1_end; r.s2_end = g.s2_end; r.Lr = lr;
     r.score = g.score + out_index; r.end_query = g.end_query + out_index; r.end_ref = g.end_ref + out_index;
+    r.multi_n = 0; r.r_off = nullptr; r.out_map = nullptr; r.first_id = 0;
     wave32_reduce_kernel<<<1, 32, 0, c.stream>>>(r);
     c.launches += 2;
     return PSB_OK;
@@ -648,6 +667,7 @@ struct psb_db {
     int msize = 0;
     int maxlen = 0;                 // longest subject
     int nlong = 0;                  // subjects longer than 65535 (sorted first)
+    std::vector<int> top_len;       // lengths of the (up to 4096) longest subjects, descending
     uint8_t mapper[256];
     unsigned *d_words = nullptr;
     long long *d_word_off = nullptr;  // n+1, sorted order (length descending, stable)
@@ -828,54 +848,140 @@ static const void *sw16_fn(int K) {
 
 static constexpr int kSw16WarpsPerBlock = 8;
 
-// packed 16-bit local scan of the whole database; subjects that leave the 16-bit range (and
-// subjects too long for 16-bit column indices) are re-run by the 32-bit kernel
+// packed 16-bit local scan of the whole database.  Subjects that leave the 16-bit range are
+// re-run by the 32-bit per-pair kernel; subjects too long for 16-bit column indices go to the
+// multi-pair wavefront kernel.  The sweep of one subject is serial in its length, and on an SM
+// shared by sixteen ALU-bound warps a step takes ~0.6 us, so the longest subjects of a shard
+// (7 000 aa in the UniProt-like distribution) bound the kernel at ~4 ms however small the shard
+// is -- what limits strong scaling at 8 GPUs.  Those few subjects ("head") are therefore swept by
+// a separate small launch of the same kernel, one warp per SM sub-partition on SMs it owns
+// outright, beside the main launch.
 static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, int open, int gap, psb_db *db,
                      int *const d_out[6], int64_t *n_retried) {
     Ctx &c = g_ctx;
     const Sw16Profile &sp = dp->sw16;
-    // sorted by length descending: the first `nlong` subjects exceed the 16-bit column range
-    const int64_t nlong = db->nlong;
+    const HostMatrix &m = prof->matrix;
+    const int lq = sp.lq;
+    // one group step costs ~0.6 us when the SM is full; keep a subject's sweep under ~40 % of the
+    // time the whole shard needs at ~4.9 TCUPS
+    const double est_ms = (double)lq * (double)db->residues / 4.9e9;
+    const double long_len = std::max(1024.0, 0.4 * est_ms / 0.62e-3);
+    int64_t nroute = 0;
+    while (nroute < (int64_t)db->top_len.size() && db->top_len[nroute] > 65535) ++nroute;
+    int64_t nhead = nroute;
+    while (nhead < (int64_t)db->top_len.size() && db->top_len[nhead] > long_len) ++nhead;
+    nhead = std::min<int64_t>(((nhead - nroute + 3) / 4) * 4, std::max<int64_t>(0, (db->n - nroute) / 8 / 4 * 4));
+    if (db->nlong > nroute) {
+        // more over-long subjects than the routed head covers: not a workload for the packed kernel
+        *n_retried = db->n;
+        return scan_general(cfg, prof, dp, open, gap, db, nullptr, 0, d_out);
+    }
     DevMem d_retry, d_cnt;
     PSB_TRY(d_retry.alloc(((size_t)db->n + 2) * sizeof(int), c.stream));
-    PSB_TRY(d_cnt.alloc(2 * sizeof(int), c.stream));
-    PSB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 2 * sizeof(int), c.stream));
-    if (nlong > 0) {
-        std::vector<int> ids(nlong);
-        std::iota(ids.begin(), ids.end(), 0);
-        PSB_CUDA(cudaMemcpyAsync(d_retry.p, ids.data(), (size_t)nlong * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-        const int nl = (int)nlong;
-        PSB_CUDA(cudaMemcpyAsync(d_cnt.as<int>(), &nl, sizeof(int), cudaMemcpyHostToDevice, c.stream));
-        PSB_CUDA(cudaStreamSynchronize(c.stream));
+    PSB_TRY(d_cnt.alloc(4 * sizeof(int), c.stream));
+    PSB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(int), c.stream));
+
+    DevMem d_lbytes, d_loff, d_bnd, d_ctl, d_cand;
+    if (nroute > 0) {
+        std::vector<long long> loff(nroute + 1);
+        loff[0] = 0;
+        for (int64_t i = 0; i < nroute; ++i) loff[i + 1] = loff[i] + db->top_len[i];
+        const int K = lq <= 64 ? 1 : 2;
+        const int nstrips = (lq + 32 * K - 1) / (32 * K);
+        PSB_TRY(d_lbytes.alloc((size_t)loff[nroute], c.stream));
+        PSB_TRY(d_loff.alloc((size_t)(nroute + 1) * sizeof(long long), c.stream));
+        PSB_TRY(d_bnd.alloc((size_t)nstrips * 2 * (size_t)loff[nroute] * sizeof(int), c.stream));
+        PSB_TRY(d_ctl.alloc(((size_t)nroute * nstrips + 2) * sizeof(int), c.stream));
+        PSB_TRY(d_cand.alloc((size_t)nroute * nstrips * 8 * sizeof(int), c.stream));
+        PSB_CUDA(cudaMemcpyAsync(d_loff.p, loff.data(), (size_t)(nroute + 1) * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+        PSB_CUDA(cudaMemsetAsync(d_ctl.p, 0, ((size_t)nroute * nstrips + 2) * sizeof(int), c.stream));
+        PSB_CUDA(cudaStreamSynchronize(c.stream));  // `loff` is a host temporary
+        PSB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+        PSB_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+        UnpackParams u;
+        u.words = db->d_words; u.word_off = db->d_word_off; u.ids = nullptr; u.out_off = d_loff.as<long long>();
+        u.out = d_lbytes.as<uint8_t>(); u.n = nroute; u.bits = db->bits;
+        unpack_db_kernel<<<(unsigned)std::min<int64_t>(nroute, 1024), 256, 0, c.side>>>(u);
+        Wave32Params w;
+        std::memset(&w, 0, sizeof(w));
+        w.q = dp->d_query; w.r = d_lbytes.as<uint8_t>(); w.Lq = lq; w.Lr = 0;
+        w.matrix = dp->d_matrix; w.size = m.size; w.open = open; w.gap = gap;
+        w.mode = cfg.mode; w.s1_beg = cfg.s1_beg; w.s1_end = cfg.s1_end; w.s2_beg = cfg.s2_beg; w.s2_end = cfg.s2_end;
+        w.bnd = d_bnd.as<int>(); w.next_strip = d_ctl.as<int>(); w.progress = d_ctl.as<int>() + 1; w.cand = d_cand.as<int>();
+        w.multi_n = (int)nroute; w.r_off = d_loff.as<long long>();
+        const void *fn = wave32_fn(K);
+        // Full-size CTAs that also reserve most of an SM's shared memory: the strips of the long
+        // subjects then own a few SMs outright instead of crawling beside sixteen ALU-bound warps
+        // of the main kernel on every SM (each of their steps is a serial dependency).  The main
+        // kernel's blocks that find no room start on those SMs as soon as the strips are done.
+        constexpr int kRouteWarps = 32;
+        const size_t smem = std::max<size_t>(wave32_smem_bytes(m.size, kRouteWarps), 160 * 1024);
+        PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // all warps of this launch must be resident together (strips wait on one another): one CTA
+        // per SM at most, issued before the main kernel so that its blocks are placed first
+        const long long items = nroute * nstrips;
+        long long blocks = std::min<long long>((items + kRouteWarps - 1) / kRouteWarps, (long long)c.sms);
+        void *args[] = {&w};
+        PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kRouteWarps * 32), args, smem, c.side));
+        WaveReduceParams r;
+        std::memset(&r, 0, sizeof(r));
+        r.cand = d_cand.as<int>(); r.nstrips = nstrips; r.mode = cfg.mode; r.s1_end = cfg.s1_end; r.s2_end = cfg.s2_end;
+        r.score = d_out[0]; r.end_query = d_out[1]; r.end_ref = d_out[2];
+        r.multi_n = (int)nroute; r.r_off = d_loff.as<long long>(); r.out_map = db->d_perm; r.first_id = 0;
+        wave32_reduce_kernel<<<(unsigned)((nroute + 127) / 128), 128, 0, c.side>>>(r);
+        PSB_CUDA(cudaEventRecord(c.ev_join, c.side));
+        c.launches += 3;
     }
-    const int64_t nshort = db->n - nlong;
+    const int64_t nshort = db->n - nroute;
     if (nshort > 0) {
         Sw16Params p;
         std::memset(&p, 0, sizeof(p));
         p.prof = sp.prof; p.nletters = sp.nletters; p.lq = sp.lq; p.open = open; p.gap = gap; p.max_score = sp.max_score;
-        p.words = db->d_words; p.word_off = db->d_word_off + nlong; p.len = db->d_len + nlong; p.bits = db->bits;
-        p.n = nshort; p.out_map = db->d_perm + nlong;
+        p.words = db->d_words; p.bits = db->bits;
         p.score = d_out[0]; p.end_query = d_out[1]; p.end_ref = d_out[2];
-        p.retry = d_retry.as<int>(); p.retry_count = d_cnt.as<int>(); p.sid_base = (int)nlong;
-        p.counter = d_cnt.as<int>() + 1; p.mul_one = 1u; p.mul_16 = 16u;
+        p.retry = d_retry.as<int>(); p.retry_count = d_cnt.as<int>();
+        p.mul_one = 1u; p.mul_16 = 16u;
         const void *fn = sw16_fn(sp.K);
         if (!fn) { set_error("sw16: no kernel for this query length"); return PSB_EUNSUPPORTED; }
         const size_t smem = sw16_smem_bytes(sp.nletters, sp.chunks, kSw16WarpsPerBlock);
-        if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem_excl = std::max<size_t>(sw16_smem_bytes(sp.nletters, sp.chunks, 4), 150 * 1024);
+        PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, smem_excl)));
         int per_sm = 0;
         PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSw16WarpsPerBlock * 32, smem));
         if (per_sm < 1) per_sm = 1;
-        const long long slots = ((nshort + 1) / 2 + 1) / 2;  // a warp takes two items (four subjects) at a time
-        long long blocks = std::min<long long>((slots + kSw16WarpsPerBlock - 1) / kSw16WarpsPerBlock, (long long)c.sms * per_sm);
-        if (blocks < 1) blocks = 1;
-        void *args[] = {&p};
-        PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kSw16WarpsPerBlock * 32), args, smem, c.stream));
-        c.launches++;
+        if (nhead > 0) {
+            // head: the longest subjects, 4 warps per CTA (one per sub-partition), each CTA alone on
+            // its SM (the shared-memory request keeps the main launch's CTAs away)
+            if (nroute == 0) {
+                PSB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+                PSB_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+            }
+            Sw16Params h = p;
+            h.word_off = db->d_word_off + nroute; h.len = db->d_len + nroute; h.n = nhead; h.out_map = db->d_perm + nroute;
+            h.sid_base = (int)nroute; h.counter = d_cnt.as<int>() + 2;
+            const long long hslots = (nhead / 2 + 1) / 2;
+            void *hargs[] = {&h};
+            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)((hslots + 3) / 4)), dim3(4 * 32), hargs, smem_excl, c.side));
+            PSB_CUDA(cudaEventRecord(c.ev_join, c.side));
+            c.launches++;
+        }
+        const int64_t nrest = nshort - nhead;
+        if (nrest > 0) {
+            p.word_off = db->d_word_off + nroute + nhead; p.len = db->d_len + nroute + nhead; p.n = nrest;
+            p.out_map = db->d_perm + nroute + nhead; p.sid_base = (int)(nroute + nhead); p.counter = d_cnt.as<int>() + 1;
+            const long long slots = ((nrest + 1) / 2 + 1) / 2;  // a warp takes two items (four subjects) at a time
+            long long blocks = std::min<long long>((slots + kSw16WarpsPerBlock - 1) / kSw16WarpsPerBlock, (long long)c.sms * per_sm);
+            if (blocks < 1) blocks = 1;
+            void *args[] = {&p};
+            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kSw16WarpsPerBlock * 32), args, smem, c.stream));
+            c.launches++;
+        }
     }
+    if (nroute > 0 || nhead > 0) PSB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
     int nretry = 0;
     PSB_CUDA(cudaMemcpyAsync(&nretry, d_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     PSB_CUDA(cudaStreamSynchronize(c.stream));
-    *n_retried = nretry;
+    *n_retried = nretry + nroute;   // subjects that did not come out of the packed 16-bit kernel
     if (nretry > 0) PSB_TRY(scan_general(cfg, prof, dp, open, gap, db, d_retry.as<int>(), nretry, d_out));
     return PSB_OK;
 }
@@ -996,6 +1102,9 @@ psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const
     if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
     if (stats[0] != 0) return fail("psb_db_create: " + std::to_string(stats[0]) + " empty or oversized subject(s)");
     db->maxlen = stats[1]; db->nlong = stats[2]; db->words = total_words;
+    db->top_len.resize((size_t)std::min<int64_t>(n, 4096));
+    ck(cudaMemcpyAsync(db->top_len.data(), db->d_len, db->top_len.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    ck(cudaStreamSynchronize(c.stream));
     ck(cudaMallocAsync(&db->d_words, (size_t)db->words * 4 + 64, c.stream));
     if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
     PackParams pp;

@@ -31,6 +31,11 @@ struct Wave32Params {
     int *progress;           // per strip: number of bottom-row columns published
     int *next_strip;         // work counter
     int *cand;               // per strip 8 ints: bestH, bestJ, bestI, colH, colI
+    // multi-pair form (database scans: one query against several long subjects in one launch):
+    // when multi_n > 0 the pair of item (subject s, strip b) is (q, r + r_off[s]) with Lr = r_len[s];
+    // bnd / progress / cand are laid out subject-major (bnd at 2 * nstrips * r_off[s] ints).
+    int multi_n;
+    const long long *r_off;  // multi_n + 1 byte offsets into r
 };
 
 inline size_t wave32_smem_bytes(int size, int warps) {
@@ -70,20 +75,29 @@ PSB_KERNEL void wave32_kernel(Wave32Params p) {
     const bool left_free = is_sw || (mode == MODE_SG && p.s2_beg);
     const bool row_ends = mode == MODE_SG && p.s1_end;
     const bool col_ends = mode == MODE_SG && p.s2_end;
-    const int Lq = p.Lq, Lr = p.Lr;
+    const int Lq = p.Lq;
     const int rows_per_strip = 32 * K;
     const int nstrips = (Lq + rows_per_strip - 1) / rows_per_strip;
-    const int nsteps = Lr + 31;
+    const int nitems = nstrips * (p.multi_n > 0 ? p.multi_n : 1);
 
     for (;;) {
-        int strip = 0;
-        if (lane == 0) strip = atomic_add(p.next_strip, 1);
-        strip = shfl(strip, 0);
-        if (strip >= nstrips) break;
+        int item = 0;
+        if (lane == 0) item = atomic_add(p.next_strip, 1);
+        item = shfl(item, 0);
+        if (item >= nitems) break;
+        // items are claimed in order, subject-major: strip b of a subject is always claimed after
+        // its strip b-1
+        const int subj = item / nstrips, strip = item - subj * nstrips;
+        const long long rbase = p.multi_n > 0 ? p.r_off[subj] : 0;
+        const int Lr = p.multi_n > 0 ? (int)(p.r_off[subj + 1] - rbase) : p.Lr;
+        const uint8_t *rseq = p.r + rbase;
+        const int nsteps = Lr + 31;
+        int *bnd0 = p.bnd + 2ll * nstrips * rbase;          // this subject's boundary lines
+        int *progress = p.progress + (long long)subj * nstrips;
         const bool last_strip = strip == nstrips - 1;
         const int i0 = strip * rows_per_strip + lane * K;
-        int *bndT_in = p.bnd + (long long)(strip - 1) * 2 * Lr, *bndF_in = bndT_in + Lr;   // written by strip-1
-        int *bndT_out = p.bnd + (long long)strip * 2 * Lr, *bndF_out = bndT_out + Lr;
+        int *bndT_in = bnd0 + (long long)(strip - 1) * 2 * Lr, *bndF_in = bndT_in + Lr;   // written by strip-1
+        int *bndT_out = bnd0 + (long long)strip * 2 * Lr, *bndF_out = bndT_out + Lr;
         int T[K], E[K], rowbase[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -105,16 +119,16 @@ PSB_KERNEL void wave32_kernel(Wave32Params p) {
 #if !defined(PSB_EMULATE)
                     __threadfence();
 #endif
-                    st_release(p.progress + strip, s - 31);
+                    st_release(progress + strip, s - 31);
                 }
                 const int need = (s + 32 < Lr) ? s + 32 : Lr;   // columns [s, need) are staged now
                 if (strip > 0 && s < Lr) {
-                    if (lane == 0) while (ld_acquire(p.progress + strip - 1) < need) backoff();
+                    if (lane == 0) while (ld_acquire(progress + strip - 1) < need) backoff();
                     sync_warp();
                 }
                 const int c = s + lane;
                 if (c < Lr) {
-                    ringL[c & 63] = p.r[c];
+                    ringL[c & 63] = rseq[c];
                     if (strip > 0) { ringT[c & 63] = ld_cg(bndT_in + c); ringF[c & 63] = ld_cg(bndF_in + c); }
                 }
                 sync_warp();
@@ -170,7 +184,7 @@ PSB_KERNEL void wave32_kernel(Wave32Params p) {
 #if !defined(PSB_EMULATE)
             __threadfence();
 #endif
-            st_release(p.progress + strip, Lr);
+            st_release(progress + strip, Lr);
         }
         // merge the strip's lanes: (score desc, end_ref asc, end_query asc)
 #pragma unroll
@@ -181,32 +195,40 @@ PSB_KERNEL void wave32_kernel(Wave32Params p) {
             if (cH > colH || (cH == colH && cI < colI)) { colH = cH; colI = cI; }
         }
         if (lane == 0) {
-            int *c = p.cand + strip * 8;
+            int *c = p.cand + (long long)item * 8;
             c[0] = bestH; c[1] = bestJ; c[2] = bestI; c[3] = colH; c[4] = colI;
         }
     }
 }
 
-// final pick over the per-strip candidates, same tie-breaks as the in-warp merge
+// final pick over the per-strip candidates, same tie-breaks as the in-warp merge.  One thread per
+// subject (a single pair is subject 0).
 struct WaveReduceParams {
     const int *cand;
     int nstrips;
     int mode, s1_end, s2_end;
-    int Lr;
-    int *score, *end_query, *end_ref;   // single outputs (already offset to the pair)
+    int Lr;                             // single pair
+    int *score, *end_query, *end_ref;   // outputs
+    int multi_n;                        // > 0: subject s writes at out_map[first_id + s], Lr from r_off
+    const long long *r_off;
+    const int *out_map;
+    int first_id;
 };
 PSB_KERNEL void wave32_reduce_kernel(WaveReduceParams p) {
-    if (thread_in_block() != 0 || block_id() != 0) return;
+    const int subj = block_id() * threads_per_block() + thread_in_block();
+    if (subj >= (p.multi_n > 0 ? p.multi_n : 1)) return;
+    const int Lr = p.multi_n > 0 ? (int)(p.r_off[subj + 1] - p.r_off[subj]) : p.Lr;
     int bestH = NEG_INF32, bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
     for (int s = 0; s < p.nstrips; ++s) {
-        const int *c = p.cand + s * 8;
+        const int *c = p.cand + ((long long)subj * p.nstrips + s) * 8;
         if (c[0] > bestH || (c[0] == bestH && (c[1] < bestJ || (c[1] == bestJ && c[2] < bestI)))) { bestH = c[0]; bestJ = c[1]; bestI = c[2]; }
         if (c[3] > colH || (c[3] == colH && c[4] < colI)) { colH = c[3]; colI = c[4]; }
     }
     const bool row_ends = p.mode == MODE_SG && p.s1_end, col_ends = p.mode == MODE_SG && p.s2_end;
-    if (col_ends && (!row_ends || colH > bestH)) { bestH = colH; bestJ = p.Lr - 1; bestI = colI; }
+    if (col_ends && (!row_ends || colH > bestH)) { bestH = colH; bestJ = Lr - 1; bestI = colI; }
     if (p.mode == MODE_SW && bestH <= 0) { bestH = 0; bestJ = 0; bestI = 0; }
-    *p.score = bestH; *p.end_query = bestI; *p.end_ref = bestJ;
+    const int o = p.multi_n > 0 ? (p.out_map ? p.out_map[p.first_id + subj] : p.first_id + subj) : 0;
+    p.score[o] = bestH; p.end_query[o] = bestI; p.end_ref[o] = bestJ;
 }
 
 }  // namespace psb

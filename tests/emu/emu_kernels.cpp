@@ -66,7 +66,7 @@ extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams 
 #define WCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { wave32_kernel<KK>(p); }); break;
     switch (K) { WCASE(1) WCASE(2) WCASE(4) WCASE(8) default: return -1; }
     WaveReduceParams r = *rp;
-    emu::launch(1, 64, [&]() { wave32_reduce_kernel(r); });
+    emu::launch((r.multi_n + 31) / 32 + (r.multi_n == 0), 64, [&]() { wave32_reduce_kernel(r); });
     return 0;
 }
 extern "C" int emu_sizeof_wave32() { return (int)sizeof(Wave32Params); }

@@ -153,12 +153,14 @@ class Wave32Params(C.Structure):
     _fields_ = [("q", C.c_void_p), ("r", C.c_void_p), ("Lq", C.c_int), ("Lr", C.c_int), ("matrix", C.c_void_p),
                 ("size", C.c_int), ("open", C.c_int), ("gap", C.c_int), ("mode", C.c_int), ("s1_beg", C.c_int),
                 ("s1_end", C.c_int), ("s2_beg", C.c_int), ("s2_end", C.c_int), ("bnd", C.c_void_p),
-                ("progress", C.c_void_p), ("next_strip", C.c_void_p), ("cand", C.c_void_p)]
+                ("progress", C.c_void_p), ("next_strip", C.c_void_p), ("cand", C.c_void_p), ("multi_n", C.c_int),
+                ("r_off", C.c_void_p)]
 
 
 class WaveReduceParams(C.Structure):
     _fields_ = [("cand", C.c_void_p), ("nstrips", C.c_int), ("mode", C.c_int), ("s1_end", C.c_int), ("s2_end", C.c_int),
-                ("Lr", C.c_int), ("score", C.c_void_p), ("end_query", C.c_void_p), ("end_ref", C.c_void_p)]
+                ("Lr", C.c_int), ("score", C.c_void_p), ("end_query", C.c_void_p), ("end_ref", C.c_void_p),
+                ("multi_n", C.c_int), ("r_off", C.c_void_p), ("out_map", C.c_void_p), ("first_id", C.c_int)]
 
 
 def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1):
@@ -176,9 +178,34 @@ def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1):
     out = np.zeros(3, dtype=np.int32)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     p = Wave32Params(ptr(qm), ptr(rm), len(qm), len(rm), ptr(table), mat.size, open, gap, mode, flags[0], flags[1], flags[2],
-                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand))
+                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand), 0, None)
     rp = WaveReduceParams(ptr(cand), nstrips, mode, flags[1], flags[3], len(rm), out.ctypes.data, out.ctypes.data + 4,
-                          out.ctypes.data + 8)
+                          out.ctypes.data + 8, 0, None, None, 0)
     rc = lib().emu_wave32(K, C.byref(p), C.byref(rp), nblocks)
     assert rc == 0
     return int(out[0]), int(out[1]), int(out[2])
+
+
+def wave32_multi(q, subjects, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1):
+    """Multi-pair form of the wavefront kernel: one query vs several subjects in one launch."""
+    mapper = mat.mapper.astype(np.uint8)
+    qm = np.ascontiguousarray(mapper[np.asarray(q, dtype=np.uint8)])
+    sm = [mapper[np.asarray(s, dtype=np.uint8)] for s in subjects]
+    rcat = np.ascontiguousarray(np.concatenate(sm))
+    roff = np.zeros(len(sm) + 1, dtype=np.int64); roff[1:] = np.cumsum([len(x) for x in sm])
+    table = np.ascontiguousarray(mat.table, dtype=np.int32)
+    n = len(sm)
+    nstrips = (len(qm) + 32 * K - 1) // (32 * K)
+    bnd = np.zeros(nstrips * 2 * int(roff[-1]) + 16, dtype=np.int32)
+    progress = np.zeros(n * nstrips + 1, dtype=np.int32)
+    nxt = np.zeros(1, dtype=np.int32)
+    cand = np.zeros(n * nstrips * 8 + 8, dtype=np.int32)
+    outs = [np.full(n, -777, dtype=np.int32) for _ in range(3)]
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    p = Wave32Params(ptr(qm), ptr(rcat), len(qm), 0, ptr(table), mat.size, open, gap, mode, flags[0], flags[1], flags[2],
+                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand), n, ptr(roff))
+    rp = WaveReduceParams(ptr(cand), nstrips, mode, flags[1], flags[3], 0, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), n,
+                          ptr(roff), None, 0)
+    rc = lib().emu_wave32(K, C.byref(p), C.byref(rp), nblocks)
+    assert rc == 0
+    return outs

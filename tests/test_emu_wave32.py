@@ -29,3 +29,15 @@ def test_wave_sg_flags(oracle, flags):
     exp = oracle.align(q, r, mat, mode=1, open=5, gap=2, s1_beg=flags[0], s1_end=flags[1], s2_beg=flags[2], s2_end=flags[3])
     got = emu_harness.wave32(q, r, mat, 1, 1, 5, 2, flags)
     assert got == (exp["score"], exp["end_query"], exp["end_ref"])
+
+
+def test_wave_multi_pair(oracle, blosum62):
+    # database-scan form: several subjects, strips of all of them in one work queue
+    q = psb_data.random_seq(5003, 0, 100)
+    subs = [psb_data.random_seq(5004, i, 40 + 25 * i) for i in range(4)]
+    subs[2] = np.concatenate([subs[2][:20], psb_data.mutate(q, 5005, 0, 0.1, 0.02)])
+    for mode in (0, 2):
+        got = emu_harness.wave32_multi(q, subs, blosum62, 1, mode, 10, 1)
+        for i, s in enumerate(subs):
+            exp = oracle.align(q, s, blosum62, mode=mode, open=10, gap=1)
+            assert (got[0][i], got[1][i], got[2][i]) == (exp["score"], exp["end_query"], exp["end_ref"]), (mode, i)
