@@ -284,6 +284,11 @@ void psb_db_free(psb_db_t *db);
  * with "_profile"; top_k > 0 additionally fills out->impl-side top-k (see psb_batch_topk). */
 int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const psb_db_t *db,
              psb_batch_t **out);
+/* the same scan for a database that lives in HOST memory (pinned or pageable): the residues are cut
+ * into pieces whose upload, device-side packing and scan are pipelined on two streams, so the
+ * host-to-device copy hides under the kernels.  Nothing stays resident afterwards. */
+int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
+                  const int64_t *off, int64_t n, psb_batch_t **out);
 /* indices (caller order) of the k best scores of a scan, ties by smaller index; host-side merge */
 int psb_batch_topk(const psb_batch_t *batch, int k, int64_t *idx_out, int *score_out);
 

@@ -595,6 +595,23 @@ class Aligner:
         return BatchResult(out)
 
 
+def _scan_host(self, subjects):
+    """the aligner's profile against a database held in HOST memory (psb_scan_host): upload,
+    device-side packing and scan are pipelined inside the call; nothing stays resident"""
+    if self._profile.is_null():
+        raise Panic("scan_host() needs an aligner built with .profile(...)")
+    cat, off = _concat(subjects)
+    out = C.POINTER(CBatch)()
+    rc_ = lib().psb_scan_host(self.fn_name.encode(), self._profile.inner, self.gap_open, self.gap_extend,
+                              cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(off) - 1, C.byref(out))
+    if rc_ != 0:
+        raise DeviceError(f"psb_scan_host failed ({rc_}): {last_error()}")
+    return BatchResult(out)
+
+
+Aligner.scan_host = _scan_host
+
+
 def shard_plan(offsets, n_shards):
     """residue-balanced assignment of subjects to GPUs (psb_shard_plan)"""
     off = np.ascontiguousarray(offsets, dtype=np.int64)

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libparasail_b200.so")
+# PSB_LIB_PATH selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PSB_LIB_PATH") or os.path.join(HERE, "libparasail_b200.so")
 
 
 class CMatrix(C.Structure):
@@ -61,7 +62,7 @@ ALL_SYMBOLS = (
      "parasail_traceback_generic", "parasail_nw_banded", "parasail_ssw", "parasail_ssw_init", "parasail_result_ssw_free",
      "psb_last_error", "psb_device_count", "psb_set_device", "psb_set_stream", "psb_synchronize", "psb_batch_free",
      "psb_align_pairs", "psb_db_create", "psb_db_count", "psb_db_residues", "psb_db_device_bytes", "psb_db_free",
-     "psb_scan", "psb_batch_topk", "psb_shard_plan", "psb_last_kernel_ms", "psb_last_launches", "psb_version"]
+     "psb_scan", "psb_scan_host", "psb_batch_topk", "psb_shard_plan", "psb_last_kernel_ms", "psb_last_launches", "psb_version"]
     + PROFILE_CREATORS
     + [f"parasail_result_get_{g}" for g in RESULT_INT_GETTERS + RESULT_ARRAY_GETTERS]
     + [f"parasail_result_is_{p}" for p in RESULT_PREDICATES])
@@ -157,6 +158,9 @@ def lib():
     L.psb_db_free.argtypes = [C.c_void_p]
     L.psb_scan.restype = C.c_int
     L.psb_scan.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.POINTER(CBatch))]
+    L.psb_scan_host.restype = C.c_int
+    L.psb_scan_host.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.POINTER(C.POINTER(CBatch))]
     L.psb_batch_topk.restype = C.c_int
     L.psb_batch_topk.argtypes = [C.POINTER(CBatch), C.c_int, C.c_void_p, C.c_void_p]
     L.psb_shard_plan.restype = C.c_int

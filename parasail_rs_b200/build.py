@@ -19,12 +19,14 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> parasail_rs_b200/libparasail_b200.so"""
-    if not force and not _stale():
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> parasail_rs_b200/libparasail_b200.so
+    (`defines`/`out` build tuning variants next to it, e.g. defines=["SW16_UNROLL=1"])"""
+    out = out or OUT
+    if out == OUT and not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -33,7 +35,7 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libparasail_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return OUT
+    return out
 
 
 def build_tools():

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -35,6 +36,8 @@ struct Ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t side = nullptr;          // long subjects of a scan run here, beside the main kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t copy = nullptr;          // host->device uploads of psb_scan_host, beside the kernels
+    cudaEvent_t ev_alloc = nullptr;
     int sms = 0;
     double last_ms = 0.0;
     int launches = 0;
@@ -85,6 +88,8 @@ static int ensure_ctx() {
     PSB_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi_pri));
     PSB_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     PSB_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    PSB_CUDA(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    PSB_CUDA(cudaEventCreateWithFlags(&c.ev_alloc, cudaEventDisableTiming));
     // keep freed stream-ordered allocations cached so repeated batches do not hit the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
@@ -730,16 +735,11 @@ static int get_dev_profile(const parasail_profile *prof, DevProfile **out) {
     return PSB_OK;
 }
 
-__global__ void db_lengths_kernel(const long long *off, long long n, int rpw, int *len, int *idx, long long *wcount, int *stats) {
+__global__ void db_lengths_kernel(const long long *off, long long n, int *len, int *idx) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
-        if (i == n) { wcount[n] = 0; break; }
-        const long long l = off[i + 1] - off[i];
-        len[i] = (int)l; idx[i] = (int)i;
-        wcount[i] = (l + rpw - 1) / rpw;
-        if (l <= 0 || l > 0x7fffffff) atomicAdd(&stats[0], 1);   // empty / absurd subjects
-        atomicMax(&stats[1], (int)(l > 0x7fffffff ? 0x7fffffff : l));
-        if (l > 65535) atomicAdd(&stats[2], 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        len[i] = (int)(off[i + 1] - off[i]);
+        idx[i] = (int)i;
     }
 }
 __global__ void db_wcount_sorted_kernel(const int *len_sorted, long long n, int rpw, long long *wcount) {
@@ -846,7 +846,7 @@ static const void *sw16_fn(int K) {
     return nullptr;
 }
 
-static constexpr int kSw16WarpsPerBlock = 8;
+static constexpr int kSw16WarpsPerBlock = SW16_WARPS_PER_BLOCK;
 
 // packed 16-bit local scan of the whole database.  Subjects that leave the 16-bit range are
 // re-run by the 32-bit per-pair kernel; subjects too long for 16-bit column indices go to the
@@ -1048,12 +1048,27 @@ int psb_align_pairs(const char *fn_name, const parasail_matrix_t *matrix, int op
     return rc;
 }
 
-psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const parasail_matrix_t *matrix) {
-    if (!cat || !off || n <= 0 || !matrix) { set_error("psb_db_create: NULL argument or empty database"); return nullptr; }
-    if (n > 0x7ffffffe) { set_error("psb_db_create: more than 2^31-2 subjects"); return nullptr; }
-    if (ensure_ctx() != PSB_OK) return nullptr;
+}  // extern "C"
+
+namespace psb {
+
+// Database construction in two phases so that psb_scan_host can overlap the upload of one piece with
+// the scan of the previous one.  Phase A (db_begin): one host pass over the offsets (validation,
+// longest lengths, packed size), device allocations, and the host->device copies on `up` (the
+// caller's stream or the context's copy stream).  Phase B (db_finish): lengths, stable radix sort
+// by decreasing length, word offsets (scan), residue mapping + bit packing, all on the compute
+// stream and without any host synchronisation.
+struct DbBuild {
+    psb_db *db = nullptr;
+    DevMem d_raw, d_off, d_len0, d_idx0, d_wcount, d_tmp;
+    cudaEvent_t uploaded = nullptr;
+    long long raw_base = 0;
+    unsigned lut[64];
+    ~DbBuild() { if (uploaded) cudaEventDestroy(uploaded); }
+};
+
+static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int64_t n, const HostMatrix &hm, bool use_copy_stream) {
     Ctx &c = g_ctx;
-    HostMatrix hm(matrix);
     if (hm.size > 32) { set_error("psb_db_create: alphabets above 32 letters cannot be 5-bit packed"); return nullptr; }
     psb_db *db = new psb_db();
     db->device = c.device; db->stream = c.stream; db->n = n; db->msize = hm.size;
@@ -1065,57 +1080,99 @@ psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const
         set_error(what);
         cudaStreamSynchronize(c.stream);
         psb_db_free(db);
-        return (psb_db_t *)nullptr;
+        return (psb_db *)nullptr;
     };
-    if (db->residues <= 0) return fail("psb_db_create: offsets are not increasing");
-    // everything below runs on the device: lengths, stable sort by decreasing length (radix sort),
-    // word offsets (scan), residue mapping + bit packing.  The host only touches off[0] and off[n].
-    DevMem d_raw, d_off, d_len0, d_idx0, d_wcount, d_stats, d_tmp;
+    // host pass: validation, histogram of lengths (for the longest few), exact packed size
+    std::vector<int> hist(65537, 0);
+    std::vector<int> huge;   // lengths above 65535
+    long long words = 0;
+    int maxlen = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t l = off[i + 1] - off[i];
+        if (l <= 0 || l > 0x7fffffff) return fail("psb_db_create: empty or oversized subject " + std::to_string(i));
+        words += (l + rpw - 1) / rpw;
+        if (l > 65535) huge.push_back((int)l); else hist[(size_t)l]++;
+        if (l > maxlen) maxlen = (int)l;
+    }
+    std::sort(huge.begin(), huge.end(), [](int a, int b2) { return a > b2; });
+    db->maxlen = maxlen; db->nlong = (int)huge.size(); db->words = words;
+    db->top_len = huge;
+    if (db->top_len.size() > 4096) db->top_len.resize(4096);
+    for (int l = 65535; l >= 1 && db->top_len.size() < 4096; --l)
+        for (int t = 0; t < hist[l] && db->top_len.size() < 4096; ++t) db->top_len.push_back(l);
+
     const size_t n1 = (size_t)n + 1;
-    if (d_raw.alloc((size_t)db->residues, c.stream) != PSB_OK || d_off.alloc(n1 * 8, c.stream) != PSB_OK ||
-        d_len0.alloc((size_t)n * 4, c.stream) != PSB_OK || d_idx0.alloc((size_t)n * 4, c.stream) != PSB_OK ||
-        d_wcount.alloc(n1 * 8, c.stream) != PSB_OK || d_stats.alloc(16, c.stream) != PSB_OK)
+    if (B.d_raw.alloc((size_t)db->residues, c.stream) != PSB_OK || B.d_off.alloc(n1 * 8, c.stream) != PSB_OK ||
+        B.d_len0.alloc((size_t)n * 4, c.stream) != PSB_OK || B.d_idx0.alloc((size_t)n * 4, c.stream) != PSB_OK ||
+        B.d_wcount.alloc(n1 * 8, c.stream) != PSB_OK)
         return fail(psb_last_error());
     cudaError_t e = cudaSuccess;
     auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     ck(cudaMallocAsync(&db->d_word_off, n1 * 8, c.stream));
     ck(cudaMallocAsync(&db->d_perm, (size_t)n * 4, c.stream));
     ck(cudaMallocAsync(&db->d_len, (size_t)n * 4, c.stream));
-    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
-    ck(cudaMemcpyAsync(d_off.p, off, n1 * 8, cudaMemcpyHostToDevice, c.stream));
-    ck(cudaMemcpyAsync(d_raw.p, cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, c.stream));
-    ck(cudaMemsetAsync(d_stats.p, 0, 16, c.stream));
-    db_lengths_kernel<<<c.sms * 4, 256, 0, c.stream>>>(d_off.as<long long>(), n, rpw, d_len0.as<int>(), d_idx0.as<int>(),
-                                                      d_wcount.as<long long>(), d_stats.as<int>());
-    size_t tb = 0, tb2 = 0;
-    ck(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, d_len0.as<int>(), db->d_len, d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
-    ck(cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
-    if (d_tmp.alloc(std::max(tb, tb2), c.stream) != PSB_OK) return fail(psb_last_error());
-    ck(cub::DeviceRadixSort::SortPairsDescending(d_tmp.p, tb, d_len0.as<int>(), db->d_len, d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
-    db_wcount_sorted_kernel<<<c.sms * 4, 256, 0, c.stream>>>(db->d_len, n, rpw, d_wcount.as<long long>());
-    ck(cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
-    int stats[4] = {0, 0, 0, 0};
-    long long total_words = 0;
-    ck(cudaMemcpyAsync(stats, d_stats.p, 16, cudaMemcpyDeviceToHost, c.stream));
-    ck(cudaMemcpyAsync(&total_words, db->d_word_off + n, 8, cudaMemcpyDeviceToHost, c.stream));
-    ck(cudaStreamSynchronize(c.stream));
-    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
-    if (stats[0] != 0) return fail("psb_db_create: " + std::to_string(stats[0]) + " empty or oversized subject(s)");
-    db->maxlen = stats[1]; db->nlong = stats[2]; db->words = total_words;
-    db->top_len.resize((size_t)std::min<int64_t>(n, 4096));
-    ck(cudaMemcpyAsync(db->top_len.data(), db->d_len, db->top_len.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    ck(cudaStreamSynchronize(c.stream));
     ck(cudaMallocAsync(&db->d_words, (size_t)db->words * 4 + 64, c.stream));
     if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
+    cudaStream_t up = c.stream;
+    if (use_copy_stream) {
+        // the staging buffers come from the compute stream's pool: order the copies after the allocations
+        ck(cudaEventRecord(c.ev_alloc, c.stream));
+        ck(cudaStreamWaitEvent(c.copy, c.ev_alloc, 0));
+        up = c.copy;
+    }
+    ck(cudaMemcpyAsync(B.d_off.p, off, n1 * 8, cudaMemcpyHostToDevice, up));
+    ck(cudaMemcpyAsync(B.d_raw.p, cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, up));
+    if (use_copy_stream) {
+        ck(cudaEventCreateWithFlags(&B.uploaded, cudaEventDisableTiming));
+        ck(cudaEventRecord(B.uploaded, up));
+    }
+    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
+    B.db = db; B.raw_base = off[0];
+    fill_lut(B.lut, hm.mapper);
+    return db;
+}
+
+static int db_finish(DbBuild &B) {
+    Ctx &c = g_ctx;
+    psb_db *db = B.db;
+    const int64_t n = db->n;
+    const size_t n1 = (size_t)n + 1;
+    const int rpw = db->bits == 2 ? 16 : 6;
+    if (B.uploaded) PSB_CUDA(cudaStreamWaitEvent(c.stream, B.uploaded, 0));
+    db_lengths_kernel<<<c.sms * 4, 256, 0, c.stream>>>(B.d_off.as<long long>(), n, B.d_len0.as<int>(), B.d_idx0.as<int>());
+    size_t tb = 0, tb2 = 0;
+    PSB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, B.d_len0.as<int>(), db->d_len, B.d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, B.d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
+    PSB_TRY(B.d_tmp.alloc(std::max(tb, tb2), c.stream));
+    PSB_CUDA(cub::DeviceRadixSort::SortPairsDescending(B.d_tmp.p, tb, B.d_len0.as<int>(), db->d_len, B.d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
+    db_wcount_sorted_kernel<<<c.sms * 4, 256, 0, c.stream>>>(db->d_len, n, rpw, B.d_wcount.as<long long>());
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(B.d_tmp.p, tb2, B.d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
     PackParams pp;
-    pp.raw = d_raw.as<uint8_t>(); pp.raw_off = d_off.as<long long>(); pp.raw_base = off[0]; pp.perm = db->d_perm;
+    pp.raw = B.d_raw.as<uint8_t>(); pp.raw_off = B.d_off.as<long long>(); pp.raw_base = B.raw_base; pp.perm = db->d_perm;
     pp.word_off = db->d_word_off; pp.words = db->d_words; pp.n = n; pp.bits = db->bits;
-    fill_lut(pp.lut, hm.mapper);
+    std::memcpy(pp.lut, B.lut, sizeof(pp.lut));
     pack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(pp);
-    c.launches += 6;
+    c.launches += 5;
+    PSB_CUDA(cudaGetLastError());
     // no synchronisation: later work on this stream is ordered after the packing kernel, and the
-    // staging buffers are returned to the pool in stream order
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail(std::string("database packing: ") + cudaGetErrorString(e));
+    // staging buffers go back to the pool in stream order when B is destroyed
+    return PSB_OK;
+}
+
+}  // namespace psb
+
+extern "C" {
+
+psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const parasail_matrix_t *matrix) {
+    if (!cat || !off || n <= 0 || !matrix) { set_error("psb_db_create: NULL argument or empty database"); return nullptr; }
+    if (n > 0x7ffffffe) { set_error("psb_db_create: more than 2^31-2 subjects"); return nullptr; }
+    if (off[n] <= off[0]) { set_error("psb_db_create: offsets are not increasing"); return nullptr; }
+    if (ensure_ctx() != PSB_OK) return nullptr;
+    HostMatrix hm(matrix);
+    DbBuild B;
+    psb_db *db = db_begin(B, cat, off, n, hm, false);
+    if (!db) return nullptr;
+    if (db_finish(B) != PSB_OK) { cudaStreamSynchronize(g_ctx.stream); psb_db_free(db); return nullptr; }
     return db;
 }
 
@@ -1136,12 +1193,50 @@ void psb_db_free(psb_db_t *db) {
     delete db;
 }
 
+}  // extern "C"
+
+namespace psb {
+// one scan of a resident database; per-subject results are copied to hosts[k] + host_base
+static int scan_core(const FnConfig &cfg, const parasail_profile *profile, int open, int gap, psb_db *db, int *const hosts[6],
+                     int64_t host_base, int64_t *retried) {
+    Ctx &c = g_ctx;
+    DevProfile *dp = nullptr;
+    PSB_TRY(get_dev_profile(profile, &dp));
+    DevMem d_out[6];
+    int *outp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const int nout = cfg.stats ? 6 : 3;
+    for (int k = 0; k < nout; ++k) { PSB_TRY(d_out[k].alloc((size_t)db->n * sizeof(int), c.stream)); outp[k] = d_out[k].as<int>(); }
+    PSB_CUDA(cudaEventRecord(c.ev0, c.stream));
+    const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 && sw16_prepare(profile, dp, open, gap);
+    int rc;
+    *retried = 0;
+    if (fast) rc = scan_sw16(cfg, profile, dp, open, gap, db, outp, retried);
+    else rc = scan_general(cfg, profile, dp, open, gap, db, nullptr, 0, outp);
+    if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); return rc; }
+    PSB_CUDA(cudaEventRecord(c.ev1, c.stream));
+    for (int k = 0; k < nout; ++k)
+        PSB_CUDA(cudaMemcpyAsync(hosts[k] + host_base, d_out[k].p, (size_t)db->n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) { set_error(std::string("psb_scan: ") + cudaGetErrorString(e)); return PSB_ECUDA; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_ms += ms;
+    return PSB_OK;
+}
+static int scan_check(const char *who, const char *fn_name, const parasail_profile_t *profile, FnConfig *cfg) {
+    if (!parse_fn_name(fn_name, cfg) || !cfg->profile) { set_error(std::string(who) + ": not a profile function name: " + (fn_name ? fn_name : "(null)")); return PSB_EINVAL; }
+    if (!profile) { set_error(std::string(who) + ": NULL profile"); return PSB_EINVAL; }
+    if (cfg->trace || cfg->table || cfg->rowcol) { set_error(std::string(who) + ": trace/table/rowcol outputs are not available for database scans"); return PSB_EUNSUPPORTED; }
+    return PSB_OK;
+}
+}  // namespace psb
+
+extern "C" {
+
 int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const psb_db_t *db_c, psb_batch_t **out) {
     if (out) *out = nullptr;
     FnConfig cfg;
-    if (!parse_fn_name(fn_name, &cfg) || !cfg.profile) { set_error(std::string("psb_scan: not a profile function name: ") + (fn_name ? fn_name : "(null)")); return PSB_EINVAL; }
-    if (!profile || !db_c || !out) { set_error("psb_scan: NULL argument"); return PSB_EINVAL; }
-    if (cfg.trace || cfg.table || cfg.rowcol) { set_error("psb_scan: trace/table/rowcol outputs are not available for database scans"); return PSB_EUNSUPPORTED; }
+    PSB_TRY(scan_check("psb_scan", fn_name, profile, &cfg));
+    if (!db_c || !out) { set_error("psb_scan: NULL argument"); return PSB_EINVAL; }
     psb_db *db = const_cast<psb_db *>(db_c);
     PSB_TRY(ensure_ctx());
     Ctx &c = g_ctx;
@@ -1151,38 +1246,67 @@ int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, i
         return PSB_EINVAL;
     }
     c.last_ms = 0.0; c.launches = 0;
-    DevProfile *dp = nullptr;
-    PSB_TRY(get_dev_profile(profile, &dp));
     psb_batch_t *b = new_batch(db->n, cfg);
     if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
-    const int lq = (int)profile->query.size();
-    b->cells = (double)lq * (double)db->residues;
-    DevMem d_out[6];
-    int *outp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    const int nout = cfg.stats ? 6 : 3;
-    int rc = PSB_OK;
-    for (int k = 0; k < nout && rc == PSB_OK; ++k) { rc = d_out[k].alloc((size_t)db->n * sizeof(int), c.stream); outp[k] = d_out[k].as<int>(); }
-    if (rc == PSB_OK) rc = cudaEventRecord(c.ev0, c.stream) == cudaSuccess ? PSB_OK : PSB_ECUDA;
-    if (rc == PSB_OK) {
-        const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 &&
-                          sw16_prepare(profile, dp, open, gap);
-        if (fast) {
-            int64_t retried = 0;
-            rc = scan_sw16(cfg, profile, dp, open, gap, db, outp, &retried);
-            b->n_retried = retried;
-        } else {
-            rc = scan_general(cfg, profile, dp, open, gap, db, nullptr, 0, outp);
-        }
-    }
-    if (rc == PSB_OK && cudaEventRecord(c.ev1, c.stream) != cudaSuccess) rc = PSB_ECUDA;
+    b->cells = (double)profile->query.size() * (double)db->residues;
     int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
-    for (int k = 0; k < nout && rc == PSB_OK; ++k)
-        if (cudaMemcpyAsync(hosts[k], d_out[k].p, (size_t)db->n * sizeof(int), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) rc = PSB_ECUDA;
-    cudaError_t e = cudaStreamSynchronize(c.stream);
-    if (rc == PSB_OK && e != cudaSuccess) { set_error(std::string("psb_scan: ") + cudaGetErrorString(e)); rc = PSB_ECUDA; }
+    int64_t retried = 0;
+    const int rc = scan_core(cfg, profile, open, gap, db, hosts, 0, &retried);
     if (rc != PSB_OK) { free_batch(b); return rc; }
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_ms = ms;
+    b->n_retried = retried;
+    *out = b;
+    return PSB_OK;
+}
+
+int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
+                  const int64_t *off, int64_t n, psb_batch_t **out) {
+    if (out) *out = nullptr;
+    FnConfig cfg;
+    PSB_TRY(scan_check("psb_scan_host", fn_name, profile, &cfg));
+    if (!cat || !off || n <= 0 || !out || off[n] <= off[0]) { set_error("psb_scan_host: NULL argument or empty database"); return PSB_EINVAL; }
+    if (n > 0x7ffffffe) { set_error("psb_scan_host: more than 2^31-2 subjects"); return PSB_EUNSUPPORTED; }
+    PSB_TRY(ensure_ctx());
+    Ctx &c = g_ctx;
+    c.last_ms = 0.0; c.launches = 0;
+    const HostMatrix &hm = profile->matrix;
+    // a few large pieces: the upload of piece k+1 (copy stream) runs under the scan of piece k.  Every
+    // piece pays the scan kernel's ramp-up and tail once, so pieces are kept big (192 MB of residues
+    // by default; PSB_SCAN_HOST_PIECE_MB overrides it for experiments).
+    const int64_t total = off[n] - off[0];
+    long long piece_mb = 192;
+    if (const char *ev = std::getenv("PSB_SCAN_HOST_PIECE_MB")) piece_mb = std::max(8ll, std::atoll(ev));
+    const int64_t piece = piece_mb << 20;
+    const int npieces = (int)std::max<int64_t>(1, std::min<int64_t>(32, std::min<int64_t>(n, (total + piece * 3 / 4) / piece)));
+    std::vector<int64_t> cut(npieces + 1, n);
+    cut[0] = 0;
+    for (int k = 1; k < npieces; ++k) {
+        const int64_t target = off[0] + total * k / npieces;
+        cut[k] = std::lower_bound(off, off + n + 1, target) - off;
+        if (cut[k] <= cut[k - 1]) cut[k] = std::min<int64_t>(n, cut[k - 1] + 1);
+    }
+    psb_batch_t *b = new_batch(n, cfg);
+    if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
+    b->cells = (double)profile->query.size() * (double)total;
+    int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
+    int rc = PSB_OK;
+    std::vector<DbBuild> builds(npieces);
+    auto begin = [&](int k) -> int {
+        if (cut[k + 1] <= cut[k]) return PSB_OK;
+        return db_begin(builds[k], cat, off + cut[k], cut[k + 1] - cut[k], hm, true) ? PSB_OK : PSB_ECUDA;
+    };
+    rc = begin(0);
+    for (int k = 0; k < npieces && rc == PSB_OK; ++k) {
+        if (!builds[k].db) continue;
+        rc = db_finish(builds[k]);
+        if (rc == PSB_OK && k + 1 < npieces) rc = begin(k + 1);   // enqueue the next upload before this scan blocks
+        int64_t retried = 0;
+        if (rc == PSB_OK) rc = scan_core(cfg, profile, open, gap, builds[k].db, hosts, cut[k], &retried);
+        b->n_retried += retried;
+    }
+    cudaStreamSynchronize(c.copy);
+    cudaStreamSynchronize(c.stream);
+    for (auto &B : builds) if (B.db) psb_db_free(B.db);
+    if (rc != PSB_OK) { free_batch(b); return rc; }
     *out = b;
     return PSB_OK;
 }

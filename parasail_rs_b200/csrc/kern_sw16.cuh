@@ -117,8 +117,23 @@ PSB_DEV unsigned sw16_fetch_code(const unsigned *words, long long w0, int len, i
     return (words[w0 + w] >> (5 * (c - 6 * w))) & 31u;
 }
 
+// tuning knobs (overridable at build time for experiments)
+#ifndef SW16_UNROLL
+#define SW16_UNROLL 2
+#endif
+#define PSB_PRAGMA_(x) _Pragma(#x)
+#define PSB_UNROLL(n) PSB_PRAGMA_(unroll n)
+#ifndef SW16_WARPS_PER_BLOCK
+#define SW16_WARPS_PER_BLOCK 8
+#endif
+#if defined(SW16_MIN_BLOCKS) && !defined(PSB_EMULATE)
+#define SW16_BOUNDS __launch_bounds__(SW16_WARPS_PER_BLOCK * 32, SW16_MIN_BLOCKS)
+#else
+#define SW16_BOUNDS
+#endif
+
 template <int K>
-PSB_KERNEL void sw16_scan_kernel(Sw16Params p) {
+PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
     constexpr int G = SW16_G;
     constexpr int CH = (K + 15) / 16;                 // 16-row chunks per lane
     constexpr unsigned LSTRIDE = CH * G * 16;         // bytes per letter
@@ -184,7 +199,7 @@ PSB_KERNEL void sw16_scan_kernel(Sw16Params p) {
             }
             sync_warp();
             const int send = (s0 + 32 < nsteps) ? s0 + 32 : nsteps;
-#pragma unroll 2
+            PSB_UNROLL(SW16_UNROLL)
             for (int s = s0; s < send; ++s) {
                 const int j = s - lg;
                 unsigned Tup = shfl_up(Tout, 1);

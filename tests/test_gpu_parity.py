@@ -206,6 +206,25 @@ def test_scan_other_modes_and_stats(ps, oracle, blosum62, mode):
     scan_case(ps, oracle, blosum62, query, cat, off, mode="local", stats=True)
 
 
+def test_scan_host_equals_resident_scan(ps, oracle, blosum62):
+    # psb_scan_host (piecewise upload pipelined with the scan) returns exactly what a resident scan returns
+    query = psb_data.random_seq(2501, 0, 400)
+    cat, off = psb_data.protein_db(2502, 2503, 400000, query=query, planted_frac=0.01)   # ~145 MB: several pieces
+    b62 = ps.Matrix.from_name("blosum62")
+    a = ps.Aligner.new().local().gap_open(10).gap_extend(1).profile(ps.Profile.new(query, False, b62)).build()
+    base = a.scan(ps.Database((cat, off), b62))
+    host = a.scan_host((cat, off))
+    for k in KEYS3:
+        assert np.array_equal(getattr(host, k), getattr(base, k)), k
+    assert host.cells == base.cells
+    # small database, other mode, stats: single piece through the 32-bit path, against the oracle
+    cat2, off2 = psb_data.protein_db(2504, 2505, 300, query=query[:120], planted_frac=0.1)
+    a2 = ps.Aligner.new().semi_global().gap_open(10).gap_extend(1).profile(ps.Profile.new(query[:120], True, b62)).build()
+    got = a2.scan_host((cat2, off2))
+    exp = oracle.align_batch(query[:120], np.array([0, 120]), cat2, off2, blosum62, mode=1, open=10, gap=1, shared_query=True, stats=True)
+    assert_same(got, exp, KEYS6, "scan_host sg stats")
+
+
 def test_scan_permutation_invariance_large(ps):
     # size-independent property at a size the scalar oracle would need minutes for: shuffling the
     # database permutes the results and nothing else
