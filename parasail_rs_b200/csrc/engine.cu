@@ -260,23 +260,28 @@ static long long max_grid_warps() { return (long long)g_ctx.sms * 16 * kWarpsPer
 // ---- one long pair over the whole GPU (kern_wave32.cuh) -------------------------------------------
 static constexpr int kWaveMinLq = 2048;   // below this the per-pair kernel is used
 
-template <int K> static const void *wave32_fn_k() { return (const void *)wave32_kernel<K>; }
-static const void *wave32_fn(int K) {
+template <int K> static const void *wave32_fn_k(bool v2) { return v2 ? (const void *)wave32v2_kernel<K> : (const void *)wave32_kernel<K>; }
+static const void *wave32_fn(int K, bool v2) {
     switch (K) {
-        case 1: return wave32_fn_k<1>();
-        case 2: return wave32_fn_k<2>();
-        case 4: return wave32_fn_k<4>();
-        case 8: return wave32_fn_k<8>();
-        case 16: return wave32_fn_k<16>();
+        case 1: return wave32_fn_k<1>(v2);
+        case 2: return wave32_fn_k<2>(v2);
+        case 4: return wave32_fn_k<4>(v2);
+        case 8: return wave32_fn_k<8>(v2);
+        case 16: return wave32_fn_k<16>(v2);
     }
     return nullptr;
 }
+// the latency-optimised generation needs open >= extend and byte-sized (score + open)
+static bool wave32_v2_ok(const HostMatrix &m, int open, int gap) {
+    return open >= gap && gotoh32_profile_ok(m.size, m.min, m.max, open, m.type == PARASAIL_MATRIX_TYPE_PSSM);
+}
 
-static int launch_wave32(const Gotoh32Params &g, long long q_byte_off, int lq, long long r_byte_off, int lr, int out_index) {
+static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long q_byte_off, int lq, long long r_byte_off, int lr, int out_index) {
     Ctx &c = g_ctx;
     // strips of 32*K rows: enough strips to occupy the chip, as few as possible beyond that
     const int K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4);
-    const void *fn = K == 16 ? wave32_fn_k<16>() : (K == 8 ? wave32_fn_k<8>() : wave32_fn_k<4>());
+    const bool v2 = wave32_v2_ok(m, g.open, g.gap);
+    const void *fn = wave32_fn(K, v2);
     const int nstrips = (lq + 32 * K - 1) / (32 * K);
     DevMem d_bnd, d_ctl, d_cand;
     PSB_TRY(d_bnd.alloc((size_t)nstrips * 2 * (size_t)lr * sizeof(int), c.stream));
@@ -289,7 +294,7 @@ static int launch_wave32(const Gotoh32Params &g, long long q_byte_off, int lq, l
     p.mode = g.mode; p.s1_beg = g.s1_beg; p.s1_end = g.s1_end; p.s2_beg = g.s2_beg; p.s2_end = g.s2_end;
     p.bnd = d_bnd.as<int>(); p.progress = d_ctl.as<int>() + 1; p.next_strip = d_ctl.as<int>(); p.cand = d_cand.as<int>();
     p.multi_n = 0; p.r_off = nullptr;
-    const size_t smem = wave32_smem_bytes(g.size, kWarpsPerBlock);
+    const size_t smem = v2 ? wave32v2_smem_bytes(g.size, kWarpsPerBlock) : wave32_smem_bytes(g.size, kWarpsPerBlock);
     if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * 32, smem));
@@ -465,7 +470,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         const long long qb = (req.shared_query ? 0 : qoff_rel[id]), rb = roff_rel[id];
         const int lq = (int)(req.shared_query ? qoff_rel[1] : qoff_rel[id + 1] - qoff_rel[id]);
         const int lr = (int)(roff_rel[id + 1] - roff_rel[id]);
-        PSB_TRY(launch_wave32(p, qb, lq, rb, lr, id));
+        PSB_TRY(launch_wave32(p, m, qb, lq, rb, lr, id));
     }
 
     // device-side trace walk -> CIGAR CSR
@@ -909,13 +914,14 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         w.mode = cfg.mode; w.s1_beg = cfg.s1_beg; w.s1_end = cfg.s1_end; w.s2_beg = cfg.s2_beg; w.s2_end = cfg.s2_end;
         w.bnd = d_bnd.as<int>(); w.next_strip = d_ctl.as<int>(); w.progress = d_ctl.as<int>() + 1; w.cand = d_cand.as<int>();
         w.multi_n = (int)nroute; w.r_off = d_loff.as<long long>();
-        const void *fn = wave32_fn(K);
+        const bool v2 = wave32_v2_ok(m, open, gap);
+        const void *fn = wave32_fn(K, v2);
         // Full-size CTAs that also reserve most of an SM's shared memory: the strips of the long
         // subjects then own a few SMs outright instead of crawling beside sixteen ALU-bound warps
         // of the main kernel on every SM (each of their steps is a serial dependency).  The main
         // kernel's blocks that find no room start on those SMs as soon as the strips are done.
-        constexpr int kRouteWarps = 32;
-        const size_t smem = std::max<size_t>(wave32_smem_bytes(m.size, kRouteWarps), 160 * 1024);
+        const int kRouteWarps = v2 ? 8 : 32;   // generation 2 keeps a 12 KB profile per warp
+        const size_t smem = std::max<size_t>(v2 ? wave32v2_smem_bytes(m.size, kRouteWarps) : wave32_smem_bytes(m.size, kRouteWarps), 160 * 1024);
         PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // all warps of this launch must be resident together (strips wait on one another): one CTA
         // per SM at most, issued before the main kernel so that its blocks are placed first

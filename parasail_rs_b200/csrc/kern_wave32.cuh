@@ -201,6 +201,195 @@ PSB_KERNEL void wave32_kernel(Wave32Params p) {
     }
 }
 
+// ---- generation 2 of the strip sweep: built for LATENCY ------------------------------------------
+// A strip is one warp and every step hands its bottom row to the next lane, so the time of a long
+// pair is (columns + strips * lag) x the latency of one step, not a throughput figure.  This form
+// (needs open >= extend and matrix values + open that fit a byte; otherwise wave32_kernel runs)
+//   * takes the serial part of a column down to ONE dependent instruction per row:
+//       F[k] = max(F[k-1] - e, h0[k-1] - o)   with   h0 = max(Hdiag + S, E [,0])  off the chain
+//     (exact because H[k-1] - o = max(h0[k-1], F[k-1]) - o and F[k-1] - o <= F[k-1] - e);
+//   * reads the scores of a step with one LDS.128 from a per-warp int8 profile of the strip, whose
+//     address comes from a residue fetched one step ahead;
+//   * has no divergent branch in the step.
+inline size_t wave32v2_smem_bytes(int size, int warps) {
+    return (((size_t)size * size * sizeof(int) + 15) & ~(size_t)15) + (size_t)warps * (64 * 2 * sizeof(int) + 64 + 64 + (size_t)size * 512);
+}
+
+template <int K>
+PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
+    PSB_SHARED_DECL(smem_raw);
+    const int lane = lane_id();
+    const int size = p.size, o = p.open, e = p.gap;
+    int *smat = (int *)smem_raw;
+    const size_t mat_bytes = (((size_t)size * size * sizeof(int)) + 15) & ~(size_t)15;
+    const size_t per_warp = 64 * 2 * sizeof(int) + 64 + 64 + (size_t)size * 512;
+    unsigned char *wsm = smem_raw + mat_bytes + (size_t)warp_in_block() * per_warp;
+    int *ringT = (int *)wsm, *ringF = ringT + 64;
+    uint8_t *ringL = (uint8_t *)(ringF + 64);           // 64 residues (+64 bytes of slack keep the profile 16-byte aligned)
+    unsigned char *wprof = wsm + 64 * 2 * sizeof(int) + 128;
+    for (int x = thread_in_block(); x < size * size; x += threads_per_block()) smat[x] = p.matrix[x] + o;
+    sync_block();
+
+    const int mode = p.mode;
+    const bool is_sw = mode == MODE_SW;
+    const bool top_free = is_sw || (mode == MODE_SG && p.s1_beg);
+    const bool left_free = is_sw || (mode == MODE_SG && p.s2_beg);
+    const bool row_ends = mode == MODE_SG && p.s1_end;
+    const bool col_ends = mode == MODE_SG && p.s2_end;
+    const int Lq = p.Lq;
+    const int rows_per_strip = 32 * K;
+    const int nstrips = (Lq + rows_per_strip - 1) / rows_per_strip;
+    const int nitems = nstrips * (p.multi_n > 0 ? p.multi_n : 1);
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomic_add(p.next_strip, 1);
+        item = shfl(item, 0);
+        if (item >= nitems) break;
+        const int subj = item / nstrips, strip = item - subj * nstrips;
+        const long long rbase = p.multi_n > 0 ? p.r_off[subj] : 0;
+        const int Lr = p.multi_n > 0 ? (int)(p.r_off[subj + 1] - rbase) : p.Lr;
+        const uint8_t *rseq = p.r + rbase;
+        const int nsteps = Lr + 31;
+        int *bnd0 = p.bnd + 2ll * nstrips * rbase;
+        int *progress = p.progress + (long long)subj * nstrips;
+        const bool last_strip = strip == nstrips - 1;
+        const int i0 = strip * rows_per_strip + lane * K;
+        int *bndT_in = bnd0 + (long long)(strip - 1) * 2 * Lr, *bndF_in = bndT_in + Lr;
+        int *bndT_out = bnd0 + (long long)strip * 2 * Lr, *bndF_out = bndT_out + Lr;
+
+        // per-warp int8 profile of this strip: [letter][lane][16 rows] of (S + open), pad rows -128
+        sync_warp();
+        int T[K], E[K];
+        for (int a = 0; a < size; ++a) {
+            unsigned wv[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (i0 + k < Lq) {
+                    const unsigned b = (unsigned)smat[(int)p.q[i0 + k] * size + a] & 0xffu;
+                    wv[k >> 2] = (wv[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (b << (8 * (k & 3)));
+                }
+            }
+            uint4 v; v.x = wv[0]; v.y = wv[1]; v.z = wv[2]; v.w = wv[3];
+            *(uint4 *)(wprof + ((size_t)a * 32 + lane) * 16) = v;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            T[k] = (left_free ? 0 : -o - (i0 + k) * e) - o;
+            E[k] = NEG_INF32;
+        }
+        int Tdiag_in = (i0 == 0) ? -o : ((left_free ? 0 : -o - (i0 - 1) * e) - o);
+        int Tout = 0, Fout = NEG_INF32;
+        int bestH = NEG_INF32, bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
+        const int klast = (Lq - 1) - i0;
+        // column 0 of the ring; every 32 steps the columns s+1 .. s+32 follow (one ahead, so that the
+        // residue of the NEXT step is always staged)
+        if (lane == 0) ringL[0] = rseq[0];
+        if (strip > 0 && lane == 0) {
+            while (ld_acquire(progress + strip - 1) < 1) backoff();
+            ringT[0] = ld_cg(bndT_in); ringF[0] = ld_cg(bndF_in);
+        }
+        sync_warp();
+        int letter_next = (int)ringL[0];   // lane t first uses it at step t (column 0)
+
+        for (int s = 0; s < nsteps; ++s) {
+            if ((s & 31) == 0) {
+                sync_warp();
+                if (!last_strip && lane == 31 && s >= 32) {
+#if !defined(PSB_EMULATE)
+                    __threadfence();
+#endif
+                    st_release(progress + strip, s - 31);
+                }
+                const int need = (s + 33 < Lr) ? s + 33 : Lr;   // columns [s+1, need) are staged now
+                if (strip > 0 && s + 1 < Lr) {
+                    if (lane == 0) while (ld_acquire(progress + strip - 1) < need) backoff();
+                    sync_warp();
+                }
+                const int c = s + 1 + lane;
+                if (c < Lr) {
+                    ringL[c & 63] = rseq[c];
+                    if (strip > 0) { ringT[c & 63] = ld_cg(bndT_in + c); ringF[c & 63] = ld_cg(bndF_in + c); }
+                }
+                sync_warp();
+            }
+            const int j = s - lane;
+            const bool active = j >= 0 && j < Lr;
+            const int jc = active ? j : 0;
+            // scores of this step (address known since the previous step) and the next step's residue
+            const int letter = letter_next;
+            const uint4 pv = *(const uint4 *)(wprof + ((size_t)letter * 32 + lane) * 16);
+            const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w};
+            const int jn = j + 1;
+            letter_next = (int)ringL[(jn >= 0 && jn < Lr ? jn : 0) & 63];
+            int Tup = shfl_up(Tout, 1);
+            int Fup = shfl_up(Fout, 1);
+            if (lane == 0) {
+                const int bt = ringT[jc & 63], bf = ringF[jc & 63];
+                Tup = strip == 0 ? (top_free ? 0 : -o - jc * e) - o : bt;
+                Fup = strip == 0 ? NEG_INF32 : bf;
+            }
+            if (active) {
+                int Td = Tdiag_in;
+                int Fk = viaddmax(Fup, -e, Tup);   // F of row 0: the one place the received T enters the chain
+                int cmax = -0x7fffffff - 1;
+                int Hlast = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const unsigned SEL = (unsigned)(k & 3) * 0x1111u + 0x8880u;
+                    const int So = (int)prmt(pw[k >> 2], 0u, SEL);
+                    const int Tl = T[k];
+                    const int En = viaddmax(E[k], -e, Tl);
+                    const int h0 = is_sw ? viaddmax_relu(Td, So, En) : viaddmax(Td, So, En);
+                    const int H = h0 > Fk ? h0 : Fk;
+                    const int Fnext = viaddmax(Fk, -e, h0 - o);   // the only dependent op per row
+                    Td = Tl;
+                    T[k] = H - o; E[k] = En;
+                    if (is_sw) { const int key = H * 16 + (15 - k); cmax = cmax > key ? cmax : key; }
+                    if (k == K - 1) { Hlast = H; Fout = Fk; }
+                    Fk = Fnext;
+                }
+                Tdiag_in = Tup; Tout = Hlast - o;
+                if (lane == 31 && !last_strip) { st_cg(bndT_out + j, Tout); st_cg(bndF_out + j, Fout); }
+                if (is_sw) {
+                    const int ch = cmax >> 4;
+                    if (ch > bestH) { bestH = ch; bestJ = j; bestI = i0 + 15 - (cmax & 15); }
+                } else if (last_strip && klast >= 0 && klast < K && (row_ends || (j == Lr - 1 && !col_ends))) {
+                    int hv = 0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) if (k == klast) hv = T[k] + o;
+                    if (hv > bestH) { bestH = hv; bestJ = j; bestI = Lq - 1; }
+                }
+                if (col_ends && j == Lr - 1) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int hv = T[k] + o;
+                        if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
+                    }
+                }
+            }
+        }
+        sync_warp();
+        if (!last_strip && lane == 31) {
+#if !defined(PSB_EMULATE)
+            __threadfence();
+#endif
+            st_release(progress + strip, Lr);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const int oH = shfl_xor(bestH, m), oJ = shfl_xor(bestJ, m), oI = shfl_xor(bestI, m);
+            if (oH > bestH || (oH == bestH && (oJ < bestJ || (oJ == bestJ && oI < bestI)))) { bestH = oH; bestJ = oJ; bestI = oI; }
+            const int cH = shfl_xor(colH, m), cI = shfl_xor(colI, m);
+            if (cH > colH || (cH == colH && cI < colI)) { colH = cH; colI = cI; }
+        }
+        if (lane == 0) {
+            int *c = p.cand + (long long)item * 8;
+            c[0] = bestH; c[1] = bestJ; c[2] = bestI; c[3] = colH; c[4] = colI;
+        }
+    }
+}
+
 // final pick over the per-strip candidates, same tie-breaks as the in-warp merge.  One thread per
 // subject (a single pair is subject 0).
 struct WaveReduceParams {

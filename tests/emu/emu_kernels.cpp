@@ -60,10 +60,12 @@ extern "C" int emu_sizeof_sw16() { return (int)sizeof(Sw16Params); }
 // ---- long-pair wavefront kernel -------------------------------------------------------------------
 #include "../../parasail_rs_b200/csrc/kern_wave32.cuh"
 
+static bool g_wave_v2 = false;
+extern "C" void emu_wave32_use_v2(int on) { g_wave_v2 = on != 0; }
 extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams *rp, int nblocks) {
     Wave32Params p = *pp;
-    size_t smem = wave32_smem_bytes(p.size, 1);
-#define WCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { wave32_kernel<KK>(p); }); break;
+    size_t smem = g_wave_v2 ? wave32v2_smem_bytes(p.size, 1) : wave32_smem_bytes(p.size, 1);
+#define WCASE(KK) case KK: if (g_wave_v2) emu::launch(nblocks, smem, [&]() { wave32v2_kernel<KK>(p); }); else emu::launch(nblocks, smem, [&]() { wave32_kernel<KK>(p); }); break;
     switch (K) { WCASE(1) WCASE(2) WCASE(4) WCASE(8) default: return -1; }
     WaveReduceParams r = *rp;
     emu::launch((r.multi_n + 31) / 32 + (r.multi_n == 0), 64, [&]() { wave32_reduce_kernel(r); });

@@ -163,8 +163,9 @@ class WaveReduceParams(C.Structure):
                 ("multi_n", C.c_int), ("r_off", C.c_void_p), ("out_map", C.c_void_p), ("first_id", C.c_int)]
 
 
-def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1):
+def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1, v2=False):
     """Run the emulated long-pair wavefront kernel on one pair; returns (score, end_query, end_ref)."""
+    lib().emu_wave32_use_v2(int(v2))
     assert lib().emu_sizeof_wave32() == C.sizeof(Wave32Params) and lib().emu_sizeof_wavereduce() == C.sizeof(WaveReduceParams)
     mapper = mat.mapper.astype(np.uint8)
     qm = np.ascontiguousarray(mapper[np.asarray(q, dtype=np.uint8)])
@@ -186,8 +187,9 @@ def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1):
     return int(out[0]), int(out[1]), int(out[2])
 
 
-def wave32_multi(q, subjects, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1):
+def wave32_multi(q, subjects, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1, v2=False):
     """Multi-pair form of the wavefront kernel: one query vs several subjects in one launch."""
+    lib().emu_wave32_use_v2(int(v2))
     mapper = mat.mapper.astype(np.uint8)
     qm = np.ascontiguousarray(mapper[np.asarray(q, dtype=np.uint8)])
     sm = [mapper[np.asarray(s, dtype=np.uint8)] for s in subjects]

@@ -10,24 +10,27 @@ import psb_data
 from test_oracle_properties import SG_FLAGS
 
 
+@pytest.mark.parametrize("v2", [False, True])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("K", [1, 2])
-def test_wave_matches_oracle(oracle, mode, K):
+def test_wave_matches_oracle(oracle, mode, K, v2):
     mat = oracle.Matrix.create(b"ACGT", 2, -3)
     r = psb_data.random_seq(5001, 0, 170, protein=False)
     q = psb_data.mutate(r, 5001, 1, 0.10, 0.02, protein=False)[:150]
-    exp = oracle.align(q, r, mat, mode=mode, open=5, gap=2)
-    got = emu_harness.wave32(q, r, mat, K, mode, 5, 2)
-    assert got == (exp["score"], exp["end_query"], exp["end_ref"])
+    for o, e in ((5, 2), (3, 3), (0, 0)):
+        exp = oracle.align(q, r, mat, mode=mode, open=o, gap=e)
+        got = emu_harness.wave32(q, r, mat, K, mode, o, e, v2=v2)
+        assert got == (exp["score"], exp["end_query"], exp["end_ref"]), (o, e)
 
 
+@pytest.mark.parametrize("v2", [False, True])
 @pytest.mark.parametrize("flags", SG_FLAGS[1:])
-def test_wave_sg_flags(oracle, flags):
+def test_wave_sg_flags(oracle, flags, v2):
     mat = oracle.Matrix.create(b"ACGT", 2, -3)
     q = psb_data.random_seq(5002, 0, 100, protein=False)
     r = psb_data.random_seq(5002, 1, 90, protein=False)
     exp = oracle.align(q, r, mat, mode=1, open=5, gap=2, s1_beg=flags[0], s1_end=flags[1], s2_beg=flags[2], s2_end=flags[3])
-    got = emu_harness.wave32(q, r, mat, 1, 1, 5, 2, flags)
+    got = emu_harness.wave32(q, r, mat, 1, 1, 5, 2, flags, v2=v2)
     assert got == (exp["score"], exp["end_query"], exp["end_ref"])
 
 
@@ -36,8 +39,8 @@ def test_wave_multi_pair(oracle, blosum62):
     q = psb_data.random_seq(5003, 0, 100)
     subs = [psb_data.random_seq(5004, i, 40 + 25 * i) for i in range(4)]
     subs[2] = np.concatenate([subs[2][:20], psb_data.mutate(q, 5005, 0, 0.1, 0.02)])
-    for mode in (0, 2):
-        got = emu_harness.wave32_multi(q, subs, blosum62, 1, mode, 10, 1)
+    for mode, v2 in ((0, False), (2, False), (0, True), (2, True)):
+        got = emu_harness.wave32_multi(q, subs, blosum62, 1, mode, 10, 1, v2=v2)
         for i, s in enumerate(subs):
             exp = oracle.align(q, s, blosum62, mode=mode, open=10, gap=1)
             assert (got[0][i], got[1][i], got[2][i]) == (exp["score"], exp["end_query"], exp["end_ref"]), (mode, i)
