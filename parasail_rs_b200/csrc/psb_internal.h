@@ -49,6 +49,9 @@ struct psb_result_extra {
     std::vector<int> score_row, matches_row, similar_row, length_row;
     std::vector<int> score_col, matches_col, similar_col, length_col;
     std::vector<int8_t> trace;  // row-major TraceFlags bytes (qlen x rlen)
+    // _trace: the CIGAR the device walk produced (len<<4|op, forward order) and where it starts
+    std::vector<uint32_t> cigar_ops;
+    int beg_query = 0, beg_ref = 0;
 };
 
 struct parasail_profile {
@@ -84,9 +87,5 @@ void release_profile_resident(parasail_profile *p);
 // one pair through the batch path, wrapped as a parasail_result_t (never NULL)
 parasail_result_t *align_one(const FnConfig &cfg, const HostMatrix &m, const uint8_t *q, int qlen, const uint8_t *r,
                              int rlen, int open, int gap);
-
-// host-side trace walk shared by parasail_result_get_cigar / get_traceback (result.cpp)
-int walk_cigar(const int8_t *trace, const uint8_t *q, const uint8_t *r, int rlen, const uint8_t *mapper,
-               int end_query, int end_ref, std::vector<uint32_t> *ops, int *beg_query, int *beg_ref);
 
 }  // namespace psb

@@ -62,43 +62,17 @@ parasail_result_t *align_one(const FnConfig &cfg, const HostMatrix &m, const uin
     }
     res->score = b->score[0]; res->end_query = b->end_query[0]; res->end_ref = b->end_ref[0];
     if (cfg.stats) { res->extra->matches = b->matches[0]; res->extra->similar = b->similar[0]; res->extra->length = b->length[0]; }
+    if (cfg.trace && b->cigar_off) {
+        // the trace walk ran on the device (walk_trace_kernel); keep its CIGAR with the result
+        res->extra->cigar_ops.assign(b->cigar_ops + b->cigar_off[0], b->cigar_ops + b->cigar_off[1]);
+        res->extra->beg_query = b->beg_query[0]; res->extra->beg_ref = b->beg_ref[0];
+    }
     free_batch(b);
     if (saturates(cfg, m, res->score, qlen, rlen, open, gap)) {
         res->flag |= PARASAIL_FLAG_SATURATED;
         res->score = 0; res->end_query = 0; res->end_ref = 0;
     }
     return res;
-}
-
-// SURVEY A.7 / upstream src/cigar.c: walk the row-major trace bytes from the end cell
-int walk_cigar(const int8_t *trace, const uint8_t *q, const uint8_t *r, int rlen, const uint8_t *mapper,
-               int end_query, int end_ref, std::vector<uint32_t> *ops, int *beg_query, int *beg_ref) {
-    long long i = end_query, j = end_ref;
-    int where = 4;  // DIAG
-    std::vector<uint32_t> rev;
-    int cur = -1;
-    uint32_t len = 0;
-    auto emit = [&](int op) {
-        if (cur == op) { ++len; return; }
-        if (cur >= 0) rev.push_back((len << 4) | (uint32_t)cur);
-        cur = op; len = 1;
-    };
-    while (i >= 0 || j >= 0) {
-        if (i < 0) { emit(2); --j; continue; }
-        if (j < 0) { emit(1); --i; continue; }
-        const int t = trace[(size_t)i * (size_t)rlen + (size_t)j];
-        if (where == 4) {
-            if (t & 4) { emit(mapper[q[i]] == mapper[r[j]] ? 7 : 8); --i; --j; }
-            else if (t & 1) where = 1;
-            else if (t & 2) where = 2;
-            else break;
-        } else if (where == 1) { emit(2); where = (t & 8) ? 4 : 1; --j; }
-        else { emit(1); where = (t & 32) ? 4 : 2; --i; }
-    }
-    if (cur >= 0) rev.push_back((len << 4) | (uint32_t)cur);
-    ops->assign(rev.rbegin(), rev.rend());
-    *beg_query = (int)(i + 1); *beg_ref = (int)(j + 1);
-    return (int)ops->size();
 }
 
 }  // namespace psb
@@ -156,10 +130,12 @@ int parasail_result_is_stats_rowcol(const parasail_result_t *r) {
     return (r->flag & PARASAIL_FLAG_STATS) && (r->flag & PARASAIL_FLAG_ROWCOL);
 }
 
-// [REF src/alignment/mod.rs:400-407]
+// [REF src/alignment/mod.rs:400-407]  The walk itself ran on the GPU when the pair was aligned
+// (walk_trace_kernel + compact_cigar_kernel); this only hands the stored run-length list out.
 parasail_cigar_t *parasail_result_get_cigar(parasail_result_t *result, const char *seqA, int lena, const char *seqB,
                                             int lenb, const parasail_matrix_t *matrix) {
-    if (!result || !result->extra || result->extra->trace.empty() || !seqA || !seqB || !matrix) {
+    if (!result || !result->extra || !(result->flag & PARASAIL_FLAG_TRACE) || (result->flag & PARASAIL_FLAG_SATURATED) ||
+        !seqA || !seqB || !matrix) {
         psb::set_error("parasail_result_get_cigar: result has no trace");
         return nullptr;
     }
@@ -167,16 +143,12 @@ parasail_cigar_t *parasail_result_get_cigar(parasail_result_t *result, const cha
         psb::set_error("parasail_result_get_cigar: sequence lengths differ from the aligned pair");
         return nullptr;
     }
-    psb::HostMatrix hm(matrix);
-    std::vector<uint32_t> ops;
-    int bq = 0, br = 0;
-    psb::walk_cigar(result->extra->trace.data(), (const uint8_t *)seqA, (const uint8_t *)seqB, lenb, hm.mapper,
-                    result->end_query, result->end_ref, &ops, &bq, &br);
+    const std::vector<uint32_t> &ops = result->extra->cigar_ops;
     parasail_cigar_t *c = (parasail_cigar_t *)std::calloc(1, sizeof(parasail_cigar_t));
     c->seq = (uint32_t *)std::malloc(sizeof(uint32_t) * std::max<size_t>(ops.size(), 1));
     std::memcpy(c->seq, ops.data(), sizeof(uint32_t) * ops.size());
     c->len = (int)ops.size();
-    c->beg_query = bq; c->beg_ref = br;
+    c->beg_query = result->extra->beg_query; c->beg_ref = result->extra->beg_ref;
     return c;
 }
 
@@ -201,38 +173,33 @@ void parasail_cigar_free(parasail_cigar_t *cigar) {
     std::free(cigar);
 }
 
-// [REF src/alignment/mod.rs:356-366] three malloc'd strings, adopted by the Rust side
+// [REF src/alignment/mod.rs:356-366] three malloc'd strings, adopted by the Rust side.  Pure
+// formatting: the device-made CIGAR is expanded over the two sequences.
 parasail_traceback_t *parasail_result_get_traceback(parasail_result_t *result, const char *seqA, int lena,
                                                     const char *seqB, int lenb, const parasail_matrix_t *matrix,
                                                     char match, char pos, char neg) {
-    if (!result || !result->extra || result->extra->trace.empty() || !seqA || !seqB || !matrix) {
+    if (!result || !result->extra || !(result->flag & PARASAIL_FLAG_TRACE) || (result->flag & PARASAIL_FLAG_SATURATED) ||
+        !seqA || !seqB || !matrix) {
         psb::set_error("parasail_result_get_traceback: result has no trace");
         return nullptr;
     }
     if (lena != result->extra->qlen || lenb != result->extra->rlen) return nullptr;
     psb::HostMatrix hm(matrix);
-    const int8_t *tr = result->extra->trace.data();
     std::string qs, cs, rs;
-    long long i = result->end_query, j = result->end_ref;
-    int where = 4;
-    while (i >= 0 || j >= 0) {
-        if (i < 0) { qs.push_back('-'); rs.push_back(seqB[j]); cs.push_back(' '); --j; continue; }
-        if (j < 0) { qs.push_back(seqA[i]); rs.push_back('-'); cs.push_back(' '); --i; continue; }
-        const int t = tr[(size_t)i * lenb + j];
-        if (where == 4) {
-            if (t & 4) {
+    int i = result->extra->beg_query, j = result->extra->beg_ref;
+    for (uint32_t w : result->extra->cigar_ops) {
+        const int op = (int)(w & 0xf);
+        for (uint32_t t = 0; t < (w >> 4); ++t) {
+            if (op == 7 || op == 8) {
                 const int a = hm.mapper[(uint8_t)seqA[i]], b = hm.mapper[(uint8_t)seqB[j]];
-                const int sub = hm.table[(size_t)hm.size * (hm.type == PARASAIL_MATRIX_TYPE_PSSM ? (int)i : a) + b];
+                const int sub = hm.table[(size_t)hm.size * (hm.type == PARASAIL_MATRIX_TYPE_PSSM ? i : a) + b];
                 qs.push_back(seqA[i]); rs.push_back(seqB[j]);
-                cs.push_back(a == b ? match : (sub > 0 ? pos : neg));
-                --i; --j;
-            } else if (t & 1) where = 1;
-            else if (t & 2) where = 2;
-            else break;
-        } else if (where == 1) { qs.push_back('-'); rs.push_back(seqB[j]); cs.push_back(' '); where = (t & 8) ? 4 : 1; --j; }
-        else { qs.push_back(seqA[i]); rs.push_back('-'); cs.push_back(' '); where = (t & 32) ? 4 : 2; --i; }
+                cs.push_back(op == 7 ? match : (sub > 0 ? pos : neg));
+                ++i; ++j;
+            } else if (op == 1) { qs.push_back(seqA[i]); rs.push_back('-'); cs.push_back(' '); ++i; }
+            else { qs.push_back('-'); rs.push_back(seqB[j]); cs.push_back(' '); ++j; }
+        }
     }
-    std::reverse(qs.begin(), qs.end()); std::reverse(cs.begin(), cs.end()); std::reverse(rs.begin(), rs.end());
     auto dup = [](const std::string &s) { char *p = (char *)std::malloc(s.size() + 1); std::memcpy(p, s.c_str(), s.size() + 1); return p; };
     parasail_traceback_t *tb = (parasail_traceback_t *)std::calloc(1, sizeof(parasail_traceback_t));
     tb->query = dup(qs); tb->comp = dup(cs); tb->ref = dup(rs);
