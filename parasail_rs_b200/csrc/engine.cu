@@ -255,7 +255,12 @@ static int launch_gotoh32(int K, Variant v, Gotoh32Params &p, int nwork, bool pr
     return PSB_OK;
 }
 
-static long long max_grid_warps() { return (long long)g_ctx.sms * 16 * kWarpsPerBlock; }
+// upper bound on the warps any launch of `nwork` items can have resident (scratch lines are per warp)
+static long long max_grid_warps(long long nwork) {
+    const long long cap = (long long)g_ctx.sms * 16 * kWarpsPerBlock;
+    const long long need = ((nwork + kWarpsPerBlock - 1) / kWarpsPerBlock) * kWarpsPerBlock;
+    return std::max<long long>(kWarpsPerBlock, std::min(cap, need));
+}
 
 // ---- one long pair over the whole GPU (kern_wave32.cuh) -------------------------------------------
 static constexpr int kWaveMinLq = 2048;   // below this the per-pair kernel is used
@@ -404,7 +409,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     const bool stats_kernel = cfg.stats || want_table;
     const int bnd_words_per_col = 2 + (stats_kernel ? 2 * ((wide_stats || want_table) ? 2 : 1) : 0);
     const long long bnd_stride = (long long)max_lr_multistrip * bnd_words_per_col;
-    if (bnd_stride > 0) PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps()) * sizeof(int), c.stream));
+    if (bnd_stride > 0) PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps(n)) * sizeof(int), c.stream));
 
     // trace / table blocks: [strip][step][lane][K] per pair
     DevMem d_trace, d_traceoff, d_tab[4], d_rev, d_revoff, d_nops, d_beg[2];
@@ -797,7 +802,7 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     long long bnd_stride = 0;
     if (lq > 32 * K) {
         bnd_stride = (long long)db->maxlen * (2 + (cfg.stats ? (wide ? 4 : 2) : 0));
-        PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps()) * sizeof(int), c.stream));
+        PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps(d_subset ? nsubset : db->n)) * sizeof(int), c.stream));
     }
     Gotoh32Params p;
     std::memset(&p, 0, sizeof(p));

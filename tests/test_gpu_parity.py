@@ -309,6 +309,36 @@ def test_long_pair_wavefront(ps, oracle, mode):
     assert_same(gb, oracle_batch(oracle, qs, rs, m, mode, 5, 2), KEYS3, f"wave batch mode {mode}")
 
 
+def test_concurrent_host_threads(ps, oracle, blosum62):
+    # Aligner / Profile / Matrix handles are Send + Sync in the reference [REF src/aligner/mod.rs:532-535]:
+    # four host threads (each gets its own stream) share one profile, one database and one aligner
+    import threading
+    b62 = ps.Matrix.from_name("blosum62")
+    query = psb_data.random_seq(2701, 0, 200)
+    cat, off = psb_data.protein_db(2702, 2703, 3000, query=query, planted_frac=0.05)
+    scan_aligner = ps.Aligner.new().local().gap_open(10).gap_extend(1).profile(ps.Profile.new(query, False, b62)).build()
+    db = ps.Database((cat, off), b62)
+    pair_aligner = ps.Aligner.new().semi_global().matrix(b62).gap_open(10).gap_extend(1).use_stats().build()
+    qs, rs = mixed_pairs(2704, 60, (1, 300), (1, 300), True)
+    exp_scan = oracle.align_batch(query, np.array([0, len(query)]), cat, off, blosum62, mode=2, open=10, gap=1, shared_query=True)
+    exp_pairs = oracle_batch(oracle, qs, rs, blosum62, 1, 10, 1, stats=True)
+    errors = []
+
+    def work(tid):
+        try:
+            for _ in range(3):
+                if tid % 2 == 0:
+                    assert_same(scan_aligner.scan(db), exp_scan, KEYS3, f"thread {tid} scan")
+                else:
+                    assert_same(pair_aligner.align_batch(qs, rs), exp_pairs, KEYS6, f"thread {tid} pairs")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+
+
 def test_edge_cases(ps, oracle, blosum62):
     b62 = ps.Matrix.from_name("blosum62")
     # single residues, unknown letters (mapped to '*'), lower case
