@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -85,7 +86,10 @@ static int ensure_ctx() {
     PSB_CUDA(cudaEventCreate(&c.ev1));
     int lo_pri = 0, hi_pri = 0;
     cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
-    PSB_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi_pri));
+    // the side stream carries the scan's main launch when a head/wavefront launch must reach the SMs
+    // first (scan_sw16): lowest priority, so pending CTAs of the compute stream are placed before it
+    (void)hi_pri;
+    PSB_CUDA(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, lo_pri));
     PSB_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     PSB_CUDA(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     PSB_CUDA(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
@@ -688,9 +692,6 @@ struct psb_db {
     long long *d_word_off = nullptr;  // n+1, sorted order (length descending, stable)
     int *d_perm = nullptr;            // sorted position -> caller's subject id
     int *d_len = nullptr;             // sorted order
-    // unpacked copy for the general 32-bit path, built on first use
-    uint8_t *d_bytes = nullptr;
-    long long *d_byte_off = nullptr;
     std::mutex mu;
 };
 
@@ -757,38 +758,12 @@ __global__ void db_wcount_sorted_kernel(const int *len_sorted, long long n, int 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride)
         wcount[i] = i < n ? (len_sorted[i] + rpw - 1) / rpw : 0;
 }
-__global__ void db_len64_kernel(const int *len_sorted, long long n, long long *out) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) out[i] = i < n ? len_sorted[i] : 0;
-}
-
-static int db_ensure_bytes(psb_db *db) {
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(db->mu);
-    if (db->d_bytes) return PSB_OK;
-    PSB_CUDA(cudaMallocAsync(&db->d_bytes, std::max<size_t>((size_t)db->residues, 16), c.stream));
-    PSB_CUDA(cudaMallocAsync(&db->d_byte_off, ((size_t)db->n + 1) * sizeof(long long), c.stream));
-    DevMem tmp64, scan_tmp;
-    PSB_TRY(tmp64.alloc(((size_t)db->n + 1) * sizeof(long long), c.stream));
-    db_len64_kernel<<<c.sms * 4, 256, 0, c.stream>>>(db->d_len, db->n, tmp64.as<long long>());
-    size_t tb = 0;
-    PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, tmp64.as<long long>(), db->d_byte_off, (int)(db->n + 1), c.stream));
-    PSB_TRY(scan_tmp.alloc(tb, c.stream));
-    PSB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tb, tmp64.as<long long>(), db->d_byte_off, (int)(db->n + 1), c.stream));
-    UnpackParams u;
-    u.words = db->d_words; u.word_off = db->d_word_off; u.ids = nullptr; u.out_off = db->d_byte_off;
-    u.out = db->d_bytes; u.n = db->n; u.bits = db->bits;
-    unpack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(u);
-    c.launches += 3;
-    PSB_CUDA(cudaStreamSynchronize(c.stream));
-    return PSB_OK;
-}
-
-// general 32-bit path over (a subset of) the resident database; results land in caller order
+// general 32-bit path over (a subset of) the resident database, reading the subjects straight from
+// the bit-packed store; results land in caller order.  With `d_count` the number of subset entries is
+// read on the device (the 16-bit scan's re-run list), so no host synchronisation is needed to launch.
 static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, int open, int gap, psb_db *db,
-                        const int *d_subset, int nsubset, int *const d_out[6]) {
+                        const int *d_subset, int nsubset, const int *d_count, int *const d_out[6]) {
     Ctx &c = g_ctx;
-    PSB_TRY(db_ensure_bytes(db));
     const HostMatrix &m = prof->matrix;
     const int lq = (int)prof->query.size();
     const bool pssm = m.type == PARASAIL_MATRIX_TYPE_PSSM;
@@ -799,15 +774,18 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     PSB_TRY(d_counter.alloc(sizeof(int), c.stream));
     PSB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int), c.stream));
     const bool wide = !(std::min(lq, db->maxlen) < 1024 && lq + db->maxlen < 4096);
+    // a re-run list is almost always empty or tiny: a small persistent grid serves any count
+    const int nwork = d_count ? (int)std::min<int64_t>(nsubset, (int64_t)g_ctx.sms * 2 * kWarpsPerBlock) : (d_subset ? nsubset : (int)db->n);
     long long bnd_stride = 0;
     if (lq > 32 * K) {
         bnd_stride = (long long)db->maxlen * (2 + (cfg.stats ? (wide ? 4 : 2) : 0));
-        PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps(d_subset ? nsubset : db->n)) * sizeof(int), c.stream));
+        PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps(nwork)) * sizeof(int), c.stream));
     }
     Gotoh32Params p;
     std::memset(&p, 0, sizeof(p));
-    p.q = dp->d_query; p.q_off = dp->d_qoff; p.r = db->d_bytes; p.r_off = db->d_byte_off;
-    p.order = d_subset; p.n = d_subset ? nsubset : (int)db->n; p.shared_query = 1;
+    p.q = dp->d_query; p.q_off = dp->d_qoff;
+    p.r_words = db->d_words; p.r_word_off = db->d_word_off; p.r_len = db->d_len; p.r_bits = db->bits;
+    p.order = d_subset; p.n = d_subset ? nsubset : (int)db->n; p.n_dev = d_count; p.shared_query = 1;
     p.matrix = dp->d_matrix; p.size = m.size; p.is_pssm = pssm ? 1 : 0;
     p.open = open; p.gap = gap;
     p.mode = cfg.mode; p.s1_beg = cfg.s1_beg; p.s1_end = cfg.s1_end; p.s2_beg = cfg.s2_beg; p.s2_end = cfg.s2_end;
@@ -817,7 +795,7 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     p.counter = d_counter.as<int>();
     p.out_map = db->d_perm;
     const Variant v = cfg.stats ? (wide ? V_STATS64 : V_STATS32) : V_SCORE;
-    PSB_TRY(launch_gotoh32(K, v, p, p.n, fine));
+    PSB_TRY(launch_gotoh32(K, v, p, nwork, fine));
     return PSB_OK;
 }
 
@@ -867,7 +845,7 @@ static constexpr int kSw16WarpsPerBlock = SW16_WARPS_PER_BLOCK;
 // a separate small launch of the same kernel, one warp per SM sub-partition on SMs it owns
 // outright, beside the main launch.
 static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, int open, int gap, psb_db *db,
-                     int *const d_out[6], int64_t *n_retried) {
+                     int *const d_out[6], int64_t *n_retried, int *retried_host) {
     Ctx &c = g_ctx;
     const Sw16Profile &sp = dp->sw16;
     const HostMatrix &m = prof->matrix;
@@ -884,13 +862,25 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
     if (db->nlong > nroute) {
         // more over-long subjects than the routed head covers: not a workload for the packed kernel
         *n_retried = db->n;
-        return scan_general(cfg, prof, dp, open, gap, db, nullptr, 0, d_out);
+        return scan_general(cfg, prof, dp, open, gap, db, nullptr, 0, nullptr, d_out);
     }
+    if (std::getenv("PSB_DEBUG_TIMING"))
+        std::fprintf(stderr, "[psb] sw16: n %lld residues %lld est %.2f ms long_len %.0f nroute %lld nhead %lld top %d\n", (long long)db->n,
+                     (long long)db->residues, est_ms, long_len, (long long)nroute, (long long)nhead, db->top_len.empty() ? 0 : db->top_len[0]);
     DevMem d_retry, d_cnt;
     PSB_TRY(d_retry.alloc(((size_t)db->n + 2) * sizeof(int), c.stream));
     PSB_TRY(d_cnt.alloc(4 * sizeof(int), c.stream));
     PSB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(int), c.stream));
 
+    // The launches that must own their SMs (wavefront strips, head) go on the compute stream, where
+    // they start the moment the preceding work ends; the main launch goes on the side stream behind an
+    // event, so it reaches the SMs after them.  The other way round, a busy queue lets the main
+    // launch's persistent CTAs take every SM first and the head then runs alone AFTER it.
+    const bool forked = nroute > 0 || nhead > 0;
+    if (forked) {
+        PSB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+        PSB_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+    }
     DevMem d_lbytes, d_loff, d_bnd, d_ctl, d_cand;
     if (nroute > 0) {
         std::vector<long long> loff(nroute + 1);
@@ -906,12 +896,10 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         PSB_CUDA(cudaMemcpyAsync(d_loff.p, loff.data(), (size_t)(nroute + 1) * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
         PSB_CUDA(cudaMemsetAsync(d_ctl.p, 0, ((size_t)nroute * nstrips + 2) * sizeof(int), c.stream));
         PSB_CUDA(cudaStreamSynchronize(c.stream));  // `loff` is a host temporary
-        PSB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
-        PSB_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
         UnpackParams u;
         u.words = db->d_words; u.word_off = db->d_word_off; u.ids = nullptr; u.out_off = d_loff.as<long long>();
         u.out = d_lbytes.as<uint8_t>(); u.n = nroute; u.bits = db->bits;
-        unpack_db_kernel<<<(unsigned)std::min<int64_t>(nroute, 1024), 256, 0, c.side>>>(u);
+        unpack_db_kernel<<<(unsigned)std::min<int64_t>(nroute, 1024), 256, 0, c.stream>>>(u);
         Wave32Params w;
         std::memset(&w, 0, sizeof(w));
         w.q = dp->d_query; w.r = d_lbytes.as<uint8_t>(); w.Lq = lq; w.Lr = 0;
@@ -933,14 +921,13 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         const long long items = nroute * nstrips;
         long long blocks = std::min<long long>((items + kRouteWarps - 1) / kRouteWarps, (long long)c.sms);
         void *args[] = {&w};
-        PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kRouteWarps * 32), args, smem, c.side));
+        PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kRouteWarps * 32), args, smem, c.stream));
         WaveReduceParams r;
         std::memset(&r, 0, sizeof(r));
         r.cand = d_cand.as<int>(); r.nstrips = nstrips; r.mode = cfg.mode; r.s1_end = cfg.s1_end; r.s2_end = cfg.s2_end;
         r.score = d_out[0]; r.end_query = d_out[1]; r.end_ref = d_out[2];
         r.multi_n = (int)nroute; r.r_off = d_loff.as<long long>(); r.out_map = db->d_perm; r.first_id = 0;
-        wave32_reduce_kernel<<<(unsigned)((nroute + 127) / 128), 128, 0, c.side>>>(r);
-        PSB_CUDA(cudaEventRecord(c.ev_join, c.side));
+        wave32_reduce_kernel<<<(unsigned)((nroute + 127) / 128), 128, 0, c.stream>>>(r);
         c.launches += 3;
     }
     const int64_t nshort = db->n - nroute;
@@ -963,17 +950,12 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         if (nhead > 0) {
             // head: the longest subjects, 4 warps per CTA (one per sub-partition), each CTA alone on
             // its SM (the shared-memory request keeps the main launch's CTAs away)
-            if (nroute == 0) {
-                PSB_CUDA(cudaEventRecord(c.ev_fork, c.stream));
-                PSB_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
-            }
             Sw16Params h = p;
             h.word_off = db->d_word_off + nroute; h.len = db->d_len + nroute; h.n = nhead; h.out_map = db->d_perm + nroute;
             h.sid_base = (int)nroute; h.counter = d_cnt.as<int>() + 2;
             const long long hslots = (nhead / 2 + 1) / 2;
             void *hargs[] = {&h};
-            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)((hslots + 3) / 4)), dim3(4 * 32), hargs, smem_excl, c.side));
-            PSB_CUDA(cudaEventRecord(c.ev_join, c.side));
+            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)((hslots + 3) / 4)), dim3(4 * 32), hargs, smem_excl, c.stream));
             c.launches++;
         }
         const int64_t nrest = nshort - nhead;
@@ -984,16 +966,19 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
             long long blocks = std::min<long long>((slots + kSw16WarpsPerBlock - 1) / kSw16WarpsPerBlock, (long long)c.sms * per_sm);
             if (blocks < 1) blocks = 1;
             void *args[] = {&p};
-            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kSw16WarpsPerBlock * 32), args, smem, c.stream));
+            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kSw16WarpsPerBlock * 32), args, smem, forked ? c.side : c.stream));
             c.launches++;
         }
     }
-    if (nroute > 0 || nhead > 0) PSB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
-    int nretry = 0;
-    PSB_CUDA(cudaMemcpyAsync(&nretry, d_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    PSB_CUDA(cudaStreamSynchronize(c.stream));
-    *n_retried = nretry + nroute;   // subjects that did not come out of the packed 16-bit kernel
-    if (nretry > 0) PSB_TRY(scan_general(cfg, prof, dp, open, gap, db, d_retry.as<int>(), nretry, d_out));
+    if (forked) {
+        PSB_CUDA(cudaEventRecord(c.ev_join, c.side));
+        PSB_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+    }
+    // re-run list: launched unconditionally with its length read on the device (usually zero), so the
+    // scan needs no host round trip in the middle; the count reaches the host with the results
+    PSB_TRY(scan_general(cfg, prof, dp, open, gap, db, d_retry.as<int>(), (int)db->n, d_cnt.as<int>(), d_out));
+    PSB_CUDA(cudaMemcpyAsync(retried_host, d_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    *n_retried = nroute;   // + *retried_host once the stream has been synchronised
     return PSB_OK;
 }
 
@@ -1113,7 +1098,11 @@ static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int6
         for (int t = 0; t < hist[l] && db->top_len.size() < 4096; ++t) db->top_len.push_back(l);
 
     const size_t n1 = (size_t)n + 1;
-    if (B.d_raw.alloc((size_t)db->residues, c.stream) != PSB_OK || B.d_off.alloc(n1 * 8, c.stream) != PSB_OK ||
+    // with the copy stream, the staging buffers are allocated in ITS order: the upload must not queue
+    // behind whatever scan is already running on the compute stream.  They are consumed (and freed)
+    // on the compute stream, which waits for the `uploaded` event.
+    cudaStream_t up = use_copy_stream ? c.copy : c.stream;
+    if (B.d_raw.alloc((size_t)db->residues, up) != PSB_OK || B.d_off.alloc(n1 * 8, up) != PSB_OK ||
         B.d_len0.alloc((size_t)n * 4, c.stream) != PSB_OK || B.d_idx0.alloc((size_t)n * 4, c.stream) != PSB_OK ||
         B.d_wcount.alloc(n1 * 8, c.stream) != PSB_OK)
         return fail(psb_last_error());
@@ -1124,13 +1113,7 @@ static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int6
     ck(cudaMallocAsync(&db->d_len, (size_t)n * 4, c.stream));
     ck(cudaMallocAsync(&db->d_words, (size_t)db->words * 4 + 64, c.stream));
     if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
-    cudaStream_t up = c.stream;
-    if (use_copy_stream) {
-        // the staging buffers come from the compute stream's pool: order the copies after the allocations
-        ck(cudaEventRecord(c.ev_alloc, c.stream));
-        ck(cudaStreamWaitEvent(c.copy, c.ev_alloc, 0));
-        up = c.copy;
-    }
+    B.d_raw.s = c.stream; B.d_off.s = c.stream;
     ck(cudaMemcpyAsync(B.d_off.p, off, n1 * 8, cudaMemcpyHostToDevice, up));
     ck(cudaMemcpyAsync(B.d_raw.p, cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, up));
     if (use_copy_stream) {
@@ -1198,7 +1181,7 @@ void psb_db_free(psb_db_t *db) {
     int cur = 0;
     cudaGetDevice(&cur);
     cudaSetDevice(db->device);
-    void *ptrs[] = {db->d_words, db->d_word_off, db->d_perm, db->d_len, db->d_bytes, db->d_byte_off};
+    void *ptrs[] = {db->d_words, db->d_word_off, db->d_perm, db->d_len};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, db->stream);
     cudaSetDevice(cur);
     delete db;
@@ -1207,30 +1190,56 @@ void psb_db_free(psb_db_t *db) {
 }  // extern "C"
 
 namespace psb {
-// one scan of a resident database; per-subject results are copied to hosts[k] + host_base
-static int scan_core(const FnConfig &cfg, const parasail_profile *profile, int open, int gap, psb_db *db, int *const hosts[6],
-                     int64_t host_base, int64_t *retried) {
+// one scan of a resident database, in two halves so that psb_scan_host can do host work for the next
+// piece while this one runs: scan_enqueue issues the kernels and the device->host copies of the
+// per-subject results (to hosts[k] + host_base); scan_finish waits for them.
+struct ScanJob {
+    DevMem d_out[6];
+    int64_t retried = 0;
+    int *retried_host = nullptr;   // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ScanJob() = default;
+    ScanJob(const ScanJob &) = delete;
+    ScanJob &operator=(const ScanJob &) = delete;
+    ~ScanJob() {
+        if (retried_host) pinned_free(retried_host, 64);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+static int scan_enqueue(ScanJob &job, const FnConfig &cfg, const parasail_profile *profile, int open, int gap, psb_db *db,
+                        int *const hosts[6], int64_t host_base) {
     Ctx &c = g_ctx;
     DevProfile *dp = nullptr;
     PSB_TRY(get_dev_profile(profile, &dp));
-    DevMem d_out[6];
     int *outp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int nout = cfg.stats ? 6 : 3;
-    for (int k = 0; k < nout; ++k) { PSB_TRY(d_out[k].alloc((size_t)db->n * sizeof(int), c.stream)); outp[k] = d_out[k].as<int>(); }
-    PSB_CUDA(cudaEventRecord(c.ev0, c.stream));
+    for (int k = 0; k < nout; ++k) { PSB_TRY(job.d_out[k].alloc((size_t)db->n * sizeof(int), c.stream)); outp[k] = job.d_out[k].as<int>(); }
+    job.retried_host = (int *)pinned_alloc(64);
+    if (!job.retried_host) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
+    *job.retried_host = 0;
+    PSB_CUDA(cudaEventCreate(&job.ev0));
+    PSB_CUDA(cudaEventCreate(&job.ev1));
+    PSB_CUDA(cudaEventRecord(job.ev0, c.stream));
     const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 && sw16_prepare(profile, dp, open, gap);
     int rc;
-    *retried = 0;
-    if (fast) rc = scan_sw16(cfg, profile, dp, open, gap, db, outp, retried);
-    else rc = scan_general(cfg, profile, dp, open, gap, db, nullptr, 0, outp);
+    if (fast) rc = scan_sw16(cfg, profile, dp, open, gap, db, outp, &job.retried, job.retried_host);
+    else rc = scan_general(cfg, profile, dp, open, gap, db, nullptr, 0, nullptr, outp);
     if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); return rc; }
-    PSB_CUDA(cudaEventRecord(c.ev1, c.stream));
+    PSB_CUDA(cudaEventRecord(job.ev1, c.stream));
     for (int k = 0; k < nout; ++k)
-        PSB_CUDA(cudaMemcpyAsync(hosts[k] + host_base, d_out[k].p, (size_t)db->n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        PSB_CUDA(cudaMemcpyAsync(hosts[k] + host_base, job.d_out[k].p, (size_t)db->n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    return PSB_OK;
+}
+// call after the stream has been synchronised
+static int scan_finish(ScanJob &job) {
+    Ctx &c = g_ctx;
     cudaError_t e = cudaStreamSynchronize(c.stream);
     if (e != cudaSuccess) { set_error(std::string("psb_scan: ") + cudaGetErrorString(e)); return PSB_ECUDA; }
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_ms += ms;
+    if (cudaEventElapsedTime(&ms, job.ev0, job.ev1) == cudaSuccess) c.last_ms += ms;
+    if (std::getenv("PSB_DEBUG_TIMING")) std::fprintf(stderr, "[psb] scan job: %.3f ms, %d re-run at 32 bit\n", ms, *job.retried_host);
+    job.retried += *job.retried_host;
     return PSB_OK;
 }
 static int scan_check(const char *who, const char *fn_name, const parasail_profile_t *profile, FnConfig *cfg) {
@@ -1261,10 +1270,11 @@ int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, i
     if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
     b->cells = (double)profile->query.size() * (double)db->residues;
     int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
-    int64_t retried = 0;
-    const int rc = scan_core(cfg, profile, open, gap, db, hosts, 0, &retried);
-    if (rc != PSB_OK) { free_batch(b); return rc; }
-    b->n_retried = retried;
+    ScanJob job;
+    int rc = scan_enqueue(job, cfg, profile, open, gap, db, hosts, 0);
+    if (rc == PSB_OK) rc = scan_finish(job);
+    if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); free_batch(b); return rc; }
+    b->n_retried = job.retried;
     *out = b;
     return PSB_OK;
 }
@@ -1280,18 +1290,22 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
     Ctx &c = g_ctx;
     c.last_ms = 0.0; c.launches = 0;
     const HostMatrix &hm = profile->matrix;
-    // a few large pieces: the upload of piece k+1 (copy stream) runs under the scan of piece k.  Every
-    // piece pays the scan kernel's ramp-up and tail once, so pieces are kept big (192 MB of residues
-    // by default; PSB_SCAN_HOST_PIECE_MB overrides it for experiments).
+    // pieces: the upload of piece k+1 (copy stream) runs under the scan of piece k, and nothing on the
+    // host waits for the GPU until the last piece is queued.  The first piece is small so the scan
+    // starts early; the others are big because every piece pays the scan kernel's ramp-up and tail
+    // once.  PSB_SCAN_HOST_FIRST_MB / PSB_SCAN_HOST_PIECE_MB override the sizes for experiments.
     const int64_t total = off[n] - off[0];
-    long long piece_mb = 192;
+    long long piece_mb = 96, first_mb = 24;
     if (const char *ev = std::getenv("PSB_SCAN_HOST_PIECE_MB")) piece_mb = std::max(8ll, std::atoll(ev));
+    if (const char *ev = std::getenv("PSB_SCAN_HOST_FIRST_MB")) first_mb = std::max(1ll, std::atoll(ev));
     const int64_t piece = piece_mb << 20;
-    const int npieces = (int)std::max<int64_t>(1, std::min<int64_t>(32, std::min<int64_t>(n, (total + piece * 3 / 4) / piece)));
+    const int64_t first = total > (first_mb << 20) + piece / 4 ? (first_mb << 20) : total;
+    const int nrest = first == total ? 0 : (int)std::max<int64_t>(1, std::min<int64_t>(30, (total - first + piece * 3 / 4) / piece));
+    const int npieces = (int)std::min<int64_t>(n, 1 + nrest);
     std::vector<int64_t> cut(npieces + 1, n);
     cut[0] = 0;
     for (int k = 1; k < npieces; ++k) {
-        const int64_t target = off[0] + total * k / npieces;
+        const int64_t target = off[0] + first + (total - first) * (k - 1) / std::max(1, npieces - 1);
         cut[k] = std::lower_bound(off, off + n + 1, target) - off;
         if (cut[k] <= cut[k - 1]) cut[k] = std::min<int64_t>(n, cut[k - 1] + 1);
     }
@@ -1305,17 +1319,29 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
         if (cut[k + 1] <= cut[k]) return PSB_OK;
         return db_begin(builds[k], cat, off + cut[k], cut[k + 1] - cut[k], hm, true) ? PSB_OK : PSB_ECUDA;
     };
+    std::vector<ScanJob> jobs(npieces);
+    const bool dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
+    const auto t_in = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count(); };
     rc = begin(0);
+    if (dbg) std::fprintf(stderr, "[psb] scan_host: %d pieces, first upload queued at %.3f ms\n", npieces, since());
     for (int k = 0; k < npieces && rc == PSB_OK; ++k) {
         if (!builds[k].db) continue;
         rc = db_finish(builds[k]);
-        if (rc == PSB_OK && k + 1 < npieces) rc = begin(k + 1);   // enqueue the next upload before this scan blocks
-        int64_t retried = 0;
-        if (rc == PSB_OK) rc = scan_core(cfg, profile, open, gap, builds[k].db, hosts, cut[k], &retried);
-        b->n_retried += retried;
+        if (rc == PSB_OK) rc = scan_enqueue(jobs[k], cfg, profile, open, gap, builds[k].db, hosts, cut[k]);
+        if (dbg) std::fprintf(stderr, "[psb] scan_host: piece %d queued at %.3f ms\n", k, since());
+        // while this piece is being scanned: host pass over the next piece's offsets and its upload
+        if (rc == PSB_OK && k + 1 < npieces) rc = begin(k + 1);
     }
     cudaStreamSynchronize(c.copy);
+    if (dbg) std::fprintf(stderr, "[psb] scan_host: uploads done at %.3f ms\n", since());
     cudaStreamSynchronize(c.stream);
+    if (dbg) std::fprintf(stderr, "[psb] scan_host: all done at %.3f ms\n", since());
+    for (int k = 0; k < npieces && rc == PSB_OK; ++k) {
+        if (!jobs[k].ev0) continue;
+        rc = scan_finish(jobs[k]);
+        b->n_retried += jobs[k].retried;
+    }
     for (auto &B : builds) if (B.db) psb_db_free(B.db);
     if (rc != PSB_OK) { free_batch(b); return rc; }
     *out = b;

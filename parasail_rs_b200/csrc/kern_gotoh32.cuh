@@ -49,6 +49,12 @@ struct Gotoh32Params {
     const int *out_map;         // results are written at out_map[pair id] (NULL: pair id)
     int *tabH, *tabM, *tabS, *tabL;  // TABLE only: per-cell planes, same indexing as the trace
     const long long *tab_off;   // element offset of each pair's table block (indexed by pair id)
+    // database scans read their subjects straight from the bit-packed store (r / r_off unused):
+    const unsigned *r_words;    // packed residues (kern_util.cuh layout), NULL for byte subjects
+    const long long *r_word_off;  // first word of each subject (indexed by pair id)
+    const int *r_len;           // residues of each subject
+    int r_bits;                 // 5 or 2
+    const int *n_dev;           // when set, the number of work items is read from device memory
 };
 
 // statistics word: matches | similar | length packed so that one add updates all three
@@ -121,14 +127,15 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
         int slot = 0;
         if (lane == 0) slot = atomic_add(p.counter, 1);
         slot = shfl(slot, 0);
-        if (slot >= p.n) break;
+        if (slot >= (p.n_dev ? ld_cg(p.n_dev) : p.n)) break;
         const int pid = p.order ? p.order[slot] : slot;
         const long long qo = p.shared_query ? p.q_off[0] : p.q_off[pid];
         const int Lq = (int)((p.shared_query ? p.q_off[1] : p.q_off[pid + 1]) - qo);
-        const long long ro = p.r_off[pid];
-        const int Lr = (int)(p.r_off[pid + 1] - ro);
+        const bool packed = p.r_words != nullptr;
+        const long long ro = packed ? p.r_word_off[pid] : p.r_off[pid];
+        const int Lr = packed ? p.r_len[pid] : (int)(p.r_off[pid + 1] - ro);
         const uint8_t *q = p.q + qo;
-        const uint8_t *r = p.r + ro;
+        const uint8_t *r = packed ? nullptr : p.r + ro;
         const int rows_per_strip = 32 * K;
         const int nstrips = (Lq + rows_per_strip - 1) / rows_per_strip;
         const int nsteps = Lr + 31;
@@ -188,7 +195,14 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                     sync_warp();
                     const int c = s + lane;
                     if (c < Lr) {
-                        ringL[c & 63] = r[c];
+                        if (packed) {
+                            const unsigned word = p.r_bits == 2 ? p.r_words[ro + (c >> 4)]
+                                                                : p.r_words[ro + (int)(((unsigned long long)(unsigned)c * 0xAAAAAAABull) >> 34)];
+                            const int within = p.r_bits == 2 ? (c & 15) : c - 6 * (int)(((unsigned long long)(unsigned)c * 0xAAAAAAABull) >> 34);
+                            ringL[c & 63] = (uint8_t)((word >> (p.r_bits * within)) & ((1u << p.r_bits) - 1u));
+                        } else {
+                            ringL[c & 63] = r[c];
+                        }
                         if (strip > 0) {
                             ringT[c & 63] = ld_cg(bndT + c);
                             ringF[c & 63] = ld_cg(bndF + c);

@@ -32,7 +32,8 @@ class Gotoh32Params(C.Structure):
                 ("matches", C.c_void_p), ("similar", C.c_void_p), ("length", C.c_void_p), ("bnd", C.c_void_p),
                 ("bnd_stride", C.c_longlong), ("trace", C.c_void_p), ("trace_off", C.c_void_p),
                 ("counter", C.c_void_p), ("out_map", C.c_void_p), ("tabH", C.c_void_p), ("tabM", C.c_void_p),
-                ("tabS", C.c_void_p), ("tabL", C.c_void_p), ("tab_off", C.c_void_p)]
+                ("tabS", C.c_void_p), ("tabL", C.c_void_p), ("tab_off", C.c_void_p), ("r_words", C.c_void_p),
+                ("r_word_off", C.c_void_p), ("r_len", C.c_void_p), ("r_bits", C.c_int), ("n_dev", C.c_void_p)]
 
 
 def trace_to_rowmajor(blob, off, K, lq, lr):
@@ -50,7 +51,7 @@ def trace_to_rowmajor(blob, off, K, lq, lr):
 
 
 def gotoh32(qs, rs, mat, K, mode, open, gap, flags=(1, 1, 1, 1), stats=False, trace=False, wide=False,
-            shared_query=False, nblocks=1, profile=False):
+            shared_query=False, nblocks=1, profile=False, packed_bits=0):
     """Run the emulated general kernel on pairs (lists of uint8 arrays of raw residues)."""
     assert lib().emu_sizeof_params() == C.sizeof(Gotoh32Params)
     mapper = mat.mapper.astype(np.uint8)
@@ -80,7 +81,15 @@ def gotoh32(qs, rs, mat, K, mode, open, gap, flags=(1, 1, 1, 1), stats=False, tr
                       mat.size, int(mat.is_pssm), open, gap, mode, flags[0], flags[1], flags[2], flags[3],
                       ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(outs["matches"]),
                       ptr(outs["similar"]), ptr(outs["length"]), ptr(bnd), per_col * maxlr, ptr(blob),
-                      ptr(trace_off), ptr(counter), None, None, None, None, None, None)
+                      ptr(trace_off), ptr(counter), None, None, None, None, None, None, None, None, None, 0, None)
+    if packed_bits:
+        # subjects from the bit-packed store, in the store's (length-sorted) order; work count from memory
+        words, word_off, lens, perm = pack_db(rm, packed_bits)
+        ndev = np.array([n], dtype=np.int32)
+        p.r_words, p.r_word_off, p.r_len, p.r_bits = ptr(words).value, ptr(word_off).value, ptr(lens).value, packed_bits
+        p.out_map, p.n_dev = ptr(perm).value, ptr(ndev).value
+        p.n = n + 5   # the bound is not the count
+        keep_alive = (words, word_off, lens, perm, ndev)
     lib().emu_gotoh32_use_profile(int(profile))
     rc = lib().emu_gotoh32(K, int(stats), int(trace), int(wide), C.byref(p), nblocks)
     lib().emu_gotoh32_use_profile(0)

@@ -85,3 +85,20 @@ def test_per_warp_profile_variant(oracle, blosum62, mode, variant):
     mat = oracle.Matrix.create(b"ACGT", 2, -3)
     qs, rs = pairs(62, 3, (1, 90), (1, 90), False)
     compare(oracle, mat, qs, rs, 2, mode, 0, 0, stats=variant == "stats", trace=variant == "trace", profile=True)
+
+
+@pytest.mark.parametrize("bits,protein", [(5, True), (2, False)])
+def test_packed_subjects_and_device_count(oracle, blosum62, bits, protein):
+    # database-scan form: one query, subjects read from the 5-bit / 2-bit packed store, results
+    # scattered through out_map, number of work items read from device memory
+    mat = blosum62 if protein else oracle.Matrix.create(b"ACG", 2, -3)   # 4 columns incl. wildcard -> 2 bits
+    q = psb_data.random_seq(71, 0, 70, protein) if protein else np.frombuffer(b"ACGACGGACCAGCAGGCA", dtype=np.uint8)
+    subs = [psb_data.random_seq(72, i, 20 + 13 * i, protein) for i in range(5)]
+    if not protein:
+        subs = [np.frombuffer(bytes(s).replace(b"T", b"A"), dtype=np.uint8) for s in subs]
+    for mode in (0, 2):
+        got = emu_harness.gotoh32([q], subs, mat, 2, mode, 5, 2, shared_query=True, profile=True, packed_bits=bits, stats=True)
+        for i, s_ in enumerate(subs):
+            exp = oracle.align(q, s_, mat, mode=mode, open=5, gap=2)
+            assert (got["score"][i], got["end_query"][i], got["end_ref"][i], got["matches"][i], got["length"][i]) == \
+                (exp["score"], exp["end_query"], exp["end_ref"], exp["matches"], exp["length"]), (mode, i)
