@@ -938,11 +938,11 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         p.words = db->d_words; p.bits = db->bits;
         p.score = d_out[0]; p.end_query = d_out[1]; p.end_ref = d_out[2];
         p.retry = d_retry.as<int>(); p.retry_count = d_cnt.as<int>();
-        p.mul_one = 1u; p.mul_16 = 16u;
+        p.mul_one = 1u; p.mul_64k = 65536u;
         const void *fn = sw16_fn(sp.K);
         if (!fn) { set_error("sw16: no kernel for this query length"); return PSB_EUNSUPPORTED; }
-        const size_t smem = sw16_smem_bytes(sp.nletters, sp.chunks, kSw16WarpsPerBlock);
-        const size_t smem_excl = std::max<size_t>(sw16_smem_bytes(sp.nletters, sp.chunks, 4), 150 * 1024);
+        const size_t smem = sw16_smem_bytes(sp.nletters, sp.K, kSw16WarpsPerBlock);
+        const size_t smem_excl = std::max<size_t>(sw16_smem_bytes(sp.nletters, sp.K, 4), 150 * 1024);
         PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, smem_excl)));
         int per_sm = 0;
         PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSw16WarpsPerBlock * 32, smem));
@@ -1054,13 +1054,72 @@ namespace psb {
 // caller's stream or the context's copy stream).  Phase B (db_finish): lengths, stable radix sort
 // by decreasing length, word offsets (scan), residue mapping + bit packing, all on the compute
 // stream and without any host synchronisation.
+// Device staging blocks for psb_scan_host's uploads.  They are filled on the copy stream while the
+// compute stream is busy, so they cannot come from a stream-ordered pool without tying the two
+// streams together (an allocation that cannot reuse a block freed on the other stream falls back to
+// mapping fresh memory, a host-blocking call of tens of milliseconds).  Plain allocations, recycled
+// process-wide; a block is handed back only after both streams have been synchronised.
+struct StageBlock { void *p; size_t bytes; int device; };
+static std::mutex g_stage_mu;
+static std::vector<StageBlock> g_stage_free;
+static size_t g_stage_cached = 0;
+static void *stage_acquire(int device, size_t need, size_t *got) {
+    const size_t gran = (size_t)8 << 20;
+    const size_t want = (need + gran - 1) / gran * gran;
+    {
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        int pick = -1;
+        for (int i = 0; i < (int)g_stage_free.size(); ++i) {
+            const StageBlock &b = g_stage_free[i];
+            if (b.device == device && b.bytes >= want && b.bytes <= 2 * want && (pick < 0 || b.bytes < g_stage_free[pick].bytes)) pick = i;
+        }
+        if (pick >= 0) {
+            StageBlock b = g_stage_free[pick];
+            g_stage_free.erase(g_stage_free.begin() + pick);
+            g_stage_cached -= b.bytes;
+            *got = b.bytes;
+            return b.p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *got = want;
+    return p;
+}
+static void stage_release(int device, void *p, size_t bytes) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        if (g_stage_cached + bytes <= ((size_t)4 << 30) && g_stage_free.size() < 256) {
+            g_stage_free.push_back({p, bytes, device});
+            g_stage_cached += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
 struct DbBuild {
     psb_db *db = nullptr;
     DevMem d_raw, d_off, d_len0, d_idx0, d_wcount, d_tmp;
+    // copy-stream uploads use recycled staging blocks instead of d_raw / d_off
+    void *st_raw = nullptr, *st_off = nullptr;
+    size_t st_raw_bytes = 0, st_off_bytes = 0;
+    int st_device = 0;
     cudaEvent_t uploaded = nullptr;
     long long raw_base = 0;
     unsigned lut[64];
-    ~DbBuild() { if (uploaded) cudaEventDestroy(uploaded); }
+    uint8_t *raw() const { return st_raw ? (uint8_t *)st_raw : d_raw.as<uint8_t>(); }
+    long long *offs() const { return st_off ? (long long *)st_off : d_off.as<long long>(); }
+    DbBuild() = default;
+    DbBuild(const DbBuild &) = delete;
+    DbBuild &operator=(const DbBuild &) = delete;
+    // the owner synchronises the streams that used the staging blocks before destroying this
+    ~DbBuild() {
+        if (uploaded) cudaEventDestroy(uploaded);
+        stage_release(st_device, st_raw, st_raw_bytes);
+        stage_release(st_device, st_off, st_off_bytes);
+    }
 };
 
 static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int64_t n, const HostMatrix &hm, bool use_copy_stream) {
@@ -1098,12 +1157,18 @@ static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int6
         for (int t = 0; t < hist[l] && db->top_len.size() < 4096; ++t) db->top_len.push_back(l);
 
     const size_t n1 = (size_t)n + 1;
-    // with the copy stream, the staging buffers are allocated in ITS order: the upload must not queue
-    // behind whatever scan is already running on the compute stream.  They are consumed (and freed)
-    // on the compute stream, which waits for the `uploaded` event.
+    // with the copy stream, the upload must not queue behind whatever scan is already running on the
+    // compute stream: its staging blocks are recycled plain allocations (see StageBlock)
     cudaStream_t up = use_copy_stream ? c.copy : c.stream;
-    if (B.d_raw.alloc((size_t)db->residues, up) != PSB_OK || B.d_off.alloc(n1 * 8, up) != PSB_OK ||
-        B.d_len0.alloc((size_t)n * 4, c.stream) != PSB_OK || B.d_idx0.alloc((size_t)n * 4, c.stream) != PSB_OK ||
+    if (use_copy_stream) {
+        B.st_device = c.device;
+        B.st_raw = stage_acquire(c.device, (size_t)db->residues, &B.st_raw_bytes);
+        B.st_off = stage_acquire(c.device, n1 * 8, &B.st_off_bytes);
+        if (!B.st_raw || !B.st_off) return fail("psb_scan_host: device allocation of the staging blocks failed");
+    } else if (B.d_raw.alloc((size_t)db->residues, up) != PSB_OK || B.d_off.alloc(n1 * 8, up) != PSB_OK) {
+        return fail(psb_last_error());
+    }
+    if (B.d_len0.alloc((size_t)n * 4, c.stream) != PSB_OK || B.d_idx0.alloc((size_t)n * 4, c.stream) != PSB_OK ||
         B.d_wcount.alloc(n1 * 8, c.stream) != PSB_OK)
         return fail(psb_last_error());
     cudaError_t e = cudaSuccess;
@@ -1113,9 +1178,8 @@ static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int6
     ck(cudaMallocAsync(&db->d_len, (size_t)n * 4, c.stream));
     ck(cudaMallocAsync(&db->d_words, (size_t)db->words * 4 + 64, c.stream));
     if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
-    B.d_raw.s = c.stream; B.d_off.s = c.stream;
-    ck(cudaMemcpyAsync(B.d_off.p, off, n1 * 8, cudaMemcpyHostToDevice, up));
-    ck(cudaMemcpyAsync(B.d_raw.p, cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, up));
+    ck(cudaMemcpyAsync(B.offs(), off, n1 * 8, cudaMemcpyHostToDevice, up));
+    ck(cudaMemcpyAsync(B.raw(), cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, up));
     if (use_copy_stream) {
         ck(cudaEventCreateWithFlags(&B.uploaded, cudaEventDisableTiming));
         ck(cudaEventRecord(B.uploaded, up));
@@ -1133,7 +1197,7 @@ static int db_finish(DbBuild &B) {
     const size_t n1 = (size_t)n + 1;
     const int rpw = db->bits == 2 ? 16 : 6;
     if (B.uploaded) PSB_CUDA(cudaStreamWaitEvent(c.stream, B.uploaded, 0));
-    db_lengths_kernel<<<c.sms * 4, 256, 0, c.stream>>>(B.d_off.as<long long>(), n, B.d_len0.as<int>(), B.d_idx0.as<int>());
+    db_lengths_kernel<<<c.sms * 4, 256, 0, c.stream>>>(B.offs(), n, B.d_len0.as<int>(), B.d_idx0.as<int>());
     size_t tb = 0, tb2 = 0;
     PSB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, B.d_len0.as<int>(), db->d_len, B.d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
     PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, B.d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
@@ -1142,7 +1206,7 @@ static int db_finish(DbBuild &B) {
     db_wcount_sorted_kernel<<<c.sms * 4, 256, 0, c.stream>>>(db->d_len, n, rpw, B.d_wcount.as<long long>());
     PSB_CUDA(cub::DeviceScan::ExclusiveSum(B.d_tmp.p, tb2, B.d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
     PackParams pp;
-    pp.raw = B.d_raw.as<uint8_t>(); pp.raw_off = B.d_off.as<long long>(); pp.raw_base = B.raw_base; pp.perm = db->d_perm;
+    pp.raw = B.raw(); pp.raw_off = B.offs(); pp.raw_base = B.raw_base; pp.perm = db->d_perm;
     pp.word_off = db->d_word_off; pp.words = db->d_words; pp.n = n; pp.bits = db->bits;
     std::memcpy(pp.lut, B.lut, sizeof(pp.lut));
     pack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(pp);

@@ -40,11 +40,24 @@ namespace psb {
 
 static constexpr int SW16_G = 16;  // lanes per group
 
+// SW16_PROF32=1: the profile holds one 32-bit word (S+o, zero-extended 16 bit) per letter and row, and
+// the two subjects' scores are joined by (b << 16) + a, an add-class instruction that issues at twice
+// the rate of the DPX/PRMT pipe the recurrence saturates.  SW16_PROF32=0: int8 profile joined by PRMT
+// (4x less shared-memory traffic, one more instruction per row on the saturated pipe).
+#ifndef SW16_PROF32
+#define SW16_PROF32 1
+#endif
+// rows of one letter that one LDS.128 fetches for a lane
+static constexpr int SW16_ROWS_PER_LOAD = SW16_PROF32 ? 4 : 16;
+inline constexpr int sw16_chunks(int K) { return (K + SW16_ROWS_PER_LOAD - 1) / SW16_ROWS_PER_LOAD; }
+// words per lane and half of the parked H column (>= K, a multiple of 4)
+inline constexpr int sw16_park_words(int K) { return SW16_PROF32 ? ((K + 3) / 4) * 4 : ((K + 15) / 16) * 16; }
+
 struct Sw16Profile {
-    int8_t *prof = nullptr;  // device: [nletters][chunks][16 lanes][16] bytes of (S + open); pad letter last
+    int8_t *prof = nullptr;  // device: [nletters][chunks][16 lanes][16 bytes] of (S + open); pad letter last
     int lq = 0;
     int K = 0;               // rows per lane
-    int chunks = 0;          // ceil(K / 16)
+    int chunks = 0;          // sw16_chunks(K): 16-byte loads per lane and letter
     int nletters = 0;        // alphabet size + 1 (the pad letter)
     int max_score = 0, min_score = 0;
     int open_baked = -1;
@@ -64,12 +77,26 @@ inline bool sw16_build_profile(const uint8_t *mapped_query, int lq, const int *t
                                Sw16Profile *out, std::vector<int8_t> *host) {
     const int K = sw16_pick_k(lq);
     if (K == 0 || size + 1 > 32) return false;
-    out->lq = lq; out->K = K; out->chunks = (K + 15) / 16; out->nletters = size + 1; out->open_baked = open;
+    out->lq = lq; out->K = K; out->chunks = sw16_chunks(K); out->nletters = size + 1; out->open_baked = open;
     int mx = -1000000, mn = 1000000;
     for (int i = 0; i < size * size; ++i) { mx = table[i] > mx ? table[i] : mx; mn = table[i] < mn ? table[i] : mn; }
     out->max_score = mx; out->min_score = mn;
     if (!sw16_supported(*out, open, 0)) return false;
     const size_t ls = sw16_letter_stride(out->chunks);
+#if SW16_PROF32
+    // rows past the query and the pad letter score S+o = -128, as in the int8 layout
+    host->assign((size_t)(size + 1) * ls, (int8_t)0);
+    unsigned *w = (unsigned *)host->data();
+    for (size_t x = 0; x < host->size() / 4; ++x) w[x] = 0xff80u;
+    for (int a = 0; a < size; ++a)
+        for (int lane = 0; lane < SW16_G; ++lane)
+            for (int k = 0; k < K; ++k) {
+                const int i = lane * K + k;
+                if (i < lq)
+                    w[((size_t)a * ls + ((size_t)(k >> 2) * SW16_G + lane) * 16) / 4 + (k & 3)] =
+                        (unsigned)(table[(size_t)mapped_query[i] * size + a] + open) & 0xffffu;
+            }
+#else
     host->assign((size_t)(size + 1) * ls, (int8_t)-128);
     for (int a = 0; a < size; ++a)
         for (int lane = 0; lane < SW16_G; ++lane)
@@ -79,6 +106,7 @@ inline bool sw16_build_profile(const uint8_t *mapped_query, int lq, const int *t
                     (*host)[(size_t)a * ls + ((size_t)(k >> 4) * SW16_G + lane) * 16 + (k & 15)] =
                         (int8_t)(table[(size_t)mapped_query[i] * size + a] + open);
             }
+#endif
     return true;
 }
 
@@ -100,14 +128,14 @@ struct Sw16Params {
     int sid_base;                 // added to a subject index before it is pushed to `retry`
     int *counter;                 // dynamic work queue over pairs of items
     unsigned mul_one;             // the constant 1, kept opaque so that T = X*1 - o can be an IMAD
-    unsigned mul_16;              // (unused by this kernel generation)
+    unsigned mul_64k;             // the constant 65536, opaque for the same reason: (b << 16) + a as an IMAD
 };
 
 // per warp: 2 rings of 64 words, 2 published group bests (padded to 16 B), and 2 halves x 32 lanes x
-// chunks*16 words of parked H columns
-inline size_t sw16_warp_smem(int chunks) { return 2 * 64 * 4 + 16 + (size_t)2 * 32 * chunks * 16 * 4; }
-inline size_t sw16_smem_bytes(int nletters, int chunks, int warps) {
-    return (size_t)nletters * sw16_letter_stride(chunks) + (size_t)warps * sw16_warp_smem(chunks);
+// sw16_park_words(K) words of parked H columns
+inline size_t sw16_warp_smem(int K) { return 2 * 64 * 4 + 16 + (size_t)2 * 32 * sw16_park_words(K) * 4; }
+inline size_t sw16_smem_bytes(int nletters, int K, int warps) {
+    return (size_t)nletters * sw16_letter_stride(sw16_chunks(K)) + (size_t)warps * sw16_warp_smem(K);
 }
 
 PSB_DEV unsigned sw16_fetch_code(const unsigned *words, long long w0, int len, int c, int bits, int pad_code) {
@@ -138,7 +166,7 @@ PSB_DEV unsigned sw16_fetch_code(const unsigned *words, long long w0, int len, i
 template <int K>
 PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
     constexpr int G = SW16_G;
-    constexpr int CH = (K + 15) / 16;                 // 16-row chunks per lane
+    constexpr int CH = (K + SW16_ROWS_PER_LOAD - 1) / SW16_ROWS_PER_LOAD;   // = sw16_chunks(K): 16-byte profile loads per lane and letter
     constexpr unsigned LSTRIDE = CH * G * 16;         // bytes per letter
     PSB_SHARED_DECL(smem_raw);
     const int lane = lane_id();
@@ -153,7 +181,7 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
     }
     sync_block();
     const unsigned char *lane_base = smem_raw + lg * 16;
-    constexpr int PARKW = CH * 16;                    // parked words per lane and half (>= K)
+    constexpr int PARKW = SW16_PROF32 ? ((K + 3) / 4) * 4 : ((K + 15) / 16) * 16;   // = sw16_park_words(K)
     unsigned char *wsm = smem_raw + (size_t)p.nletters * LSTRIDE + (size_t)warp_in_block() * (2 * 64 * 4 + 16 + 2 * 32 * PARKW * 4);
     unsigned *ring = (unsigned *)wsm + grp * 64;
     volatile unsigned *gpub = (volatile unsigned *)(wsm + 2 * 64 * 4) + grp;   // group best - 1, per half
@@ -163,6 +191,8 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
     const unsigned NEGE = ((unsigned)(-p.gap) & 0xffffu) * 0x10001u;
     const unsigned NEGO = 0u - O2;
     const unsigned one = p.mul_one;
+    const unsigned m64k = p.mul_64k;
+    (void)m64k;
     const long long nitems = (p.n + 1) >> 1;
     const long long nslots = (nitems + 1) >> 1;       // a warp takes two items at a time
     const int limit = 32767 - p.open - p.max_score;   // scores from here on may have wrapped
@@ -230,9 +260,13 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                     unsigned cmax = 0, tprev = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
+#if SW16_PROF32
+                        const unsigned So = wbs[k] * m64k + was[k];
+#else
                         constexpr unsigned SEL0 = 0xC480u;
                         const unsigned sel = SEL0 + (unsigned)(k & 3) * 0x1111u;
                         const unsigned So = prmt(was[k >> 2], wbs[k >> 2], sel);
+#endif
                         const unsigned Tl = Tin[k];
                         const unsigned En = viaddmax2(E[k], NEGE, Tl);
                         const unsigned Fn = viaddmax2(Fu, NEGE, Tu);

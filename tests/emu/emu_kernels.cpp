@@ -53,7 +53,7 @@ extern "C" int emu_sw16_build(const uint8_t *mapped_query, int lq, const int *ta
 
 extern "C" int emu_sw16(int K, const Sw16Params *pp, int nblocks) {
     Sw16Params p = *pp;
-    size_t smem = sw16_smem_bytes(p.nletters, (K + 15) / 16, 1);
+    size_t smem = sw16_smem_bytes(p.nletters, K, 1);
 #define SCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { sw16_scan_kernel<KK>(p); }); return 0;
     switch (K) { SCASE(4) SCASE(8) SCASE(12) SCASE(16) SCASE(20) SCASE(25) SCASE(28) SCASE(32) }
     return -1;

@@ -105,7 +105,7 @@ class Sw16Params(C.Structure):
                 ("max_score", C.c_int), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
                 ("bits", C.c_int), ("n", C.c_longlong), ("out_map", C.c_void_p), ("score", C.c_void_p),
                 ("end_query", C.c_void_p), ("end_ref", C.c_void_p), ("retry", C.c_void_p),
-                ("retry_count", C.c_void_p), ("sid_base", C.c_int), ("counter", C.c_void_p), ("mul_one", C.c_uint), ("mul_16", C.c_uint)]
+                ("retry_count", C.c_void_p), ("sid_base", C.c_int), ("counter", C.c_void_p), ("mul_one", C.c_uint), ("mul_64k", C.c_uint)]
 
 
 def pack_db(subjects_mapped, bits):
@@ -138,7 +138,7 @@ def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1):
     qm = np.ascontiguousarray(mapper[np.asarray(query, dtype=np.uint8)])
     sm = [mapper[np.asarray(s, dtype=np.uint8)] for s in subjects]
     table = np.ascontiguousarray(mat.table, dtype=np.int32)
-    prof = np.zeros(33 * 512, dtype=np.int8)
+    prof = np.zeros(33 * 2048, dtype=np.int8)
     K, mx, ch = C.c_int(), C.c_int(), C.c_int()
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     nb = lib().emu_sw16_build(ptr(qm), len(qm), ptr(table), mat.size, open, ptr(prof), prof.size, C.byref(K), C.byref(mx),
@@ -152,7 +152,7 @@ def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1):
     counter = np.zeros(1, dtype=np.int32)
     p = Sw16Params(ptr(prof), mat.size + 1, len(qm), open, gap, mx.value, ptr(words), ptr(word_off), ptr(lens), bits, n,
                    ptr(perm), ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(retry),
-                   ptr(retry_count), 0, ptr(counter), 1, 16)
+                   ptr(retry_count), 0, ptr(counter), 1, 65536)
     rc = lib().emu_sw16(K.value, C.byref(p), nblocks)
     assert rc == 0, (rc, K.value)
     return outs, sorted(int(perm[i]) for i in retry[: retry_count[0]])
