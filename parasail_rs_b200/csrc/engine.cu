@@ -280,6 +280,14 @@ static const void *wave32_fn(int K, bool v2) {
     }
     return nullptr;
 }
+static const void *wave32v3_fn(int K) {
+    switch (K) {
+        case 4: return (const void *)wave32v3_kernel<4, 4>;
+        case 8: return (const void *)wave32v3_kernel<8, 4>;
+        case 16: return (const void *)wave32v3_kernel<16, 4>;
+    }
+    return nullptr;
+}
 // the latency-optimised generation needs open >= extend and byte-sized (score + open)
 static bool wave32_v2_ok(const HostMatrix &m, int open, int gap) {
     return open >= gap && gotoh32_profile_ok(m.size, m.min, m.max, open, m.type == PARASAIL_MATRIX_TYPE_PSSM);
@@ -288,37 +296,69 @@ static bool wave32_v2_ok(const HostMatrix &m, int open, int gap) {
 static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long q_byte_off, int lq, long long r_byte_off, int lr, int out_index) {
     Ctx &c = g_ctx;
     // strips of 32*K rows: enough strips to occupy the chip, as few as possible beyond that
-    const int K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4);
+    int K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4);
+    int wpb = kWarpsPerBlock;
     const bool v2 = wave32_v2_ok(m, g.open, g.gap);
-    const void *fn = wave32_fn(K, v2);
+    // local alignments take the column-blocked generation (K x 4 tiles per lane and step): the shortest
+    // critical path, Lq/K + Lr/4 steps, with the smallest K whose strips are all resident at once
+    bool v3 = v2 && g.mode == MODE_SW;
+    // experiment knobs (tools/c5_probe.py): generation, rows per lane and warps per CTA of the launch
+    if (const char *ev = std::getenv("PSB_WAVE_GEN")) { if (std::atoi(ev) == 2) v3 = false; }
+    if (v3) {
+        // measured on C5 (tools/c5_probe.py): a step costs about the same for 4 and 8 rows per lane (a
+        // warp alone on its scheduler is bound by per-step latencies) and twice as much for 16, while
+        // every strip adds ~34 steps to the path: 8 rows, 4 warps per CTA (one per scheduler)
+        K = 8; wpb = 4;
+        if ((lq + 32 * K - 1) / (32 * K) > c.sms * 16) K = 16;
+        if ((lq + 32 * K - 1) / (32 * K) > c.sms * 16 || !wave32v3_score_fits(K, 4, std::min(lq, lr), m.max)) v3 = false;
+        if (!v3) { K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4); wpb = kWarpsPerBlock; }
+    }
+    if (const char *ev = std::getenv("PSB_WAVE_K")) {
+        const int k = std::atoi(ev);
+        if ((k == 1 || k == 2 || k == 4 || k == 8 || k == 16) && (!v3 || k >= 4)) K = k;
+    }
+    if (const char *ev = std::getenv("PSB_WAVE_WARPS")) { const int w = std::atoi(ev); if (w >= 1 && w <= 32) wpb = w; }
+    const void *fn = v3 ? wave32v3_fn(K) : wave32_fn(K, v2);
     const int nstrips = (lq + 32 * K - 1) / (32 * K);
     DevMem d_bnd, d_ctl, d_cand;
     PSB_TRY(d_bnd.alloc((size_t)nstrips * 2 * (size_t)lr * sizeof(int), c.stream));
     PSB_TRY(d_ctl.alloc(((size_t)nstrips + 2) * sizeof(int), c.stream));
     PSB_TRY(d_cand.alloc((size_t)nstrips * 8 * sizeof(int), c.stream));
     PSB_CUDA(cudaMemsetAsync(d_ctl.p, 0, ((size_t)nstrips + 2) * sizeof(int), c.stream));
+    // generation 3 hands rows over through self-validating words: the lines start out all-zero (invalid)
+    if (v3) PSB_CUDA(cudaMemsetAsync(d_bnd.p, 0, (size_t)nstrips * 2 * (size_t)lr * sizeof(int), c.stream));
     Wave32Params p;
     p.q = g.q + q_byte_off; p.r = g.r + r_byte_off; p.Lq = lq; p.Lr = lr;
     p.matrix = g.matrix; p.size = g.size; p.open = g.open; p.gap = g.gap;
     p.mode = g.mode; p.s1_beg = g.s1_beg; p.s1_end = g.s1_end; p.s2_beg = g.s2_beg; p.s2_end = g.s2_end;
     p.bnd = d_bnd.as<int>(); p.progress = d_ctl.as<int>() + 1; p.next_strip = d_ctl.as<int>(); p.cand = d_cand.as<int>();
     p.multi_n = 0; p.r_off = nullptr;
-    const size_t smem = v2 ? wave32v2_smem_bytes(g.size, kWarpsPerBlock) : wave32_smem_bytes(g.size, kWarpsPerBlock);
+    const size_t smem = v3 ? wave32v3_smem_bytes(g.size, wpb) : (v2 ? wave32v2_smem_bytes(g.size, wpb) : wave32_smem_bytes(g.size, wpb));
     if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * 32, smem));
+    PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpb * 32, smem));
     if (per_sm < 1) per_sm = 1;
     // every launched warp must be resident at once: the strips wait on one another
-    long long blocks = std::min<long long>((nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock, (long long)c.sms * per_sm);
+    long long blocks = std::min<long long>((nstrips + wpb - 1) / wpb, (long long)c.sms * per_sm);
     if (blocks < 1) blocks = 1;
     void *args[] = {&p};
-    PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kWarpsPerBlock * 32), args, smem, c.stream));
+    PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(wpb * 32), args, smem, c.stream));
     WaveReduceParams r;
     r.cand = d_cand.as<int>(); r.nstrips = nstrips; r.mode = g.mode; r.s1_end = g.s1_end; r.s2_end = g.s2_end; r.Lr = lr;
     r.score = g.score + out_index; r.end_query = g.end_query + out_index; r.end_ref = g.end_ref + out_index;
     r.multi_n = 0; r.r_off = nullptr; r.out_map = nullptr; r.first_id = 0;
     wave32_reduce_kernel<<<1, 32, 0, c.stream>>>(r);
     c.launches += 2;
+    if (v3 && std::getenv("PSB_DEBUG_TIMING")) {
+        // per-strip timeline of the column-blocked kernel: claimed / first columns available / done (us)
+        std::vector<int> h((size_t)nstrips * 8);
+        PSB_CUDA(cudaMemcpyAsync(h.data(), d_cand.p, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        PSB_CUDA(cudaStreamSynchronize(c.stream));
+        const int t0 = h[5];
+        for (int k = 0; k < nstrips; k = k < 8 ? k + 1 : k + std::max(1, nstrips / 12))
+            std::fprintf(stderr, "[psb] wave strip %4d: claimed %7d us, first columns %7d us, done %7d us\n", k, h[(size_t)k * 8 + 5] - t0,
+                         h[(size_t)k * 8 + 6] - t0, h[(size_t)k * 8 + 7] - t0);
+    }
     return PSB_OK;
 }
 

@@ -10,12 +10,18 @@
 // counter by persistent warps that are all resident at once; strip b may start column chunk c as
 // soon as strip b-1 has published the bottom row (T, F) of that chunk to its boundary line in
 // global memory -- so the strips themselves form a second, coarser anti-diagonal wavefront across
-// the SMs.  Publication is a release-store of a column counter after a __threadfence; the consumer
-// polls it with an acquire-load.  Waiting is deadlock-free because a warp only ever waits for the
+// the SMs.  Publication is a release-store (st.release.gpu) of a column counter by the lane that wrote
+// the boundary values; the consumer's lane 0 polls it with an acquire-load and the warp then reads the
+// line behind a warp barrier.  Waiting is deadlock-free because a warp only ever waits for the
 // strip claimed immediately before its own, which belongs to a warp that is running or finished.
 #pragma once
 #include "psb_defs.h"
 #include "psb_simt.h"
+
+#ifndef PSB_UNROLL
+#define PSB_PRAGMA_(x) _Pragma(#x)
+#define PSB_UNROLL(n) PSB_PRAGMA_(unroll n)
+#endif
 
 namespace psb {
 
@@ -50,7 +56,18 @@ PSB_DEV int ld_acquire(const int *p) {
 }
 PSB_DEV void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 PSB_DEV void backoff() { __nanosleep(64); }
+// 64-bit relaxed accesses at GPU scope: single-copy atomic, served by L2, never hoisted out of a poll loop
+PSB_DEV long long ld_relaxed64(const long long *p) {
+    long long v;
+    asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+PSB_DEV void st_relaxed64(long long *p, long long v) { asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+PSB_DEV int wave_time_us() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (int)(t >> 10); }
 #else
+inline int wave_time_us() { return 0; }
+inline long long ld_relaxed64(const long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void st_relaxed64(long long *p, long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 inline int ld_acquire(const int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void st_release(int *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void backoff() {}
@@ -116,9 +133,6 @@ PSB_KERNEL void wave32_kernel(Wave32Params p) {
                 // publish what lane 31 has finished (columns < s - 31), then wait for the strip above
                 sync_warp();
                 if (!last_strip && lane == 31 && s >= 32) {
-#if !defined(PSB_EMULATE)
-                    __threadfence();
-#endif
                     st_release(progress + strip, s - 31);
                 }
                 const int need = (s + 32 < Lr) ? s + 32 : Lr;   // columns [s, need) are staged now
@@ -181,9 +195,6 @@ PSB_KERNEL void wave32_kernel(Wave32Params p) {
         // the whole bottom row is out
         sync_warp();
         if (!last_strip && lane == 31) {
-#if !defined(PSB_EMULATE)
-            __threadfence();
-#endif
             st_release(progress + strip, Lr);
         }
         // merge the strip's lanes: (score desc, end_ref asc, end_query asc)
@@ -296,9 +307,6 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
             if ((s & 31) == 0) {
                 sync_warp();
                 if (!last_strip && lane == 31 && s >= 32) {
-#if !defined(PSB_EMULATE)
-                    __threadfence();
-#endif
                     st_release(progress + strip, s - 31);
                 }
                 const int need = (s + 33 < Lr) ? s + 33 : Lr;   // columns [s+1, need) are staged now
@@ -371,9 +379,6 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
         }
         sync_warp();
         if (!last_strip && lane == 31) {
-#if !defined(PSB_EMULATE)
-            __threadfence();
-#endif
             st_release(progress + strip, Lr);
         }
 #pragma unroll
@@ -386,6 +391,235 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
         if (lane == 0) {
             int *c = p.cand + (long long)item * 8;
             c[0] = bestH; c[1] = bestJ; c[2] = bestI; c[3] = colH; c[4] = colI;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Generation 3 (local alignment, open >= extend, byte-sized S + open): column-blocked strips.
+//
+// What bounds one long pair is the critical path, not throughput: the wavefront has to cross
+// Lq/K lanes and Lr/C column blocks, one step each, and a warp that runs alone on its scheduler
+// pays ~4 cycles per instruction whatever it does.  Generation 2 moved one column per step and
+// spent ~100 of its ~130 instructions per step on bookkeeping (ncu, profiles/r1e_ncu_wave_*).
+// Here a lane owns K rows and fills C consecutive columns per step (a K x C tile), so the
+// per-step bookkeeping -- shuffles, ring reads, boundary stores, the end-cell update -- is paid once
+// per C columns, the path is Lq/K + Lr/C steps long, and the tile's cells give the scheduler
+// independent work (rows of column c+1 can start as soon as row 0 of column c is done).
+//   * lane t fills column block b = s - t at step s; its bottom row's (T, F) of the C columns and
+//     the block's four residues travel to lane t+1 by shfl_up;
+//   * strip hand-over without fences or counters: lane 31 stores each bottom-row column as ONE
+//     64-bit word (T with bit 30 flipped, F).  |T| < 2^30, so a written word has different top two
+//     bits in its T half, which the zero-filled line can never show: every word validates itself.
+//     Lane 0 of the strip below loads the four words of block s+2 straight from the line (relaxed,
+//     L2) while it works on block s -- two alternating register sets, no moves -- and checks them when
+//     their step comes; only a strip that is still catching up finds a word unwritten and re-polls.
+//     A strip can therefore start 32 steps after the one above it (the skew of the 32 lanes) plus one
+//     L2 round trip, and nothing else orders the strips;
+//   * residues: a 64-column shared ring refilled every 8 steps from registers loaded one refill early;
+//   * columns past the end of the subject carry a pad letter scoring -128: their H is a decayed E of
+//     a real cell, which can never beat that cell (strict >), so the step has no column mask;
+//   * end cell: key = (H << BITS) + (K*C-1 - (c*K + k)) -- the maximum prefers the smaller column, then
+//     the smaller row -- and a branch-free update of (best key, best block).
+// `bnd` must be zero-filled before the launch; `progress` is not used by this generation.
+inline size_t wave32v3_smem_bytes(int size, int warps) {
+    return (((size_t)size * size * sizeof(int) + 15) & ~(size_t)15) + (size_t)warps * (64 + (size_t)(size + 1) * 512);
+}
+// scores must leave room for the tile index below them in the 32-bit key (and stay below 2^30)
+inline bool wave32v3_score_fits(int K, int C, long long min_len, int max_score) {
+    int bits = 0;
+    while ((1 << bits) < K * C) ++bits;
+    return min_len * (long long)(max_score > 1 ? max_score : 1) < (1ll << (30 - bits));
+}
+PSB_DEV bool wave32v3_valid(long long w) { const unsigned t = (unsigned)w; return (((t >> 30) ^ (t >> 31)) & 1u) != 0; }
+PSB_DEV long long wave32v3_pack(int T, int F) { return (long long)(((unsigned long long)(unsigned)F << 32) | (unsigned)(T ^ 0x40000000)); }
+
+template <int K, int C>
+PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
+    static_assert(C == 4, "four residues travel in one word");
+    static_assert(K <= 16, "one 16-byte profile slot per lane and letter");
+    constexpr int KC = K * C;
+    constexpr int BITS = KC <= 16 ? 4 : (KC <= 32 ? 5 : 6);
+    PSB_SHARED_DECL(smem_raw);
+    const int lane = lane_id();
+    const int size = p.size, o = p.open, e = p.gap;
+    int *smat = (int *)smem_raw;
+    const size_t mat_bytes = (((size_t)size * size * sizeof(int)) + 15) & ~(size_t)15;
+    const size_t per_warp = 64 + (size_t)(size + 1) * 512;
+    unsigned char *wsm = smem_raw + mat_bytes + (size_t)warp_in_block() * per_warp;
+    uint8_t *ringL = (uint8_t *)wsm;                     // 64 residues
+    unsigned char *wprof = wsm + 64;
+    for (int x = thread_in_block(); x < size * size; x += threads_per_block()) smat[x] = p.matrix[x] + o;
+    sync_block();
+
+    const int Lq = p.Lq;
+    const int rows_per_strip = 32 * K;
+    const int nstrips = (Lq + rows_per_strip - 1) / rows_per_strip;
+    const int nitems = nstrips * (p.multi_n > 0 ? p.multi_n : 1);
+    const long long top_edge = wave32v3_pack(-o, NEG_INF32);   // H = 0, no F
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomic_add(p.next_strip, 1);
+        item = shfl(item, 0);
+        if (item >= nitems) break;
+        const int subj = item / nstrips, strip = item - subj * nstrips;
+        const long long rbase = p.multi_n > 0 ? p.r_off[subj] : 0;
+        const int Lr = p.multi_n > 0 ? (int)(p.r_off[subj + 1] - rbase) : p.Lr;
+        const uint8_t *rseq = p.r + rbase;
+        const int nblk = (Lr + C - 1) / C;
+        const int nsteps = nblk + 31;
+        long long *bnd0 = (long long *)p.bnd + (long long)nstrips * rbase;       // one 64-bit word per column
+        const bool last_strip = strip == nstrips - 1;
+        const int i0 = strip * rows_per_strip + lane * K;
+        const long long *bnd_in = bnd0 + (long long)(strip - 1) * Lr;
+        long long *bnd_out = bnd0 + (long long)strip * Lr;
+
+        // per-warp int8 profile of this strip: [letter][lane][16 rows] of (S + open); pad rows and the
+        // pad letter (index `size`) are -128
+        sync_warp();
+        for (int a = 0; a <= size; ++a) {
+            unsigned wv[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+            if (a < size) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (i0 + k < Lq) {
+                        const unsigned b = (unsigned)smat[(int)p.q[i0 + k] * size + a] & 0xffu;
+                        wv[k >> 2] = (wv[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (b << (8 * (k & 3)));
+                    }
+                }
+            }
+            uint4 v; v.x = wv[0]; v.y = wv[1]; v.z = wv[2]; v.w = wv[3];
+            *(uint4 *)(wprof + ((size_t)a * 32 + lane) * 16) = v;
+        }
+        int T[K], E[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { T[k] = -o; E[k] = NEG_INF32; }   // H = 0 left of the first column
+        int Tdiag_in = -o;
+        int Tout[C], Fout[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { Tout[c] = -o; Fout[c] = NEG_INF32; }
+        unsigned Lw_out = 0;
+        int bestH = 0, bestKey = 0, bestB = 0;    // a local score must exceed 0 to count
+
+        const int t_claim = wave_time_us();   // debugging aid (PSB_DEBUG_TIMING): when the strip was claimed
+        // residues of the refill of group g (columns [32g, 32g+32)), loaded one group early
+        unsigned pre_l = lane < Lr ? (unsigned)rseq[lane] : (unsigned)size;
+        // lane 0: the words of the strip above for the blocks of the next two steps
+        long long WA[C], WB[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { WA[c] = top_edge; WB[c] = top_edge; }
+        if (lane == 0 && strip > 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (c < Lr) WA[c] = ld_relaxed64(bnd_in + c);
+                if (C + c < Lr) WB[c] = ld_relaxed64(bnd_in + C + c);
+            }
+        }
+        // one step of the sweep; W holds lane 0's words for block s and is reloaded with block s+2
+        auto step = [&](const int s, long long (&W)[C]) {
+            const int b = s - lane;
+            int Tup[C], Fup[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { Tup[c] = shfl_up(Tout[c], 1); Fup[c] = shfl_up(Fout[c], 1); }
+            unsigned Lw = shfl_up(Lw_out, 1);
+            if (lane == 0) {
+                if (strip > 0 && s < nblk) {
+                    // words the strip above has not written yet: re-poll (only while this strip catches up)
+                    for (;;) {
+                        unsigned ok = 0x80000000u;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) { const unsigned t = (unsigned)W[c]; ok &= t ^ (t << 1); }
+                        if (ok & 0x80000000u) break;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) if (C * s + c < Lr) W[c] = ld_relaxed64(bnd_in + C * s + c);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) { Tup[c] = (int)((unsigned)W[c] ^ 0x40000000u); Fup[c] = (int)((unsigned long long)W[c] >> 32); }
+                Lw = *(const unsigned *)(ringL + ((C * s) & 63));
+                if (strip > 0) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int cn = C * (s + 2) + c;
+                        W[c] = cn < Lr ? ld_relaxed64(bnd_in + cn) : top_edge;
+                    }
+                }
+            }
+            Lw_out = Lw;
+            if (b >= 0 && b < nblk) {
+                int cmax = -0x7fffffff - 1;
+                int Tdg = Tdiag_in;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const unsigned letter = (Lw >> (8 * c)) & 0xffu;
+                    const uint4 pv = *(const uint4 *)(wprof + ((size_t)letter * 32 + lane) * 16);
+                    const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w};
+                    int Td = Tdg;
+                    int Fk = viaddmax(Fup[c], -e, Tup[c]);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const unsigned SEL = (unsigned)(k & 3) * 0x1111u + 0x8880u;
+                        const int So = (int)prmt(pw[k >> 2], 0u, SEL);
+                        const int Tl = T[k];
+                        const int En = viaddmax(E[k], -e, Tl);
+                        const int h0 = viaddmax_relu(Td, So, En);
+                        const int H = h0 > Fk ? h0 : Fk;
+                        const int Fnext = viaddmax(Fk, -e, h0 - o);   // the only dependent op per row
+                        Td = Tl;
+                        T[k] = H - o; E[k] = En;
+                        const int key = (H << BITS) + (KC - 1 - (c * K + k));
+                        cmax = cmax > key ? cmax : key;
+                        if (k == K - 1) { Tout[c] = H - o; Fout[c] = Fk; }
+                        Fk = Fnext;
+                    }
+                    Tdg = Tup[c];
+                }
+                Tdiag_in = Tup[C - 1];
+                if (lane == 31 && !last_strip) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        if (C * b + c < Lr) st_relaxed64(bnd_out + C * b + c, wave32v3_pack(Tout[c], Fout[c]));
+                }
+                const bool upd = (cmax >> BITS) > bestH;
+                bestH = upd ? (cmax >> BITS) : bestH;
+                bestKey = upd ? cmax : bestKey;
+                bestB = upd ? b : bestB;
+            }
+        };
+        for (int s0 = 0; s0 < nsteps; s0 += 8) {
+            // ---- every 8 steps: 32 residues into the ring, the next 32 into registers ----------------
+            sync_warp();
+            {
+                const int c = C * s0 + lane;
+                ringL[c & 63] = (uint8_t)pre_l;
+                pre_l = c + 32 < Lr ? (unsigned)rseq[c + 32] : (unsigned)size;
+                sync_warp();
+            }
+            PSB_UNROLL(1)
+            for (int s = s0; s < s0 + 8; s += 2) {
+                step(s, WA);
+                step(s + 1, WB);
+            }
+        }
+        sync_warp();
+        int bestJ = 0x7fffffff, bestI = 0x7fffffff;
+        if (bestH > 0) {
+            const int idx = KC - 1 - (bestKey & ((1 << BITS) - 1));
+            bestJ = C * bestB + idx / K;
+            bestI = i0 + idx % K;
+        } else {
+            bestH = NEG_INF32;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const int oH = shfl_xor(bestH, m), oJ = shfl_xor(bestJ, m), oI = shfl_xor(bestI, m);
+            if (oH > bestH || (oH == bestH && (oJ < bestJ || (oJ == bestJ && oI < bestI)))) { bestH = oH; bestJ = oJ; bestI = oI; }
+        }
+        if (lane == 0) {
+            int *c = p.cand + (long long)item * 8;
+            c[0] = bestH; c[1] = bestJ; c[2] = bestI; c[3] = NEG_INF32; c[4] = 0x7fffffff;
+            c[5] = t_claim; c[6] = 0; c[7] = wave_time_us();
         }
     }
 }

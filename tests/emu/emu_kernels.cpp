@@ -64,9 +64,22 @@ extern "C" int emu_sizeof_sw16() { return (int)sizeof(Sw16Params); }
 #include "../../parasail_rs_b200/csrc/kern_wave32.cuh"
 
 static bool g_wave_v2 = false;
-extern "C" void emu_wave32_use_v2(int on) { g_wave_v2 = on != 0; }
+static int g_wave_gen = 1;   // 1, 2, or 3 (column-blocked, local alignment only)
+extern "C" void emu_wave32_use_v2(int on) { g_wave_v2 = on == 1; g_wave_gen = on == 2 ? 3 : (on == 1 ? 2 : 1); }
 extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams *rp, int nblocks) {
     Wave32Params p = *pp;
+    if (g_wave_gen == 3) {
+        size_t smem3 = wave32v3_smem_bytes(p.size, 1);
+        switch (K) {
+            case 4: emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<4, 4>(p); }); break;
+            case 8: emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<8, 4>(p); }); break;
+            case 16: emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<16, 4>(p); }); break;
+            default: return -1;
+        }
+        WaveReduceParams r3 = *rp;
+        emu::launch((r3.multi_n + 31) / 32 + (r3.multi_n == 0), 64, [&]() { wave32_reduce_kernel(r3); });
+        return 0;
+    }
     size_t smem = g_wave_v2 ? wave32v2_smem_bytes(p.size, 1) : wave32_smem_bytes(p.size, 1);
 #define WCASE(KK) case KK: if (g_wave_v2) emu::launch(nblocks, smem, [&]() { wave32v2_kernel<KK>(p); }); else emu::launch(nblocks, smem, [&]() { wave32_kernel<KK>(p); }); break;
     switch (K) { WCASE(1) WCASE(2) WCASE(4) WCASE(8) default: return -1; }

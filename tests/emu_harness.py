@@ -173,7 +173,8 @@ class WaveReduceParams(C.Structure):
 
 
 def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1, v2=False):
-    """Run the emulated long-pair wavefront kernel on one pair; returns (score, end_query, end_ref)."""
+    """Run the emulated long-pair wavefront kernel on one pair; returns (score, end_query, end_ref).
+    v2: False/True select generation 1/2; the integer 2 selects generation 3 (column-blocked, local only)."""
     lib().emu_wave32_use_v2(int(v2))
     assert lib().emu_sizeof_wave32() == C.sizeof(Wave32Params) and lib().emu_sizeof_wavereduce() == C.sizeof(WaveReduceParams)
     mapper = mat.mapper.astype(np.uint8)
