@@ -124,17 +124,40 @@ def run_reference(args, rank):
     value = cells / dt / 1e9
     threads = int(res["threads"])
     sample = f"{n_sample} subjects of the C2 database per step ({cells / args.steps:.3g} cells), striped AVX2 8->16->32 bit"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "s8/s16 (sat escalation)", "data": "synthetic",
         "config": {"workload": workload_name(args.db), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_JSON_FD = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print banners there too (NCCL's version line when
+    NCCL_DEBUG is set on the box), so everything but the result line is sent to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line)
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -310,7 +333,7 @@ def main():
     }
     if cpu:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -309,6 +309,36 @@ def test_long_pair_wavefront(ps, oracle, mode):
     assert_same(gb, oracle_batch(oracle, qs, rs, m, mode, 5, 2), KEYS3, f"wave batch mode {mode}")
 
 
+def test_long_local_pair_column_blocked(ps, oracle, blosum62, monkeypatch):
+    # local long pairs take the column-blocked generation of the wavefront kernel (4 columns per step,
+    # strips hand over through self-validating 64-bit words): reference lengths around the block size,
+    # protein scores, repeats (many equal maxima), open == extend, and a pair without any match
+    b62 = ps.Matrix.from_name("blosum62")
+    q = psb_data.random_seq(5201, 0, 2600)
+    rep = np.concatenate([q[100:400]] * 9)
+    cases = [(q, rep), (q, rep[:2049]), (q, rep[:2050]), (q, rep[:2051]), (q, psb_data.mutate(q, 5202, 0, 0.2, 0.03)[:1999]),
+             (q, q[:5]), (q, psb_data.random_seq(5203, 1, 700))]
+    for o, e in ((10, 1), (4, 4)):
+        a = ps.Aligner.new().local().matrix(b62).gap_open(o).gap_extend(e).build()
+        gb = a.align_batch([c[0] for c in cases], [c[1] for c in cases])
+        assert_same(gb, oracle_batch(oracle, [c[0] for c in cases], [c[1] for c in cases], blosum62, 2, o, e), KEYS3,
+                    f"column-blocked wavefront open {o} ext {e}")
+    dna = ps.Matrix.create(b"ACGT", 2, -3)
+    a = ps.Aligner.new().local().matrix(dna).gap_open(5).gap_extend(2).solution_width(32).build()
+    zero = a.align(np.frombuffer(b"A" * 4000, dtype=np.uint8), np.frombuffer(b"C" * 3001, dtype=np.uint8))
+    assert (zero.get_score(), zero.get_end_query(), zero.get_end_ref()) == (0, 0, 0)
+    # the two generations agree on a bigger pair (24 strips)
+    r = psb_data.random_seq(5204, 0, 30001, protein=False)
+    qq = psb_data.mutate(r, 5204, 1, 0.08, 0.01, protein=False)[:6100]
+    g3 = a.align(qq, r)
+    monkeypatch.setenv("PSB_WAVE_GEN", "2")
+    g2 = a.align(qq, r)
+    monkeypatch.delenv("PSB_WAVE_GEN")
+    assert (g3.get_score(), g3.get_end_query(), g3.get_end_ref()) == (g2.get_score(), g2.get_end_query(), g2.get_end_ref())
+    exp = oracle.align(qq, r, oracle.Matrix.create(b"ACGT", 2, -3), mode=2, open=5, gap=2)
+    assert (g3.get_score(), g3.get_end_query(), g3.get_end_ref()) == (exp["score"], exp["end_query"], exp["end_ref"])
+
+
 def test_concurrent_host_threads(ps, oracle, blosum62):
     # Aligner / Profile / Matrix handles are Send + Sync in the reference [REF src/aligner/mod.rs:532-535]:
     # four host threads (each gets its own stream) share one profile, one database and one aligner
