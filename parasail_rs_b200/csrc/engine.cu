@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1301,7 +1302,7 @@ struct ScanJob {
     DevMem d_out[6];
     int64_t retried = 0;
     int *retried_host = nullptr;   // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;   // kernels begin / end, results on the host
     ScanJob() = default;
     ScanJob(const ScanJob &) = delete;
     ScanJob &operator=(const ScanJob &) = delete;
@@ -1309,6 +1310,7 @@ struct ScanJob {
         if (retried_host) pinned_free(retried_host, 64);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (done) cudaEventDestroy(done);
     }
 };
 static int scan_enqueue(ScanJob &job, const FnConfig &cfg, const parasail_profile *profile, int open, int gap, psb_db *db,
@@ -1333,12 +1335,14 @@ static int scan_enqueue(ScanJob &job, const FnConfig &cfg, const parasail_profil
     PSB_CUDA(cudaEventRecord(job.ev1, c.stream));
     for (int k = 0; k < nout; ++k)
         PSB_CUDA(cudaMemcpyAsync(hosts[k] + host_base, job.d_out[k].p, (size_t)db->n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    PSB_CUDA(cudaEventCreateWithFlags(&job.done, cudaEventDisableTiming));
+    PSB_CUDA(cudaEventRecord(job.done, c.stream));
     return PSB_OK;
 }
-// call after the stream has been synchronised
+// waits until the job's results are on the host
 static int scan_finish(ScanJob &job) {
     Ctx &c = g_ctx;
-    cudaError_t e = cudaStreamSynchronize(c.stream);
+    cudaError_t e = job.done ? cudaEventSynchronize(job.done) : cudaStreamSynchronize(c.stream);
     if (e != cudaSuccess) { set_error(std::string("psb_scan: ") + cudaGetErrorString(e)); return PSB_ECUDA; }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, job.ev0, job.ev1) == cudaSuccess) c.last_ms += ms;
@@ -1418,35 +1422,48 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
     b->cells = (double)profile->query.size() * (double)total;
     int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
     int rc = PSB_OK;
-    std::vector<DbBuild> builds(npieces);
+    std::vector<std::unique_ptr<DbBuild>> builds(npieces);
+    std::vector<std::unique_ptr<ScanJob>> jobs(npieces);
+    for (int k = 0; k < npieces; ++k) { builds[k].reset(new DbBuild()); jobs[k].reset(new ScanJob()); }
     auto begin = [&](int k) -> int {
         if (cut[k + 1] <= cut[k]) return PSB_OK;
-        return db_begin(builds[k], cat, off + cut[k], cut[k + 1] - cut[k], hm, true) ? PSB_OK : PSB_ECUDA;
+        return db_begin(*builds[k], cat, off + cut[k], cut[k + 1] - cut[k], hm, true) ? PSB_OK : PSB_ECUDA;
     };
-    std::vector<ScanJob> jobs(npieces);
+    // a finished piece gives its device memory back (staging blocks, packed shard, result arrays), so
+    // at most kDepth pieces are resident however large the host database is
+    const int kDepth = 4;
+    auto retire = [&](int k) -> int {
+        if (k < 0 || !jobs[k]) return PSB_OK;
+        int r = PSB_OK;
+        if (jobs[k]->ev0) { r = scan_finish(*jobs[k]); b->n_retried += jobs[k]->retried; }
+        if (builds[k] && builds[k]->db) { psb_db_free(builds[k]->db); builds[k]->db = nullptr; }
+        jobs[k].reset(); builds[k].reset();
+        return r;
+    };
     const bool dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
     const auto t_in = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count(); };
     rc = begin(0);
     if (dbg) std::fprintf(stderr, "[psb] scan_host: %d pieces, first upload queued at %.3f ms\n", npieces, since());
     for (int k = 0; k < npieces && rc == PSB_OK; ++k) {
-        if (!builds[k].db) continue;
-        rc = db_finish(builds[k]);
-        if (rc == PSB_OK) rc = scan_enqueue(jobs[k], cfg, profile, open, gap, builds[k].db, hosts, cut[k]);
+        if (!builds[k]->db) continue;
+        rc = db_finish(*builds[k]);
+        if (rc == PSB_OK) rc = scan_enqueue(*jobs[k], cfg, profile, open, gap, builds[k]->db, hosts, cut[k]);
         if (dbg) std::fprintf(stderr, "[psb] scan_host: piece %d queued at %.3f ms\n", k, since());
         // while this piece is being scanned: host pass over the next piece's offsets and its upload
-        if (rc == PSB_OK && k + 1 < npieces) rc = begin(k + 1);
+        if (rc == PSB_OK && k + 1 < npieces) {
+            if (k + 1 >= kDepth) rc = retire(k + 1 - kDepth);
+            if (rc == PSB_OK) rc = begin(k + 1);
+        }
     }
     cudaStreamSynchronize(c.copy);
     if (dbg) std::fprintf(stderr, "[psb] scan_host: uploads done at %.3f ms\n", since());
     cudaStreamSynchronize(c.stream);
     if (dbg) std::fprintf(stderr, "[psb] scan_host: all done at %.3f ms\n", since());
-    for (int k = 0; k < npieces && rc == PSB_OK; ++k) {
-        if (!jobs[k].ev0) continue;
-        rc = scan_finish(jobs[k]);
-        b->n_retried += jobs[k].retried;
+    for (int k = 0; k < npieces; ++k) {
+        const int r = retire(k);
+        if (rc == PSB_OK) rc = r;
     }
-    for (auto &B : builds) if (B.db) psb_db_free(B.db);
     if (rc != PSB_OK) { free_batch(b); return rc; }
     *out = b;
     return PSB_OK;
