@@ -281,11 +281,11 @@ static const void *wave32_fn(int K, bool v2) {
     }
     return nullptr;
 }
-static const void *wave32v3_fn(int K) {
+static const void *wave32v3_fn(int K, bool is_sw) {
     switch (K) {
-        case 4: return (const void *)wave32v3_kernel<4, 4>;
-        case 8: return (const void *)wave32v3_kernel<8, 4>;
-        case 16: return (const void *)wave32v3_kernel<16, 4>;
+        case 4: return is_sw ? (const void *)wave32v3_kernel<4, 4, true> : (const void *)wave32v3_kernel<4, 4, false>;
+        case 8: return is_sw ? (const void *)wave32v3_kernel<8, 4, true> : (const void *)wave32v3_kernel<8, 4, false>;
+        case 16: return is_sw ? (const void *)wave32v3_kernel<16, 4, true> : (const void *)wave32v3_kernel<16, 4, false>;
     }
     return nullptr;
 }
@@ -300,9 +300,11 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
     int K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4);
     int wpb = kWarpsPerBlock;
     const bool v2 = wave32_v2_ok(m, g.open, g.gap);
-    // local alignments take the column-blocked generation (K x 4 tiles per lane and step): the shortest
-    // critical path, Lq/K + Lr/4 steps, with the smallest K whose strips are all resident at once
-    bool v3 = v2 && g.mode == MODE_SW;
+    // the column-blocked generation (K x 4 tiles per lane and step) has the shortest critical path,
+    // Lq/K + Lr/4 steps: every mode takes it when its preconditions hold (C5 local 46.5 -> 21.1 ms;
+    // 50 kb x 50 kb global 26.6 -> 19.3 ms)
+    const bool is_sw = g.mode == MODE_SW;
+    bool v3 = v2;
     // experiment knobs (tools/c5_probe.py): generation, rows per lane and warps per CTA of the launch
     if (const char *ev = std::getenv("PSB_WAVE_GEN")) { if (std::atoi(ev) == 2) v3 = false; }
     if (v3) {
@@ -311,7 +313,7 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
         // every strip adds ~34 steps to the path: 8 rows, 4 warps per CTA (one per scheduler)
         K = 8; wpb = 4;
         if ((lq + 32 * K - 1) / (32 * K) > c.sms * 16) K = 16;
-        if ((lq + 32 * K - 1) / (32 * K) > c.sms * 16 || !wave32v3_score_fits(K, 4, std::min(lq, lr), m.max)) v3 = false;
+        if ((lq + 32 * K - 1) / (32 * K) > c.sms * 16 || !wave32v3_range_ok(K, 4, is_sw, lq, lr, m.max, m.min, g.open, g.gap)) v3 = false;
         if (!v3) { K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4); wpb = kWarpsPerBlock; }
     }
     if (const char *ev = std::getenv("PSB_WAVE_K")) {
@@ -319,7 +321,7 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
         if ((k == 1 || k == 2 || k == 4 || k == 8 || k == 16) && (!v3 || k >= 4)) K = k;
     }
     if (const char *ev = std::getenv("PSB_WAVE_WARPS")) { const int w = std::atoi(ev); if (w >= 1 && w <= 32) wpb = w; }
-    const void *fn = v3 ? wave32v3_fn(K) : wave32_fn(K, v2);
+    const void *fn = v3 ? wave32v3_fn(K, is_sw) : wave32_fn(K, v2);
     const int nstrips = (lq + 32 * K - 1) / (32 * K);
     DevMem d_bnd, d_ctl, d_cand;
     PSB_TRY(d_bnd.alloc((size_t)nstrips * 2 * (size_t)lr * sizeof(int), c.stream));

@@ -396,7 +396,7 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Generation 3 (local alignment, open >= extend, byte-sized S + open): column-blocked strips.
+// Generation 3 (open >= extend, byte-sized S + open): column-blocked strips.
 //
 // What bounds one long pair is the critical path, not throughput: the wavefront has to cross
 // Lq/K lanes and Lr/C column blocks, one step each, and a warp that runs alone on its scheduler
@@ -417,24 +417,33 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
 //     A strip can therefore start 32 steps after the one above it (the skew of the 32 lanes) plus one
 //     L2 round trip, and nothing else orders the strips;
 //   * residues: a 64-column shared ring refilled every 8 steps from registers loaded one refill early;
-//   * columns past the end of the subject carry a pad letter scoring -128: their H is a decayed E of
-//     a real cell, which can never beat that cell (strict >), so the step has no column mask;
-//   * end cell: key = (H << BITS) + (K*C-1 - (c*K + k)) -- the maximum prefers the smaller column, then
-//     the smaller row -- and a branch-free update of (best key, best block).
+//   * columns past the end of the subject carry a pad letter scoring -128.  Local: their H is a decayed
+//     E of a real cell, which can never beat that cell (strict >), so the step has no column mask, and the
+//     end cell is key = (H << BITS) + (K*C-1 - (c*K + k)) -- the maximum prefers the smaller column, then
+//     the smaller row -- with a branch-free update of (best key, best block).  Global / semi-global
+//     (IS_SW = false): nothing reads a pad column's cells, the last row and last column are looked at
+//     per column as in generation 2.
 // `bnd` must be zero-filled before the launch; `progress` is not used by this generation.
 inline size_t wave32v3_smem_bytes(int size, int warps) {
     return (((size_t)size * size * sizeof(int) + 15) & ~(size_t)15) + (size_t)warps * (64 + (size_t)(size + 1) * 512);
 }
-// scores must leave room for the tile index below them in the 32-bit key (and stay below 2^30)
-inline bool wave32v3_score_fits(int K, int C, long long min_len, int max_score) {
+// local: scores must leave room for the tile index below them in the 32-bit key; every mode: |H - open|
+// stays below 2^30 (the hand-over words keep their validity mark in the top two bits of T)
+inline bool wave32v3_range_ok(int K, int C, bool is_sw, long long lq, long long lr, int max_score, int min_score, int open, int gap) {
     int bits = 0;
     while ((1 << bits) < K * C) ++bits;
-    return min_len * (long long)(max_score > 1 ? max_score : 1) < (1ll << (30 - bits));
+    const long long up = (lq < lr ? lq : lr) * (long long)(max_score > 1 ? max_score : 1);
+    if (is_sw) return up < (1ll << (30 - bits));
+    long long step = -(long long)min_score;
+    if (gap > step) step = gap;
+    if (step < 1) step = 1;
+    const long long down = (lq + lr) * step + 2ll * open + 64;
+    return up < (1ll << 29) && down < (1ll << 29);
 }
 PSB_DEV bool wave32v3_valid(long long w) { const unsigned t = (unsigned)w; return (((t >> 30) ^ (t >> 31)) & 1u) != 0; }
 PSB_DEV long long wave32v3_pack(int T, int F) { return (long long)(((unsigned long long)(unsigned)F << 32) | (unsigned)(T ^ 0x40000000)); }
 
-template <int K, int C>
+template <int K, int C, bool IS_SW>
 PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     static_assert(C == 4, "four residues travel in one word");
     static_assert(K <= 16, "one 16-byte profile slot per lane and letter");
@@ -452,11 +461,16 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     for (int x = thread_in_block(); x < size * size; x += threads_per_block()) smat[x] = p.matrix[x] + o;
     sync_block();
 
+    const int mode = p.mode;
+    const bool top_free = IS_SW || (mode == MODE_SG && p.s1_beg);
+    const bool left_free = IS_SW || (mode == MODE_SG && p.s2_beg);
+    const bool row_ends = !IS_SW && mode == MODE_SG && p.s1_end;
+    const bool col_ends = !IS_SW && mode == MODE_SG && p.s2_end;
     const int Lq = p.Lq;
     const int rows_per_strip = 32 * K;
     const int nstrips = (Lq + rows_per_strip - 1) / rows_per_strip;
     const int nitems = nstrips * (p.multi_n > 0 ? p.multi_n : 1);
-    const long long top_edge = wave32v3_pack(-o, NEG_INF32);   // H = 0, no F
+    const long long top_edge = wave32v3_pack(-o, NEG_INF32);   // H = 0, no F (local / free top edge)
 
     for (;;) {
         int item = 0;
@@ -494,14 +508,18 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
         }
         int T[K], E[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) { T[k] = -o; E[k] = NEG_INF32; }   // H = 0 left of the first column
-        int Tdiag_in = -o;
+        for (int k = 0; k < K; ++k) {
+            T[k] = (left_free ? 0 : -o - (i0 + k) * e) - o;   // column -1
+            E[k] = NEG_INF32;
+        }
+        int Tdiag_in = (i0 == 0) ? -o : ((left_free ? 0 : -o - (i0 - 1) * e) - o);
         int Tout[C], Fout[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) { Tout[c] = -o; Fout[c] = NEG_INF32; }
         unsigned Lw_out = 0;
-        int bestH = 0, bestKey = 0, bestB = 0;    // a local score must exceed 0 to count
-
+        int bestH = IS_SW ? 0 : NEG_INF32, bestKey = 0, bestB = 0;    // local: a score must exceed 0 to count
+        int bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
+        const int klast = (Lq - 1) - i0;
         const int t_claim = wave_time_us();   // debugging aid (PSB_DEBUG_TIMING): when the strip was claimed
         // residues of the refill of group g (columns [32g, 32g+32)), loaded one group early
         unsigned pre_l = lane < Lr ? (unsigned)rseq[lane] : (unsigned)size;
@@ -537,6 +555,11 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                 }
 #pragma unroll
                 for (int c = 0; c < C; ++c) { Tup[c] = (int)((unsigned)W[c] ^ 0x40000000u); Fup[c] = (int)((unsigned long long)W[c] >> 32); }
+                if (!IS_SW && strip == 0 && !top_free) {
+                    // top edge of a global alignment: H(-1, j) = -o - j*e
+#pragma unroll
+                    for (int c = 0; c < C; ++c) Tup[c] = -o - (C * s + c) * e - o;
+                }
                 Lw = *(const unsigned *)(ringL + ((C * s) & 63));
                 if (strip > 0) {
 #pragma unroll
@@ -557,23 +580,46 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w};
                     int Td = Tdg;
                     int Fk = viaddmax(Fup[c], -e, Tup[c]);
+                    int Tlast = 0, Flast = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const unsigned SEL = (unsigned)(k & 3) * 0x1111u + 0x8880u;
                         const int So = (int)prmt(pw[k >> 2], 0u, SEL);
                         const int Tl = T[k];
                         const int En = viaddmax(E[k], -e, Tl);
-                        const int h0 = viaddmax_relu(Td, So, En);
+                        const int h0 = IS_SW ? viaddmax_relu(Td, So, En) : viaddmax(Td, So, En);
                         const int H = h0 > Fk ? h0 : Fk;
                         const int Fnext = viaddmax(Fk, -e, h0 - o);   // the only dependent op per row
                         Td = Tl;
+                        if (IS_SW) {
+                            const int key = (H << BITS) + (KC - 1 - (c * K + k));
+                            cmax = cmax > key ? cmax : key;
+                        }
+                        if (k == K - 1) { Tlast = H - o; Flast = Fk; }
                         T[k] = H - o; E[k] = En;
-                        const int key = (H << BITS) + (KC - 1 - (c * K + k));
-                        cmax = cmax > key ? cmax : key;
-                        if (k == K - 1) { Tout[c] = H - o; Fout[c] = Fk; }
                         Fk = Fnext;
                     }
+                    Tout[c] = Tlast; Fout[c] = Flast;
                     Tdg = Tup[c];
+                    if (!IS_SW) {
+                        const int j = C * b + c;
+                        if (j < Lr) {
+                            if (last_strip && klast >= 0 && klast < K && (row_ends || (j == Lr - 1 && !col_ends))) {
+                                // last row: sg scans it left to right (strict >); nw reads the corner only
+                                int hv = 0;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) if (k == klast) hv = T[k] + o;
+                                if (hv > bestH) { bestH = hv; bestJ = j; bestI = Lq - 1; }
+                            }
+                            if (col_ends && j == Lr - 1) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k) {
+                                    const int hv = T[k] + o;
+                                    if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
+                                }
+                            }
+                        }
+                    }
                 }
                 Tdiag_in = Tup[C - 1];
                 if (lane == 31 && !last_strip) {
@@ -581,10 +627,12 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     for (int c = 0; c < C; ++c)
                         if (C * b + c < Lr) st_relaxed64(bnd_out + C * b + c, wave32v3_pack(Tout[c], Fout[c]));
                 }
-                const bool upd = (cmax >> BITS) > bestH;
-                bestH = upd ? (cmax >> BITS) : bestH;
-                bestKey = upd ? cmax : bestKey;
-                bestB = upd ? b : bestB;
+                if (IS_SW) {
+                    const bool upd = (cmax >> BITS) > bestH;
+                    bestH = upd ? (cmax >> BITS) : bestH;
+                    bestKey = upd ? cmax : bestKey;
+                    bestB = upd ? b : bestB;
+                }
             }
         };
         for (int s0 = 0; s0 < nsteps; s0 += 8) {
@@ -603,22 +651,25 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
         }
         sync_warp();
-        int bestJ = 0x7fffffff, bestI = 0x7fffffff;
-        if (bestH > 0) {
-            const int idx = KC - 1 - (bestKey & ((1 << BITS) - 1));
-            bestJ = C * bestB + idx / K;
-            bestI = i0 + idx % K;
-        } else {
-            bestH = NEG_INF32;
+        if (IS_SW) {
+            if (bestH > 0) {
+                const int idx = KC - 1 - (bestKey & ((1 << BITS) - 1));
+                bestJ = C * bestB + idx / K;
+                bestI = i0 + idx % K;
+            } else {
+                bestH = NEG_INF32;
+            }
         }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
             const int oH = shfl_xor(bestH, m), oJ = shfl_xor(bestJ, m), oI = shfl_xor(bestI, m);
             if (oH > bestH || (oH == bestH && (oJ < bestJ || (oJ == bestJ && oI < bestI)))) { bestH = oH; bestJ = oJ; bestI = oI; }
+            const int cH = shfl_xor(colH, m), cI = shfl_xor(colI, m);
+            if (cH > colH || (cH == colH && cI < colI)) { colH = cH; colI = cI; }
         }
         if (lane == 0) {
             int *c = p.cand + (long long)item * 8;
-            c[0] = bestH; c[1] = bestJ; c[2] = bestI; c[3] = NEG_INF32; c[4] = 0x7fffffff;
+            c[0] = bestH; c[1] = bestJ; c[2] = bestI; c[3] = colH; c[4] = colI;
             c[5] = t_claim; c[6] = 0; c[7] = wave_time_us();
         }
     }

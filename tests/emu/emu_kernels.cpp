@@ -71,9 +71,8 @@ extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams 
     if (g_wave_gen == 3) {
         size_t smem3 = wave32v3_smem_bytes(p.size, 1);
         switch (K) {
-            case 4: emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<4, 4>(p); }); break;
-            case 8: emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<8, 4>(p); }); break;
-            case 16: emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<16, 4>(p); }); break;
+#define W3CASE(KK) case KK: if (p.mode == MODE_SW) emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<KK, 4, true>(p); }); else emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<KK, 4, false>(p); }); break;
+            W3CASE(4) W3CASE(8) W3CASE(16)
             default: return -1;
         }
         WaveReduceParams r3 = *rp;

@@ -87,3 +87,27 @@ def test_wave_gen3_multi_pair(oracle, blosum62):
     for i, s in enumerate(subs):
         exp = oracle.align(q, s, blosum62, mode=2, open=10, gap=1)
         assert (got[0][i], got[1][i], got[2][i]) == (exp["score"], exp["end_query"], exp["end_ref"]), i
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("K", [4, 8])
+def test_wave_gen3_global_modes(oracle, mode, K):
+    # the column-blocked generation for nw / sg: several strips, reference lengths around the block size
+    mat = oracle.Matrix.create(b"ACGT", 2, -3)
+    for lr in (1, 4, 5, 33, 130, 259):
+        r = psb_data.random_seq(5301, lr, lr, protein=False)
+        base = np.concatenate([r] * (300 // lr + 2))[:340]
+        q = psb_data.mutate(base, 5302, lr, 0.10, 0.02, protein=False)[:300]
+        for o, e in ((5, 2), (3, 3), (0, 0)):
+            exp = oracle.align(q, r, mat, mode=mode, open=o, gap=e)
+            got = emu_harness.wave32(q, r, mat, K, mode, o, e, v2=2)
+            assert got == (exp["score"], exp["end_query"], exp["end_ref"]), (mode, K, lr, o, e)
+
+
+@pytest.mark.parametrize("flags", SG_FLAGS[1:])
+def test_wave_gen3_sg_flags(oracle, blosum62, flags):
+    q = psb_data.random_seq(5303, 0, 290)
+    r = psb_data.mutate(q, 5304, 0, 0.2, 0.04)[40:231]
+    exp = oracle.align(q, r, blosum62, mode=1, open=10, gap=1, s1_beg=flags[0], s1_end=flags[1], s2_beg=flags[2], s2_end=flags[3])
+    got = emu_harness.wave32(q, r, blosum62, 4, 1, 10, 1, flags, v2=2)
+    assert got == (exp["score"], exp["end_query"], exp["end_ref"])
