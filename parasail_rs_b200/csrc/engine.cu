@@ -984,12 +984,24 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         p.mul_one = 1u; p.mul_64k = 65536u;
         const void *fn = sw16_fn(sp.K);
         if (!fn) { set_error("sw16: no kernel for this query length"); return PSB_EUNSUPPORTED; }
-        const size_t smem = sw16_smem_bytes(sp.nletters, sp.K, kSw16WarpsPerBlock);
+        // CTA size: two CTAs of 8 warps when their profile copies fit an SM together, else one of 16
+        // (long queries with a protein alphabet: one 50 KB profile copy instead of two)
+        int wpb = kSw16WarpsPerBlock, per_sm = 0;
+        size_t smem = sw16_smem_bytes(sp.nletters, sp.K, wpb);
         const size_t smem_excl = std::max<size_t>(sw16_smem_bytes(sp.nletters, sp.K, 4), 150 * 1024);
-        PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, smem_excl)));
-        int per_sm = 0;
-        PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSw16WarpsPerBlock * 32, smem));
+        const size_t smem16 = sw16_smem_bytes(sp.nletters, sp.K, 16);
+        PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(std::max(smem, smem_excl), smem16)));
+        PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpb * 32, smem));
+        if (per_sm * wpb < 16) {
+            int per_sm16 = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm16, fn, 16 * 32, smem16) == cudaSuccess && per_sm16 * 16 > per_sm * wpb) {
+                wpb = 16; per_sm = per_sm16; smem = smem16;
+            } else {
+                cudaGetLastError();
+            }
+        }
         if (per_sm < 1) per_sm = 1;
+        if (std::getenv("PSB_DEBUG_TIMING")) std::fprintf(stderr, "[psb] sw16: K %d, %d warps per CTA, %d CTAs per SM, %zu B shared\n", sp.K, wpb, per_sm, smem);
         if (nhead > 0) {
             // head: the longest subjects, 4 warps per CTA (one per sub-partition), each CTA alone on
             // its SM (the shared-memory request keeps the main launch's CTAs away)
@@ -1006,10 +1018,10 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
             p.word_off = db->d_word_off + nroute + nhead; p.len = db->d_len + nroute + nhead; p.n = nrest;
             p.out_map = db->d_perm + nroute + nhead; p.sid_base = (int)(nroute + nhead); p.counter = d_cnt.as<int>() + 1;
             const long long slots = ((nrest + 1) / 2 + 1) / 2;  // a warp takes two items (four subjects) at a time
-            long long blocks = std::min<long long>((slots + kSw16WarpsPerBlock - 1) / kSw16WarpsPerBlock, (long long)c.sms * per_sm);
+            long long blocks = std::min<long long>((slots + wpb - 1) / wpb, (long long)c.sms * per_sm);
             if (blocks < 1) blocks = 1;
             void *args[] = {&p};
-            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(kSw16WarpsPerBlock * 32), args, smem, forked ? c.side : c.stream));
+            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(wpb * 32), args, smem, forked ? c.side : c.stream));
             c.launches++;
         }
     }
