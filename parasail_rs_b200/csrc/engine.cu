@@ -862,7 +862,18 @@ static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open,
     return true;
 }
 
+#ifdef PSB_SW16X
+// experiment build (-DPSB_SW16X): the split-column variant of the scan kernel for K >= 8
+}  // namespace psb
+#include "kern_sw16x.cuh"
+namespace psb {
+template <int K> static const void *sw16_fn_k() {
+    if constexpr (K >= 8) return (const void *)sw16x_scan_kernel<K>;
+    else return (const void *)sw16_scan_kernel<K>;
+}
+#else
 template <int K> static const void *sw16_fn_k() { return (const void *)sw16_scan_kernel<K>; }
+#endif
 static const void *sw16_fn(int K) {
     switch (K) {
         case 4: return sw16_fn_k<4>();
