@@ -7,8 +7,11 @@
 // top stall).  Here lane t fills rows [0, KU) of column s - 2t and rows [KU, K) of column s - 2t - 1 in
 // the same step: two independent chains of half the length, the same registers, the same instructions
 // per cell.  The group becomes a 32-stage systolic array (two stages per lane), so a subject pair
-// costs 16 more steps of fill/drain (~4 % at 360 columns); whether the better issue rate pays for
-// that is what has to be measured (build with -DPSB_SW16X, tools/variant_bench.sh).
+// costs 16 more steps of fill/drain (~4 % at 360 columns).
+//
+// MEASURED (B200, config C2, build with -DPSB_SW16X, tools/variant_bench.sh): 4 718 GCUPS against the
+// shipped kernel's 5 140 (30.3 ms vs 27.85 ms per scan), results equal.  The extra parallelism inside
+// a warp does not buy issue slots; the file stays as the record of that experiment.
 //
 // Bit-exactness is checked on the CPU emulation (tests/test_emu_sw16.py::test_split_column_variant).
 #pragma once
