@@ -54,3 +54,29 @@ def test_wave_gen3_random(oracle, blosum62, seed, K, nstrips, extra, lr, o, de, 
     exp = oracle.align(q, r, mat, mode=2, open=o, gap=e)
     got = emu_harness.wave32(q, r, mat, K, 2, o, e, v2=2)
     assert got == (exp["score"], exp["end_query"], exp["end_ref"]), (K, lq, lr, o, e)
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(1, 10**6), K=st.sampled_from([1, 2, 3, 4, 8]), mode=st.sampled_from([0, 1, 2]),
+       flags=st.tuples(st.integers(0, 1), st.integers(0, 1), st.integers(0, 1), st.integers(0, 1)),
+       o=st.integers(0, 12), e=st.integers(0, 8), protein=st.booleans(),
+       variant=st.sampled_from(["score", "stats", "stats_wide", "trace"]), profile=st.booleans(),
+       lq=st.integers(1, 150), lr=st.integers(1, 90), related=st.booleans())
+def test_gotoh32_random(oracle, blosum62, seed, K, mode, flags, o, e, protein, variant, profile, lq, lr, related):
+    # the general 32-bit kernel: every mode / free-end combination / output variant, matrix reads or
+    # the per-warp int8 profile, one to several strips (lq up to 150 rows against 32*K rows per strip)
+    from test_emu_gotoh32 import compare
+    mat = blosum62 if protein else oracle.Matrix.create(b"ACGT", 2, -3)
+    if mode != 1:
+        flags = (1, 1, 1, 1)
+    r = seq(seed, 0, lr, protein)
+    if related:
+        base = np.concatenate([r] * (lq // lr + 2))[: lq + 20]
+        q = psb_data.mutate(base, seed, 1, 0.15, 0.04, protein=protein)[:lq]
+        if len(q) == 0:
+            q = seq(seed, 2, lq, protein)
+    else:
+        q = seq(seed, 3, lq, protein)
+    q2, r2 = seq(seed, 4, max(1, lq // 2), protein), seq(seed, 5, max(1, lr // 3), protein)
+    compare(oracle, mat, [q, q2], [r, r2], K, mode, o, e, flags, stats=variant.startswith("stats"), trace=variant == "trace",
+            wide=variant == "stats_wide", profile=profile)
