@@ -296,9 +296,9 @@ def main():
     roofline = {
         "bound": "int_alu_dpx", "achieved": achieved, "peak": peak_s16, "unit": "GCUPS", "frac": achieved / peak_s16,
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch on a 200k-subject
-        # scan (profiles/r1c_ncu_full_sw16_keymetrics.csv: 51.7 MB + 0.28 MB for 47.6 MB of packed
+        # scan (profiles/r1e_ncu_full_sw16_keymetrics.csv: 51.76 MB + 0.16 MB for 47.6 MB of packed
         # residues + 2.4 MB of results), scaled to this launch's algorithmic bytes
-        "traffic": packed_bytes * (51.736576e6 + 0.275456e6) / (47.589941e6 + 2.4e6),
+        "traffic": packed_bytes * (51.761152e6 + 0.164352e6) / (47.589941e6 + 2.4e6),
         "kernel": "sw16_scan_kernel<25> (packed s16x2 DPX, 16-lane groups)", "kernel_ms_per_launch": float(kms.item()),
         "peak_basis": f"148 SM x {LANE_OPS_PER_CLK_SM} lane-ops/clk x {sm_mhz:.0f} MHz (sampled) / {OPS_PER_CELL} ops per cell x 2 cells per s16x2 op",
         "peak_at_max_clock": 148 * LANE_OPS_PER_CLK_SM * 1.965 / OPS_PER_CELL * 2,
