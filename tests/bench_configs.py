@@ -3,7 +3,7 @@
 checked against the CPU oracle on a sample.  Sizes are the config sizes where host-side synthetic
 generation allows it, otherwise a stated fraction.  Writes gpurun_out/configs.json.
 
-  python tools/bench_configs.py [--quick]
+  python tests/bench_configs.py [--quick]      (test infrastructure: it runs the oracle as the checker)
 """
 import argparse
 import json
