@@ -29,6 +29,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <ctype.h>
+#include <pthread.h>
 
 #define PSBO_NEG_INF (INT32_MIN / 2)
 
@@ -44,6 +45,38 @@
 
 enum { PSBO_NW = 0, PSBO_SG = 1, PSBO_SW = 2 };
 
+/*
+ * Every behaviour below that is recalled from upstream parasail rather than read
+ * from a source file ([UP] in SURVEY.md) has ONE switch here; the defaults are the
+ * rules the product kernels implement (psb_defs.h, namespace psb::rules, mirrors
+ * them).  oracle/UP_ASSUMPTIONS.md lists each rule, its confidence and what to
+ * flip; tools/diff_vs_parasail.py tries the alternatives against a real
+ * libparasail.so the day one is available.
+ */
+typedef struct psbo_rules {
+    int sw_end_tie;          /* A.4  0: max score, then smaller end_ref, then smaller end_query (default)
+                                     1: first maximum in row-major order (smaller end_query, then smaller end_ref)
+                                     2: last maximum in row-major order */
+    int sg_col_wins_tie;     /* A.4  0: last column beats last row only when strictly greater (default); 1: on ties too */
+    int sg_row_last_wins;    /* A.4  0: first maximum of the last row / column wins (strict >, default); 1: last one (>=) */
+    int h_priority;          /* A.5  0: diag >= F >= E (default); 1: diag >= E >= F; 2: F >= E > diag (gaps win ties);
+                                     3: E >= F > diag */
+    int open_on_tie;         /* A.5  0: a gap is opened only when strictly better than extending (default); 1: ties open */
+    int match_raw_bytes;     /* A.6  0: a match is equality of mapped matrix indices (default); 1: of the raw bytes */
+    int count_boundary_gaps; /* A.6  0: leading boundary gaps of nw are not counted in length (default); 1: counted */
+    int cigar_edge_stop;     /* A.7  0: the walk runs to (-1,-1) in every mode, emitting the rest as I/D (default);
+                                     1: sg/sw stop as soon as either index leaves the table (SURVEY's reading) */
+    int cigar_swap_id;       /* A.7  0: 'I' consumes query, 'D' consumes reference (default); 1: swapped */
+    int sg_flag_swap;        /* A.3  0: qb/qe act on the top/last row, db/de on the left/last column (default); 1: swapped */
+    int zero_beats_diag;     /* A.5  1: sw cell with H == 0 is ZERO even when the diagonal sums to 0 (default); 0: diag kept */
+    int band_rule;           /* f4   0: |i - j| <= k widened by the length difference so the corner is inside (default);
+                                     1: plain |i - j| <= k */
+} psbo_rules_t;
+static psbo_rules_t g_rules = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0};
+void psbo_set_rules(const psbo_rules_t *r) { if (r) g_rules = *r; else { psbo_rules_t d = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0}; g_rules = d; } }
+void psbo_get_rules(psbo_rules_t *r) { *r = g_rules; }
+int psbo_rules_count(void) { return (int)(sizeof(psbo_rules_t) / sizeof(int)); }
+
 typedef struct psbo_config {
     int mode;    /* PSBO_NW / PSBO_SG / PSBO_SW */
     int s1_beg;  /* sg: gaps at the beginning of s1/query free  -> top row zero   (qb/qx) */
@@ -52,6 +85,7 @@ typedef struct psbo_config {
     int s2_end;  /* sg: gaps at the end of s2/ref free          -> last col ends   (de/dx) */
     int open;    /* positive penalty; a gap of length k costs open + (k-1)*gap */
     int gap;
+    int band;    /* nw only: > 0 restricts the fill to a band of half-width `band` (parasail_nw_banded); 0 = full table */
 } psbo_config_t;
 
 typedef struct psbo_matrix {
@@ -84,11 +118,20 @@ int psbo_align(const uint8_t *q, int qlen, const uint8_t *r, int rlen,
     const int o = cfg->open, e = cfg->gap;
     const int mode = cfg->mode;
     int s1_beg = 0, s1_end = 0, s2_beg = 0, s2_end = 0;
+    const psbo_rules_t R = g_rules;
     if (mode == PSBO_SG) {
         s1_beg = cfg->s1_beg; s1_end = cfg->s1_end; s2_beg = cfg->s2_beg; s2_end = cfg->s2_end;
+        if (R.sg_flag_swap) { int t; t = s1_beg; s1_beg = s2_beg; s2_beg = t; t = s1_end; s1_end = s2_end; s2_end = t; }
     }
     if (mat->is_pssm) qlen = mat->length;
     if (qlen <= 0 || rlen <= 0) return -1;
+    /* banded nw: cell (i,j) is inside iff band_lo <= j - i <= band_hi */
+    int banded = mode == PSBO_NW && cfg->band > 0, band_lo = 0, band_hi = 0;
+    if (banded) {
+        const int d = rlen - qlen;
+        band_lo = -cfg->band + ((R.band_rule == 0 && d < 0) ? d : 0);
+        band_hi = cfg->band + ((R.band_rule == 0 && d > 0) ? d : 0);
+    }
 
     const int size = mat->size;
     int *s1 = (int *)malloc(sizeof(int) * (size_t)qlen);
@@ -108,6 +151,8 @@ int psbo_align(const uint8_t *q, int qlen, const uint8_t *r, int rlen,
     for (int j = 1; j <= rlen; ++j) {
         H[j] = (mode == PSBO_SW || s1_beg) ? 0 : -o - (j - 1) * e;
         F[j] = PSBO_NEG_INF;
+        if (R.count_boundary_gaps && !(mode == PSBO_SW || s1_beg)) HL[j] = j;
+        if (banded && j > band_hi) H[j] = PSBO_NEG_INF;   /* H[-1][j-1]: row -1, column j-1 */
     }
 
     int score = PSBO_NEG_INF, end_query = qlen - 1, end_ref = rlen - 1;
@@ -122,36 +167,47 @@ int psbo_align(const uint8_t *q, int qlen, const uint8_t *r, int rlen,
         const int *matrow = &mat->matrix[(size_t)size * (mat->is_pssm ? (i - 1) : s1[i - 1])];
         int NH = H[0], NHM = HM[0], NHS = HS[0], NHL = HL[0];
         int WH = (mode == PSBO_SW || s2_beg) ? 0 : -o - (i - 1) * e; /* left column H[i][-1] */
-        int WHM = 0, WHS = 0, WHL = 0;
+        int WHM = 0, WHS = 0, WHL = (R.count_boundary_gaps && !(mode == PSBO_SW || s2_beg)) ? i : 0;
+        if (banded && -i < band_lo) WH = PSBO_NEG_INF;
         int E = PSBO_NEG_INF, EM = 0, ES = 0, EL = 0;
-        H[0] = WH; HM[0] = 0; HS[0] = 0; HL[0] = 0;
+        H[0] = WH; HM[0] = 0; HS[0] = 0; HL[0] = WHL;
         for (int j = 1; j <= rlen; ++j) {
             int NWH = NH, NWM = NHM, NWS = NHS, NWL = NHL;
             int tflag = 0;
             NH = H[j]; NHM = HM[j]; NHS = HS[j]; NHL = HL[j];
             /* F: vertical, opened from the cell above iff strictly better (A.5) */
             int F_opn = NH - o, F_ext = F[j] - e;
-            if (F_opn > F_ext) { F[j] = F_opn; FM[j] = NHM; FS[j] = NHS; FL[j] = NHL + 1; tflag |= T_DIAG_F; }
+            if (F_opn > F_ext || (R.open_on_tie && F_opn == F_ext)) { F[j] = F_opn; FM[j] = NHM; FS[j] = NHS; FL[j] = NHL + 1; tflag |= T_DIAG_F; }
             else               { F[j] = F_ext;                            FL[j] = FL[j] + 1; tflag |= T_DEL_F; }
             /* E: horizontal, opened from the cell to the left iff strictly better */
             int E_opn = WH - o, E_ext = E - e;
-            if (E_opn > E_ext) { E = E_opn; EM = WHM; ES = WHS; EL = WHL + 1; tflag |= T_DIAG_E; }
+            if (E_opn > E_ext || (R.open_on_tie && E_opn == E_ext)) { E = E_opn; EM = WHM; ES = WHS; EL = WHL + 1; tflag |= T_DIAG_E; }
             else               { E = E_ext;                     EL = EL + 1;  tflag |= T_INS_E; }
             int sub = matrow[s2[j - 1]];
             int H_dag = NWH + sub;
-            /* H source priority: diagonal >= both, else F if F >= E, else E */
-            if (H_dag >= E && H_dag >= F[j]) {
+            /* H source priority (rule h_priority): diagonal >= both, else F if F >= E, else E */
+            int take_diag, take_f;
+            switch (R.h_priority) {
+                case 1: take_diag = H_dag >= E && H_dag >= F[j]; take_f = F[j] > E; break;
+                case 2: take_diag = H_dag > E && H_dag > F[j]; take_f = F[j] >= E; break;
+                case 3: take_diag = H_dag > E && H_dag > F[j]; take_f = F[j] > E; break;
+                default: take_diag = H_dag >= E && H_dag >= F[j]; take_f = F[j] >= E; break;
+            }
+            if (take_diag) {
                 WH = H_dag;
-                WHM = NWM + (s1[i - 1] == s2[j - 1]);
+                WHM = NWM + (R.match_raw_bytes ? (q && q[i - 1] == r[j - 1]) : (s1[i - 1] == s2[j - 1]));
                 WHS = NWS + (sub > 0);
                 WHL = NWL + 1;
                 tflag |= T_DIAG;
-            } else if (F[j] >= E) {
+            } else if (take_f) {
                 WH = F[j]; WHM = FM[j]; WHS = FS[j]; WHL = FL[j]; tflag |= T_DEL;
             } else {
                 WH = E; WHM = EM; WHS = ES; WHL = EL; tflag |= T_INS;
             }
-            if (mode == PSBO_SW && WH <= 0) { /* ZERO wins, stats reset */
+            if (banded && (j - i < band_lo || j - i > band_hi)) { /* outside the band: unreachable */
+                WH = PSBO_NEG_INF; E = PSBO_NEG_INF; F[j] = PSBO_NEG_INF; WHM = WHS = WHL = 0; tflag = 0;
+            }
+            if (mode == PSBO_SW && (WH < 0 || (WH == 0 && (R.zero_beats_diag || !(tflag & T_DIAG))))) { /* ZERO wins, stats reset */
                 WH = 0; WHM = 0; WHS = 0; WHL = 0;
                 tflag &= ~(T_DIAG | T_DEL | T_INS);
             }
@@ -177,17 +233,17 @@ int psbo_align(const uint8_t *q, int qlen, const uint8_t *r, int rlen,
             }
 
             if (mode == PSBO_SW) {
-                /* A.4: max score, then smallest end_ref, then smallest end_query */
-                if (WH > score || (WH == score && (j - 1) < end_ref)) {
+                /* A.4: max score, then smallest end_ref, then smallest end_query (rule sw_end_tie) */
+                if (WH > score || (WH == score && (R.sw_end_tie == 0 ? (j - 1) < end_ref : R.sw_end_tie == 2))) {
                     score = WH; end_query = i - 1; end_ref = j - 1;
                     matches = WHM; similar = WHS; length = WHL;
                 }
             } else if (mode == PSBO_SG) {
-                if (s1_end && i == qlen && WH > score) { /* last row, left to right, strict */
+                if (s1_end && i == qlen && (WH > score || (R.sg_row_last_wins && WH == score))) { /* last row, left to right, strict */
                     score = WH; end_query = i - 1; end_ref = j - 1;
                     matches = WHM; similar = WHS; length = WHL;
                 }
-                if (s2_end && j == rlen && WH > col_score) { /* last column, top to bottom, strict */
+                if (s2_end && j == rlen && (WH > col_score || (R.sg_row_last_wins && WH == col_score))) { /* last column, top to bottom, strict */
                     col_score = WH; col_i = i - 1; col_m = WHM; col_s = WHS; col_l = WHL;
                 }
             }
@@ -199,7 +255,7 @@ int psbo_align(const uint8_t *q, int qlen, const uint8_t *r, int rlen,
     }
     if (mode == PSBO_SG && s2_end) {
         /* the last column beats the last row only when strictly greater (A.4) */
-        if (!s1_end || col_score > score) {
+        if (!s1_end || col_score > score || (R.sg_col_wins_tie && col_score == score)) {
             score = col_score; end_query = col_i; end_ref = rlen - 1;
             matches = col_m; similar = col_s; length = col_l;
         }
@@ -223,14 +279,16 @@ int psbo_align(const uint8_t *q, int qlen, const uint8_t *r, int rlen,
  */
 int psbo_cigar(const int8_t *trace, const uint8_t *q, int qlen, const uint8_t *r, int rlen,
                const psbo_matrix_t *mat, int end_query, int end_ref,
-               uint32_t *ops_out, int *beg_query, int *beg_ref)
+               uint32_t *ops_out, int *beg_query, int *beg_ref, int mode)
 {
     (void)qlen;
+    const psbo_rules_t R = g_rules;
+    const uint32_t OP_I = R.cigar_swap_id ? 2 : 1, OP_D = R.cigar_swap_id ? 1 : 2;
     int64_t i = end_query, j = end_ref;
     int where = T_DIAG;
     uint32_t *rev = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(end_query + end_ref + 4));
     int nrev = 0;
-    int cur_op = -1; uint32_t cur_len = 0;
+    int64_t cur_op = -1; uint32_t cur_len = 0;
 #define EMIT(op_) do { \
         if (cur_op == (op_)) { cur_len++; } \
         else { \
@@ -238,23 +296,25 @@ int psbo_cigar(const int8_t *trace, const uint8_t *q, int qlen, const uint8_t *r
             cur_op = (op_); cur_len = 1; \
         } } while (0)
     while (i >= 0 || j >= 0) {
-        if (i < 0) { EMIT(2); --j; continue; }
-        if (j < 0) { EMIT(1); --i; continue; }
+        if ((i < 0 || j < 0) && R.cigar_edge_stop && mode != PSBO_NW) break;
+        if (i < 0) { EMIT(OP_D); --j; continue; }
+        if (j < 0) { EMIT(OP_I); --i; continue; }
         int t = trace[(size_t)i * (size_t)rlen + (size_t)j];
         if (where == T_DIAG) {
             if (t & T_DIAG) {
                 int a = mat->mapper[q[i]], b = mat->mapper[r[j]];
+                if (R.match_raw_bytes) { a = q[i]; b = r[j]; }
                 EMIT(a == b ? 7 : 8);
                 --i; --j;
             } else if (t & T_INS) { where = T_INS; }
             else if (t & T_DEL) { where = T_DEL; }
             else break; /* ZERO */
         } else if (where == T_INS) { /* E: horizontal, consumes reference */
-            EMIT(2);
+            EMIT(OP_D);
             where = (t & T_DIAG_E) ? T_DIAG : T_INS;
             --j;
         } else { /* F: vertical, consumes query */
-            EMIT(1);
+            EMIT(OP_I);
             where = (t & T_DIAG_F) ? T_DIAG : T_DEL;
             --i;
         }
@@ -274,12 +334,14 @@ int psbo_cigar(const int8_t *trace, const uint8_t *q, int qlen, const uint8_t *r
  */
 int psbo_traceback(const int8_t *trace, const uint8_t *q, int qlen, const uint8_t *r, int rlen,
                    const psbo_matrix_t *mat, int end_query, int end_ref,
-                   char match, char pos, char neg, char *qs, char *cs, char *rs)
+                   char match, char pos, char neg, char *qs, char *cs, char *rs, int mode)
 {
     (void)qlen;
+    const psbo_rules_t R = g_rules;
     int64_t i = end_query, j = end_ref;
     int where = T_DIAG, n = 0;
     while (i >= 0 || j >= 0) {
+        if ((i < 0 || j < 0) && R.cigar_edge_stop && mode != PSBO_NW) break;
         if (i < 0) { qs[n] = '-'; rs[n] = (char)r[j]; cs[n] = ' '; ++n; --j; continue; }
         if (j < 0) { qs[n] = (char)q[i]; rs[n] = '-'; cs[n] = ' '; ++n; --i; continue; }
         int t = trace[(size_t)i * (size_t)rlen + (size_t)j];
@@ -317,36 +379,174 @@ int psbo_traceback(const int8_t *trace, const uint8_t *q, int qlen, const uint8_
  * With want_cigar the trace table is built per pair and walked; ops go to a
  * CSR (cig_off has n+1 entries, cig_ops capacity cig_cap).  Returns 0 or -1.
  */
+typedef struct psbo_batch_job {
+    const uint8_t *qcat; const int64_t *qoff; const uint8_t *rcat; const int64_t *roff;
+    int64_t n; int shared_query; const psbo_config_t *cfg; const psbo_matrix_t *mat;
+    int *score, *end_query, *end_ref, *matches, *similar, *length;
+    int want_cigar; uint32_t *cig_ops; int64_t cig_cap; int *nops_of; int *beg_query, *beg_ref;
+    int64_t next;   /* shared work counter */
+    int failed;
+} psbo_batch_job_t;
+
+static int64_t batch_slot(const psbo_batch_job_t *J, int64_t p, int qlen)
+{
+    return (J->shared_query ? (int64_t)qlen * p : J->qoff[p] - J->qoff[0]) + (J->roff[p] - J->roff[0]);
+}
+
+static void *batch_worker(void *arg)
+{
+    psbo_batch_job_t *J = (psbo_batch_job_t *)arg;
+    for (;;) {
+        const int64_t p0 = __atomic_fetch_add(&J->next, 8, __ATOMIC_RELAXED);
+        if (p0 >= J->n || __atomic_load_n(&J->failed, __ATOMIC_RELAXED)) break;
+        for (int64_t p = p0; p < p0 + 8 && p < J->n; ++p) {
+            const uint8_t *q = J->shared_query ? J->qcat : J->qcat + J->qoff[p];
+            int qlen = (int)(J->shared_query ? J->qoff[1] - J->qoff[0] : J->qoff[p + 1] - J->qoff[p]);
+            const uint8_t *r = J->rcat + J->roff[p];
+            int rlen = (int)(J->roff[p + 1] - J->roff[p]);
+            psbo_out_t o; memset(&o, 0, sizeof(o));
+            int8_t *trace = NULL;
+            if (J->want_cigar) {
+                trace = (int8_t *)malloc((size_t)qlen * (size_t)rlen); o.trace = trace;
+                if (!trace) { __atomic_store_n(&J->failed, 1, __ATOMIC_RELAXED); break; }
+            }
+            if (psbo_align(q, qlen, r, rlen, J->cfg, J->mat, &o) != 0) { free(trace); __atomic_store_n(&J->failed, 1, __ATOMIC_RELAXED); break; }
+            J->score[p] = o.score; J->end_query[p] = o.end_query; J->end_ref[p] = o.end_ref;
+            if (J->matches) J->matches[p] = o.matches;
+            if (J->similar) J->similar[p] = o.similar;
+            if (J->length) J->length[p] = o.length;
+            if (J->want_cigar) {
+                const int64_t slot = batch_slot(J, p, qlen);
+                if (slot + qlen + rlen > J->cig_cap) { free(trace); __atomic_store_n(&J->failed, 1, __ATOMIC_RELAXED); break; }
+                int bq, br;
+                J->nops_of[p] = psbo_cigar(trace, q, qlen, r, rlen, J->mat, o.end_query, o.end_ref, J->cig_ops + slot, &bq, &br, J->cfg->mode);
+                J->beg_query[p] = bq; J->beg_ref[p] = br;
+                free(trace);
+            }
+        }
+    }
+    return NULL;
+}
+
+static int g_threads = 1;
+/* worker threads of psbo_align_batch (pairs are independent; results do not depend on the count) */
+void psbo_set_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+
 int psbo_align_batch(const uint8_t *qcat, const int64_t *qoff, const uint8_t *rcat, const int64_t *roff,
                      int64_t n, int shared_query, const psbo_config_t *cfg, const psbo_matrix_t *mat,
                      int *score, int *end_query, int *end_ref, int *matches, int *similar, int *length,
                      int want_cigar, uint32_t *cig_ops, int64_t cig_cap, int64_t *cig_off,
                      int *beg_query, int *beg_ref)
 {
-    int64_t used = 0;
-    if (want_cigar && cig_off) cig_off[0] = 0;
-    for (int64_t p = 0; p < n; ++p) {
-        const uint8_t *q = shared_query ? qcat : qcat + qoff[p];
-        int qlen = (int)(shared_query ? qoff[1] - qoff[0] : qoff[p + 1] - qoff[p]);
-        const uint8_t *r = rcat + roff[p];
-        int rlen = (int)(roff[p + 1] - roff[p]);
-        psbo_out_t o; memset(&o, 0, sizeof(o));
-        int8_t *trace = NULL;
-        if (want_cigar) { trace = (int8_t *)malloc((size_t)qlen * (size_t)rlen); o.trace = trace; if (!trace) return -1; }
-        if (psbo_align(q, qlen, r, rlen, cfg, mat, &o) != 0) { free(trace); return -1; }
-        score[p] = o.score; end_query[p] = o.end_query; end_ref[p] = o.end_ref;
-        if (matches) matches[p] = o.matches;
-        if (similar) similar[p] = o.similar;
-        if (length) length[p] = o.length;
-        if (want_cigar) {
-            if (used + qlen + rlen > cig_cap) { free(trace); return -1; }
-            int bq, br;
-            int nops = psbo_cigar(trace, q, qlen, r, rlen, mat, o.end_query, o.end_ref, cig_ops + used, &bq, &br);
-            used += nops; cig_off[p + 1] = used; beg_query[p] = bq; beg_ref[p] = br;
-            free(trace);
+    /* with want_cigar every pair first writes its ops at a private slot of cig_ops (slot p starts at
+     * the sum of the lengths before it, so slots cannot overlap), then the slots are compacted */
+    psbo_batch_job_t J;
+    memset(&J, 0, sizeof(J));
+    J.qcat = qcat; J.qoff = qoff; J.rcat = rcat; J.roff = roff; J.n = n; J.shared_query = shared_query;
+    J.cfg = cfg; J.mat = mat; J.score = score; J.end_query = end_query; J.end_ref = end_ref;
+    J.matches = matches; J.similar = similar; J.length = length;
+    J.want_cigar = want_cigar; J.cig_ops = cig_ops; J.cig_cap = cig_cap; J.beg_query = beg_query; J.beg_ref = beg_ref;
+    J.nops_of = want_cigar ? (int *)calloc((size_t)n + 1, sizeof(int)) : NULL;
+    if (want_cigar && !J.nops_of) return -1;
+    int nt = g_threads;
+    if ((int64_t)nt > (n + 7) / 8) nt = (int)((n + 7) / 8);
+    if (nt <= 1) batch_worker(&J);
+    else {
+        pthread_t th[256];
+        int started = 0;
+        for (int t = 0; t < nt; ++t) if (pthread_create(&th[started], NULL, batch_worker, &J) == 0) ++started;
+        if (started == 0) batch_worker(&J);
+        for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+    }
+    if (J.failed) { free(J.nops_of); return -1; }
+    if (want_cigar) {
+        int64_t used = 0;
+        cig_off[0] = 0;
+        for (int64_t p = 0; p < n; ++p) {
+            const int qlen = (int)(shared_query ? qoff[1] - qoff[0] : qoff[p + 1] - qoff[p]);
+            memmove(cig_ops + used, cig_ops + batch_slot(&J, p, qlen), sizeof(uint32_t) * (size_t)J.nops_of[p]);
+            used += J.nops_of[p];
+            cig_off[p + 1] = used;
         }
+        free(J.nops_of);
     }
     return 0;
+}
+
+/*
+ * Oracle-free property of a batch of CIGARs (SURVEY 8d "CIGAR re-score / recount on all pairs"): walking
+ * each CIGAR from (beg_query, beg_ref) must consume exactly up to (end_query, end_ref), every '=' must sit
+ * on equal mapped residues and every 'X' on unequal ones, and -- for sw and nw -- the substitution scores
+ * minus the affine gap costs must add up to the reported score.  Returns the number of pairs that fail
+ * (first failing pair in *first_bad), or -1 on bad arguments.  Threaded like psbo_align_batch.
+ */
+typedef struct psbo_check_job {
+    const uint8_t *qcat; const int64_t *qoff; const uint8_t *rcat; const int64_t *roff; int64_t n;
+    const psbo_config_t *cfg; const psbo_matrix_t *mat;
+    const uint32_t *ops; const int64_t *off; const int *bq, *br, *eq, *er, *score;
+    int64_t next, bad, first_bad;
+} psbo_check_job_t;
+
+static void *check_worker(void *arg)
+{
+    psbo_check_job_t *J = (psbo_check_job_t *)arg;
+    const int o = J->cfg->open, e = J->cfg->gap;
+    for (;;) {
+        const int64_t p0 = __atomic_fetch_add(&J->next, 64, __ATOMIC_RELAXED);
+        if (p0 >= J->n) break;
+        for (int64_t p = p0; p < p0 + 64 && p < J->n; ++p) {
+            const uint8_t *q = J->qcat + J->qoff[p], *r = J->rcat + J->roff[p];
+            const int64_t qlen = J->qoff[p + 1] - J->qoff[p], rlen = J->roff[p + 1] - J->roff[p];
+            int64_t i = J->bq[p], j = J->br[p], sc = 0;
+            int ok = 1;
+            for (int64_t k = J->off[p]; k < J->off[p + 1] && ok; ++k) {
+                const int op = (int)(J->ops[k] & 0xf);
+                const int64_t len = J->ops[k] >> 4;
+                if (op == 7 || op == 8) {
+                    for (int64_t t = 0; t < len; ++t, ++i, ++j) {
+                        if (i >= qlen || j >= rlen) { ok = 0; break; }
+                        const int a = J->mat->mapper[q[i]], b = J->mat->mapper[r[j]];
+                        if ((a == b) != (op == 7)) { ok = 0; break; }
+                        sc += J->mat->matrix[(size_t)J->mat->size * (J->mat->is_pssm ? (int)i : a) + b];
+                    }
+                } else if (op == 1 || op == 2) {
+                    /* a local alignment that reaches the table's edge carries the rest of the other sequence as
+                     * one leading I / D run (walk rule cigar_edge_stop = 0): that run is outside the score */
+                    const int free_run = J->cfg->mode == PSBO_SW && k == J->off[p];
+                    if (op == 1) i += len; else j += len;
+                    if (!free_run) sc -= o + (len - 1) * e;
+                } else ok = 0;
+            }
+            if (ok && (i - 1 != J->eq[p] || j - 1 != J->er[p]) && !(J->off[p] == J->off[p + 1])) ok = 0;
+            if (ok && (J->cfg->mode == PSBO_SW || J->cfg->mode == PSBO_NW) && sc != J->score[p]) ok = 0;
+            if (!ok) {
+                __atomic_fetch_add(&J->bad, 1, __ATOMIC_RELAXED);
+                int64_t cur = __atomic_load_n(&J->first_bad, __ATOMIC_RELAXED);
+                while ((cur < 0 || p < cur) && !__atomic_compare_exchange_n(&J->first_bad, &cur, p, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            }
+        }
+    }
+    return NULL;
+}
+
+int64_t psbo_cigar_check_batch(const uint8_t *qcat, const int64_t *qoff, const uint8_t *rcat, const int64_t *roff, int64_t n,
+                               const psbo_config_t *cfg, const psbo_matrix_t *mat, const uint32_t *ops, const int64_t *off,
+                               const int *beg_query, const int *beg_ref, const int *end_query, const int *end_ref,
+                               const int *score, int64_t *first_bad)
+{
+    if (!qcat || !rcat || !ops || !off || n <= 0) return -1;
+    psbo_check_job_t J;
+    memset(&J, 0, sizeof(J));
+    J.qcat = qcat; J.qoff = qoff; J.rcat = rcat; J.roff = roff; J.n = n; J.cfg = cfg; J.mat = mat;
+    J.ops = ops; J.off = off; J.bq = beg_query; J.br = beg_ref; J.eq = end_query; J.er = end_ref; J.score = score;
+    J.first_bad = -1;
+    pthread_t th[256];
+    int started = 0;
+    for (int t = 0; t < g_threads; ++t) if (pthread_create(&th[started], NULL, check_worker, &J) == 0) ++started;
+    if (started == 0) check_worker(&J);
+    for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+    if (first_bad) *first_bad = J.first_bad;
+    return J.bad;
 }
 
 /* decode len<<4|op words to "12=1X3I" text; returns bytes written (excl. NUL) */

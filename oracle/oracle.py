@@ -15,7 +15,34 @@ NW, SG, SW = 0, 1, 2
 
 class Config(C.Structure):
     _fields_ = [("mode", C.c_int), ("s1_beg", C.c_int), ("s1_end", C.c_int), ("s2_beg", C.c_int),
-                ("s2_end", C.c_int), ("open", C.c_int), ("gap", C.c_int)]
+                ("s2_end", C.c_int), ("open", C.c_int), ("gap", C.c_int), ("band", C.c_int)]
+
+
+RULE_NAMES = ("sw_end_tie", "sg_col_wins_tie", "sg_row_last_wins", "h_priority", "open_on_tie", "match_raw_bytes",
+              "count_boundary_gaps", "cigar_edge_stop", "cigar_swap_id", "sg_flag_swap", "zero_beats_diag", "band_rule")
+RULE_DEFAULTS = dict(zip(RULE_NAMES, (0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0)))
+
+
+class Rules(C.Structure):
+    """the [UP] assumptions of SURVEY Appendix A as switches (oracle/UP_ASSUMPTIONS.md)"""
+    _fields_ = [(n, C.c_int) for n in RULE_NAMES]
+
+
+def set_rules(**kw):
+    """override some of the upstream-behaviour assumptions (process-wide); set_rules() restores the defaults"""
+    vals = dict(RULE_DEFAULTS)
+    for k, v in kw.items():
+        if k not in vals:
+            raise KeyError(k)
+        vals[k] = int(v)
+    r = Rules(*[vals[n] for n in RULE_NAMES])
+    assert lib().psbo_rules_count() == len(RULE_NAMES)
+    lib().psbo_set_rules(C.byref(r))
+
+
+def set_threads(n):
+    """worker threads of align_batch (0 = all hardware threads)"""
+    lib().psbo_set_threads(int(n) if n > 0 else (os.cpu_count() or 1))
 
 
 class CMatrix(C.Structure):
@@ -110,13 +137,13 @@ def _u8(b):
 
 
 def align(q, r, mat: Matrix, mode=NW, open=0, gap=0, s1_beg=True, s1_end=True, s2_beg=True, s2_end=True,
-          tables=False, rowcol=False, trace=False):
+          tables=False, rowcol=False, trace=False, band=0):
     """One pair through the oracle.  Returns a dict with score/ends/stats and any requested
     tables, rows/cols, trace bytes, CIGAR (ops, text, beg_query, beg_ref) and traceback strings."""
     qa, ra = _u8(q), _u8(r)
     qlen = mat.length if mat.is_pssm else len(qa)
     rlen = len(ra)
-    cfg = Config(mode, int(s1_beg), int(s1_end), int(s2_beg), int(s2_end), open, gap)
+    cfg = Config(mode, int(s1_beg), int(s1_end), int(s2_beg), int(s2_end), open, gap, band)
     out = Out()
     keep = {}
 
@@ -149,7 +176,7 @@ def align(q, r, mat: Matrix, mode=NW, open=0, gap=0, s1_beg=True, s1_end=True, s
         n = lib().psbo_cigar(keep["trace"].ctypes.data_as(C.c_void_p), qa.ctypes.data_as(C.c_void_p),
                              C.c_int(qlen), ra.ctypes.data_as(C.c_void_p), C.c_int(rlen), C.byref(mat.c),
                              C.c_int(out.end_query), C.c_int(out.end_ref), ops.ctypes.data_as(C.c_void_p),
-                             C.byref(bq), C.byref(br))
+                             C.byref(bq), C.byref(br), C.c_int(mode))
         res["cigar_ops"] = ops[:n].copy()
         res["cigar"] = decode_cigar(ops[:n])
         res["beg_query"], res["beg_ref"] = bq.value, br.value
@@ -157,7 +184,7 @@ def align(q, r, mat: Matrix, mode=NW, open=0, gap=0, s1_beg=True, s1_end=True, s
         lib().psbo_traceback(keep["trace"].ctypes.data_as(C.c_void_p), qa.ctypes.data_as(C.c_void_p),
                              C.c_int(qlen), ra.ctypes.data_as(C.c_void_p), C.c_int(rlen), C.byref(mat.c),
                              C.c_int(out.end_query), C.c_int(out.end_ref), C.c_char(b"|"), C.c_char(b" "),
-                             C.c_char(b" "), bufs[0], bufs[1], bufs[2])
+                             C.c_char(b" "), bufs[0], bufs[1], bufs[2], C.c_int(mode))
         res["traceback"] = tuple(b.value.decode() for b in bufs)
     return res
 
@@ -168,13 +195,14 @@ def decode_cigar(ops):
 
 
 def align_batch(qcat, qoff, rcat, roff, mat: Matrix, mode=NW, open=0, gap=0, s1_beg=True, s1_end=True,
-                s2_beg=True, s2_end=True, shared_query=False, stats=False, cigar=False):
-    """n pairs through the oracle (single thread).  Returns dict of int32 arrays (+ CIGAR CSR)."""
+                s2_beg=True, s2_end=True, shared_query=False, stats=False, cigar=False, threads=1):
+    """n pairs through the oracle (`threads` workers, 0 = all).  Returns dict of int32 arrays (+ CIGAR CSR)."""
     qcat, rcat = _u8(qcat), _u8(rcat)
     qoff = np.ascontiguousarray(qoff, dtype=np.int64)
     roff = np.ascontiguousarray(roff, dtype=np.int64)
     n = len(roff) - 1
-    cfg = Config(mode, int(s1_beg), int(s1_end), int(s2_beg), int(s2_end), open, gap)
+    cfg = Config(mode, int(s1_beg), int(s1_end), int(s2_beg), int(s2_end), open, gap, 0)
+    set_threads(threads)
     res = {k: np.zeros(n, dtype=np.int32) for k in ("score", "end_query", "end_ref", "matches", "similar",
                                                      "length", "beg_query", "beg_ref")}
     cap = 0
@@ -198,6 +226,26 @@ def align_batch(qcat, qoff, rcat, roff, mat: Matrix, mode=NW, open=0, gap=0, s1_
         res["cigar_off"] = cig_off
         res["cigar_ops"] = cig_ops[: cig_off[-1]].copy()
     return res
+
+
+def cigar_check_batch(qcat, qoff, rcat, roff, mat: Matrix, mode, open, gap, cigar_ops, cigar_off, beg_query, beg_ref,
+                      end_query, end_ref, score, threads=0):
+    """CIGAR re-score / recount property on a whole batch (no oracle fill involved): returns (number of
+    pairs whose CIGAR does not re-derive its own score and end cell, index of the first one or -1)."""
+    qcat, rcat = _u8(qcat), _u8(rcat)
+    a64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    a32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    qoff, roff, cigar_off = a64(qoff), a64(roff), a64(cigar_off)
+    ops = np.ascontiguousarray(cigar_ops, dtype=np.uint32)
+    bq, br, eq, er, sc = a32(beg_query), a32(beg_ref), a32(end_query), a32(end_ref), a32(score)
+    cfg = Config(mode, 1, 1, 1, 1, open, gap, 0)
+    set_threads(threads)
+    first = C.c_int64(-1)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().psbo_cigar_check_batch.restype = C.c_int64
+    bad = lib().psbo_cigar_check_batch(p(qcat), p(qoff), p(rcat), p(roff), C.c_int64(len(roff) - 1), C.byref(cfg), C.byref(mat.c),
+                                       p(ops), p(cigar_off), p(bq), p(br), p(eq), p(er), p(sc), C.byref(first))
+    return int(bad), int(first.value)
 
 
 # ---- the striped AVX2 CPU baseline (oracle/striped_cpu.cpp) -----------------------------------

@@ -187,6 +187,17 @@ class Profile:
         return Profile(p, bool(with_stats), len(q))
 
     @staticmethod
+    def new_ssw(query_bytes, matrix, score_size):
+        """[REF src/profile/mod.rs:337-358]"""
+        if len(query_bytes) == 0:
+            raise Panic("Query sequence has length 0.")
+        q = _bytes(query_bytes, "query")
+        p = lib().parasail_ssw_init(q, len(q), matrix.inner, int(score_size))
+        if not p:
+            raise NullProfile()
+        return Profile(p, True, len(q))
+
+    @staticmethod
     def builder(query, matrix):
         return ProfileBuilder(query, matrix)
 
@@ -535,6 +546,32 @@ class AlignerBuilder:
                        self._bandwidth)
 
 
+class SSWResult:
+    """[REF src/alignment/mod.rs:506-551] field reads on parasail_result_ssw_t, freed on drop"""
+
+    def __init__(self, inner):
+        self.inner = inner
+
+    def score(self): return int(self.inner.contents.score1)
+    def ref_start(self): return int(self.inner.contents.ref_begin1)
+    def ref_end(self): return int(self.inner.contents.ref_end1)
+    def query_start(self): return int(self.inner.contents.read_begin1)
+    def query_end(self): return int(self.inner.contents.read_end1)
+    def cigar_len(self): return int(self.inner.contents.cigarLen)
+
+    def cigar(self):
+        n = self.cigar_len()
+        return np.ctypeslib.as_array(self.inner.contents.cigar, shape=(n,)).copy() if n else np.zeros(0, dtype=np.uint32)
+
+    def __del__(self):
+        try:
+            if self.inner:
+                lib().parasail_result_ssw_free(self.inner)
+                self.inner = None
+        except Exception:
+            pass
+
+
 class Aligner:
     def __init__(self, fn_name, fn_ptr, matrix, gap_open, gap_extend, profile, vec_strategy, bandwidth):
         self.fn_name = fn_name
@@ -564,6 +601,15 @@ class Aligner:
             raise NoBandwidth()
         res = lib().parasail_nw_banded(q, len(q), r, len(r), self.gap_open, self.gap_extend, self._bandwidth, self.matrix.inner)
         return Alignment(res, self.matrix, len(q), len(r))
+
+    def ssw(self, query, reference):
+        """Striped-Smith-Waterman-compatible local alignment [REF src/aligner/mod.rs:491-529]"""
+        r = _bytes(reference, "reference")
+        if query is None:
+            raise Panic("Query sequence is required for SSW alignment for now.")
+        q = _bytes(query, "query")
+        res = lib().parasail_ssw(q, len(q), r, len(r), self.gap_open, self.gap_extend, self.matrix.inner)
+        return SSWResult(res)
 
     # ---- new batched entry points ------------------------------------------------------------
     def align_batch(self, queries, references):

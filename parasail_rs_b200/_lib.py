@@ -28,6 +28,12 @@ class CCigar(C.Structure):
     _fields_ = [("seq", C.POINTER(C.c_uint32)), ("len", C.c_int), ("beg_query", C.c_int), ("beg_ref", C.c_int)]
 
 
+class CResultSSW(C.Structure):
+    """parasail_result_ssw_t [REF src/alignment/mod.rs:507-551 reads these fields directly]"""
+    _fields_ = [("score1", C.c_uint16), ("ref_begin1", C.c_int32), ("ref_end1", C.c_int32), ("read_begin1", C.c_int32),
+                ("read_end1", C.c_int32), ("cigar", C.POINTER(C.c_uint32)), ("cigarLen", C.c_int32)]
+
+
 class CTraceback(C.Structure):
     _fields_ = [("query", C.c_void_p), ("comp", C.c_void_p), ("ref", C.c_void_p)]
 
@@ -136,6 +142,12 @@ def lib():
                                              C.c_int, C.c_int, C.c_int]
     L.parasail_nw_banded.restype = C.POINTER(CResult)
     L.parasail_nw_banded.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CMatrix)]
+    L.parasail_ssw.restype = C.POINTER(CResultSSW)
+    L.parasail_ssw.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(CMatrix)]
+    L.parasail_ssw_init.restype = C.c_void_p
+    L.parasail_ssw_init.argtypes = [C.c_char_p, C.c_int, C.POINTER(CMatrix), C.c_int8]
+    L.parasail_result_ssw_free.restype = None
+    L.parasail_result_ssw_free.argtypes = [C.POINTER(CResultSSW)]
     L.psb_last_error.restype = C.c_char_p
     L.psb_version.restype = C.c_char_p
     L.psb_device_count.restype = C.c_int

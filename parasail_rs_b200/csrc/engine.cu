@@ -25,6 +25,7 @@
 #include "kern_sw16.cuh"
 #include "kern_util.cuh"
 #include "kern_wave32.cuh"
+#include "pairs16_host.h"
 #include "psb_internal.h"
 
 namespace psb {
@@ -383,21 +384,54 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     const int64_t q_lo = req.shared_query ? req.q_off[0] : req.q_off[lo];
     const int64_t q_hi = req.shared_query ? req.q_off[1] : req.q_off[hi];
     const int64_t r_lo = req.r_off[lo], r_hi = req.r_off[hi];
-    const bool fine = gotoh32_profile_ok(m.size, m.min, m.max, req.open, pssm) && !want_table;
+    const bool banded = cfg.band > 0 && cfg.mode == MODE_NW && n == 1 && !cfg.stats && !cfg.trace && !want_table;
+    const bool fine = gotoh32_profile_ok(m.size, m.min, m.max, req.open, pssm) && !want_table && !banded;
     const ClassTable ct = class_table(fine);
     std::vector<std::vector<int>> cls(kNumClass);
+    // packed 16-bit path (kern_pairs16.cuh): pairs whose scoring scheme and lengths pass the static 16-bit
+    // bound; `_stats` results come from the trace walk there.  Explicit 32/64-bit requests, table outputs and
+    // the single-pair trace-table export stay on the 32-bit kernels.
+    const bool p16_walk = cfg.trace || cfg.stats;
+    const bool p16_on = !std::getenv("PSB_NO_P16") && pairs16_scheme_ok(m.size, m.min, m.max, req.open, req.gap, pssm) && !want_table &&
+                        !banded && cfg.width != 32 && cfg.width != 64 && !(req.extra && cfg.trace);
+    std::vector<std::vector<int>> p16_ids(p16_on ? p16_num_classes() : 0);
+    long long n_p16 = 0;
     std::vector<int> wave_ids;   // long score-only pairs: spread over the whole GPU one at a time
     int max_lr_multistrip = 0;
     int max_sum = 0, max_min = 0;
     bool uniform = true;
     int first_cls = -1;
     long long first_cells = -1;
+    int first_lq = -1, first_lr = -1;
+    // query length -> packed class.  Wide (32-lane) groups halve the profile bytes per warp: taken when the
+    // narrow class would leave fewer than 8 warps per SM (protein alphabets, queries beyond ~200 residues)
+    std::vector<int> c16_of(513, -1);
+    if (p16_on) {
+        const char *ev = std::getenv("PSB_P16_WIDE");
+        for (int lq = 1; lq <= 512; ++lq) {
+            const int narrow = p16_pick_class(lq, false);
+            bool wide = narrow >= 0 && 227 * 1024 / pairs16_warp_smem(p16_class(narrow).K, m.size + 1, cfg.mode == MODE_SW) < 8;
+            if (ev) wide = std::atoi(ev) != 0;
+            c16_of[lq] = p16_pick_class(lq, wide);
+        }
+    }
     for (int64_t i = 0; i < n; ++i) {
         const int lq = pssm ? m.length : (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + i + 1] - req.q_off[lo + i]);
         const int lr = (int)(req.r_off[lo + i + 1] - req.r_off[lo + i]);
         if (lq <= 0 || lr <= 0) { set_error("empty sequence in batch (pair " + std::to_string(lo + i) + ")"); return PSB_EINVAL; }
+        if (first_lq < 0) { first_lq = lq; first_lr = lr; }
+        else if (lq != first_lq || lr != first_lr) uniform = false;
+        if (p16_on && lq <= 512) {
+            const int c16 = c16_of[lq];
+            if (c16 >= 0 && pairs16_fits(p16_class(c16).G * p16_class(c16).K, lq, lr, m.max, m.min, req.open, req.gap, p16_walk)) {
+                p16_ids[c16].push_back((int)i);
+                ++n_p16;
+                b->cells += (double)lq * lr;
+                continue;
+            }
+        }
         const int cl = class_of_len(ct, lq);
-        const bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !cfg.stats && !cfg.trace && !(req.extra && (cfg.table || cfg.rowcol));
+        const bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !cfg.stats && !cfg.trace && !(req.extra && (cfg.table || cfg.rowcol)) && !banded;
         if (wave) { wave_ids.push_back((int)i); uniform = false; }
         else cls[cl].push_back((int)i);
         if (!wave && lq > 32 * ct.k[cl]) max_lr_multistrip = std::max(max_lr_multistrip, lr);
@@ -408,7 +442,8 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         else if (cl != first_cls || cells != first_cells) uniform = false;
         b->cells += (double)cells;
     }
-    const bool wide_stats = !(max_min < 1024 && max_sum < 4096);
+    // the coarse family carries only the wide statistics word: the strip-boundary scratch is sized for it
+    const bool wide_stats = !(max_min < 1024 && max_sum < 4096) || !fine;
 
     // upload residues + offsets (relative to this range) and map them to matrix columns
     DevMem d_q, d_r, d_qoff, d_roff, d_matrix;
@@ -463,8 +498,15 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     std::vector<long long> trace_off, rev_off;
     long long trace_total = 0, rev_total = 0;
     if (want_trace || want_table) {
-        trace_off.resize(n);
+        trace_off.assign(n, 0);
         rev_off.resize(n);
+        for (int c16 = 0; c16 < (int)p16_ids.size(); ++c16)
+            for (int id : p16_ids[c16]) {
+                const int lq = (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + id + 1] - req.q_off[lo + id]);
+                const int lr = (int)(req.r_off[lo + id + 1] - req.r_off[lo + id]);
+                rev_off[id] = rev_total;
+                rev_total += lq + lr + 2;
+            }
         for (int cl = 0; cl < kNumClass; ++cl)
             for (int id : cls[cl]) {
                 const int K = ct.k[cl];
@@ -496,6 +538,115 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     p.trace = d_trace.as<uint8_t>(); p.trace_off = d_traceoff.as<long long>();
     p.tabH = d_tab[0].as<int>(); p.tabM = d_tab[1].as<int>(); p.tabS = d_tab[2].as<int>(); p.tabL = d_tab[3].as<int>();
     p.tab_off = d_traceoff.as<long long>();
+    if (banded) {
+        // [REF src/aligner/mod.rs:457-489] band of half-width k around the main diagonal, widened by the
+        // length difference so that the corner (Lq-1, Lr-1) stays inside
+        const int lq1 = pssm ? m.length : (int)(q_hi - q_lo), lr1 = (int)(r_hi - r_lo), d = lr1 - lq1;
+        p.banded = 1; p.band_lo = -cfg.band + (d < 0 ? d : 0); p.band_hi = cfg.band + (d > 0 ? d : 0);
+    }
+
+    // CIGAR scratch of the device-side walks (both kernel families write the same reversed run lists)
+    if (want_trace) {
+        PSB_TRY(d_rev.alloc((size_t)rev_total * sizeof(unsigned), c.stream));
+        PSB_TRY(d_revoff.alloc((size_t)n * sizeof(long long), c.stream));
+        PSB_CUDA(cudaMemcpyAsync(d_revoff.p, rev_off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+        PSB_TRY(d_nops.alloc(((size_t)n + 1) * sizeof(int), c.stream));
+        PSB_CUDA(cudaMemsetAsync(d_nops.p, 0, ((size_t)n + 1) * sizeof(int), c.stream));
+        PSB_TRY(d_beg[0].alloc((size_t)n * sizeof(int), c.stream));
+        PSB_TRY(d_beg[1].alloc((size_t)n * sizeof(int), c.stream));
+    }
+
+    // ---- packed 16-bit classes: two pairs per register, sorted by reference length so that the pairs of
+    // a word (and the words of a warp) are of similar size -----------------------------------------------
+    DevMem d_items, d_toff16, d_slot16, d_ids16, d_mat8, d_trace16, d_cnt16;
+    std::vector<int> h_items, h_slot16, h_ids16;   // kept alive until the stream has consumed them
+    std::vector<long long> h_toff16;
+    std::vector<int8_t> h_mat8(33 * 32);
+    if (n_p16 > 0) {
+        const bool sw = cfg.mode == MODE_SW;
+        h_items.reserve((size_t)n_p16 + 2 * p16_ids.size());
+        h_ids16.reserve((size_t)n_p16);
+        if (p16_walk) h_slot16.assign((size_t)n, 0);
+        std::vector<int> cls_item0(p16_ids.size() + 1, 0), cls_id0(p16_ids.size() + 1, 0);
+        h_toff16.push_back(0);
+        for (int c16 = 0; c16 < (int)p16_ids.size(); ++c16) {
+            std::vector<int> &ids = p16_ids[c16];
+            cls_item0[c16] = (int)(h_items.size() / 2);
+            cls_id0[c16] = (int)h_ids16.size();
+            if (ids.empty()) continue;
+            const P16Class pc = p16_class(c16);
+            if (!uniform)
+                std::stable_sort(ids.begin(), ids.end(), [&](int a, int bb) {
+                    return req.r_off[lo + a + 1] - req.r_off[lo + a] > req.r_off[lo + bb + 1] - req.r_off[lo + bb];
+                });
+            for (size_t t = 0; t < ids.size(); t += 2) {
+                const int a = ids[t], bb = t + 1 < ids.size() ? ids[t + 1] : -1;
+                const int item = (int)(h_items.size() / 2);
+                h_items.push_back(a); h_items.push_back(bb);
+                if (p16_walk) {
+                    const long long lra = req.r_off[lo + a + 1] - req.r_off[lo + a];
+                    const long long lrb = bb >= 0 ? req.r_off[lo + bb + 1] - req.r_off[lo + bb] : 0;
+                    h_toff16.push_back(h_toff16.back() + pairs16_item_trace_words(pc.G, pc.K, (int)std::max(lra, lrb)));
+                    h_slot16[a] = 2 * item;
+                    if (bb >= 0) h_slot16[bb] = 2 * item + 1;
+                }
+            }
+            h_ids16.insert(h_ids16.end(), ids.begin(), ids.end());
+        }
+        cls_item0[p16_ids.size()] = (int)(h_items.size() / 2);
+        cls_id0[p16_ids.size()] = (int)h_ids16.size();
+        const bool top_free = sw || (cfg.mode == MODE_SG && cfg.s1_beg);
+        pairs16_build_mat8(m.table.data(), m.size, req.open, top_free, h_mat8.data());
+        PSB_TRY(d_items.alloc(h_items.size() * sizeof(int), c.stream));
+        PSB_TRY(d_mat8.alloc(h_mat8.size(), c.stream));
+        PSB_TRY(d_cnt16.alloc(sizeof(int) * (p16_ids.size() + 1), c.stream));
+        PSB_CUDA(cudaMemcpyAsync(d_items.p, h_items.data(), h_items.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        PSB_CUDA(cudaMemcpyAsync(d_mat8.p, h_mat8.data(), h_mat8.size(), cudaMemcpyHostToDevice, c.stream));
+        PSB_CUDA(cudaMemsetAsync(d_cnt16.p, 0, sizeof(int) * (p16_ids.size() + 1), c.stream));
+        if (p16_walk) {
+            PSB_TRY(d_toff16.alloc(h_toff16.size() * sizeof(long long), c.stream));
+            PSB_TRY(d_slot16.alloc(h_slot16.size() * sizeof(int), c.stream));
+            PSB_TRY(d_ids16.alloc(h_ids16.size() * sizeof(int), c.stream));
+            PSB_TRY(d_trace16.alloc((size_t)h_toff16.back() * sizeof(unsigned) + 64, c.stream));
+            PSB_CUDA(cudaMemcpyAsync(d_toff16.p, h_toff16.data(), h_toff16.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+            PSB_CUDA(cudaMemcpyAsync(d_slot16.p, h_slot16.data(), h_slot16.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+            PSB_CUDA(cudaMemcpyAsync(d_ids16.p, h_ids16.data(), h_ids16.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        }
+        std::string err;
+        for (int c16 = 0; c16 < (int)p16_ids.size(); ++c16) {
+            const int nitems = cls_item0[c16 + 1] - cls_item0[c16];
+            if (nitems == 0) continue;
+            Pairs16Params pp;
+            std::memset(&pp, 0, sizeof(pp));
+            pp.q = p.q; pp.q_off = p.q_off; pp.r = p.r; pp.r_off = p.r_off; pp.shared_query = p.shared_query;
+            pp.items = d_items.as<int>() + 2 * (size_t)cls_item0[c16]; pp.nitems = nitems;
+            pp.mat8 = d_mat8.as<int8_t>(); pp.size = m.size; pp.open = req.open; pp.gap = req.gap;
+            pp.mode = cfg.mode; pp.s1_beg = cfg.s1_beg; pp.s1_end = cfg.s1_end; pp.s2_beg = cfg.s2_beg; pp.s2_end = cfg.s2_end;
+            pp.score = p.score; pp.end_query = p.end_query; pp.end_ref = p.end_ref;
+            pp.trace = d_trace16.as<unsigned>(); pp.trace_off = p16_walk ? d_toff16.as<long long>() + cls_item0[c16] : nullptr;
+            pp.counter = d_cnt16.as<int>() + c16;
+            const int rc16 = p16_launch(c16, sw, p16_walk, pp, c.sms, c.stream, &err);
+            if (rc16 != PSB_OK) { set_error(err); return rc16; }
+            c.launches++;
+            if (p16_walk) {
+                Walk16Params w;
+                std::memset(&w, 0, sizeof(w));
+                w.q = p.q; w.q_off = p.q_off; w.r = p.r; w.r_off = p.r_off; w.shared_query = p.shared_query;
+                w.pair_ids = d_ids16.as<int>() + cls_id0[c16]; w.pair_slot = d_slot16.as<int>(); w.n = cls_id0[c16 + 1] - cls_id0[c16];
+                w.G = p16_class(c16).G; w.K = p16_class(c16).K;
+                w.trace = d_trace16.as<unsigned>(); w.trace_off = d_toff16.as<long long>();
+                w.matrix = p.matrix; w.size = m.size; w.open = req.open; w.gap = req.gap; w.is_sw = sw ? 1 : 0;
+                w.score = p.score; w.end_query = p.end_query; w.end_ref = p.end_ref;
+                w.rev_ops = d_rev.as<unsigned>(); w.rev_off = d_revoff.as<long long>();
+                w.nops = d_nops.as<int>(); w.beg_query = d_beg[0].as<int>(); w.beg_ref = d_beg[1].as<int>();
+                w.matches = p.matches; w.similar = p.similar; w.length = p.length;
+                const int rcw = p16_launch_walk(w, !cfg.trace, c.stream, &err);
+                if (rcw != PSB_OK) { set_error(err); return rcw; }
+                c.launches++;
+            }
+        }
+        b->n_retried += 0;
+    }
 
     std::vector<DevMem> d_orders(kNumClass);
     for (int cl = 0; cl < kNumClass; ++cl) {
@@ -528,13 +679,6 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     // device-side trace walk -> CIGAR CSR
     DevMem d_csroff, d_csr, d_scan_tmp;
     if (want_trace) {
-        PSB_TRY(d_rev.alloc((size_t)rev_total * sizeof(unsigned), c.stream));
-        PSB_TRY(d_revoff.alloc((size_t)n * sizeof(long long), c.stream));
-        PSB_CUDA(cudaMemcpyAsync(d_revoff.p, rev_off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
-        PSB_TRY(d_nops.alloc(((size_t)n + 1) * sizeof(int), c.stream));
-        PSB_CUDA(cudaMemsetAsync(d_nops.p, 0, ((size_t)n + 1) * sizeof(int), c.stream));
-        PSB_TRY(d_beg[0].alloc((size_t)n * sizeof(int), c.stream));
-        PSB_TRY(d_beg[1].alloc((size_t)n * sizeof(int), c.stream));
         for (int cl = 0; cl < kNumClass; ++cl) {
             if (cls[cl].empty()) continue;
             if (!d_orders[cl].p) {
@@ -692,20 +836,34 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
     c.last_ms = 0.0; c.launches = 0;
     psb_batch_t *b = new_batch(req.n, req.cfg);
     if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
-    // trace batches are cut so that a pass's trace + scratch stays within a fixed budget
-    const int64_t budget = (int64_t)24 << 30;
+    // batches that keep per-cell decisions (trace, and `_stats` on the packed path, whose statistics come from
+    // the walk) are cut so that a pass's decision bits + scratch stay within a budget of device memory
+    int64_t budget = (int64_t)64 << 30;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min<int64_t>(budget, (int64_t)(free_b / 2));
+        else cudaGetLastError();
+        budget = std::max<int64_t>(budget, (int64_t)1 << 30);
+    }
+    const HostMatrix &hm0 = *req.matrix;
+    const bool p16_scheme = !std::getenv("PSB_NO_P16") && pairs16_scheme_ok(hm0.size, hm0.min, hm0.max, req.open, req.gap, hm0.type == PARASAIL_MATRIX_TYPE_PSSM) &&
+                            req.cfg.width != 32 && req.cfg.width != 64 && !req.extra;
     int64_t csr_used = 0;
     int64_t lo = 0;
     while (lo < req.n) {
         int64_t hi = req.n;
-        if (req.cfg.trace) {
+        if (req.cfg.trace || (req.cfg.stats && p16_scheme)) {
             int64_t bytes = 0;
             hi = lo;
             while (hi < req.n) {
                 const int64_t lq = req.shared_query ? req.q_off[1] - req.q_off[0] : req.q_off[hi + 1] - req.q_off[hi];
                 const int64_t lr = req.r_off[hi + 1] - req.r_off[hi];
-                const int K = 16;  // upper bound on rows per lane of any class
-                const int64_t need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);
+                int64_t need;
+                if (p16_scheme && lq <= 512) need = (lr + 32) * (lq + 288) / 2 + 8 * (lq + lr);   // half a byte per cell of the padded frame
+                else if (req.cfg.trace) {
+                    const int K = 16;  // upper bound on rows per lane of any class
+                    need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);
+                } else need = 0;
                 if (hi > lo && bytes + need > budget) break;
                 bytes += need; ++hi;
             }
@@ -730,6 +888,7 @@ struct psb_db {
     int maxlen = 0;                 // longest subject
     int nlong = 0;                  // subjects longer than 65535 (sorted first)
     std::vector<int> top_len;       // lengths of the (up to 4096) longest subjects, descending
+    std::vector<int> host_len;      // caller-order lengths (psb_db_create only; explicit-width saturation flags)
     uint8_t mapper[256];
     unsigned *d_words = nullptr;
     long long *d_word_off = nullptr;  // n+1, sorted order (length descending, stable)
@@ -746,7 +905,10 @@ struct DevProfile {
     int *d_matrix = nullptr;
     cudaStream_t stream = nullptr;  // allocation stream (stream-ordered pool)
     std::vector<uint8_t> mapped;    // host copy of the mapped query
-    Sw16Profile sw16;               // packed int8 profile (+open) for the 16-bit scan kernel
+    // packed profiles (+open) of the 16-bit scan kernel, one per gap-open value ever used with this
+    // profile on this device: built under the profile's mutex, immutable afterwards and freed only in
+    // release_profile_resident, so concurrent scans with different penalties never see a buffer replaced
+    std::map<int, Sw16Profile> sw16;
 };
 
 void release_profile_resident(parasail_profile *p) {
@@ -756,8 +918,9 @@ void release_profile_resident(parasail_profile *p) {
         int cur = 0;
         cudaGetDevice(&cur);
         cudaSetDevice(kv.first);
-        void *ptrs[] = {d->d_query, d->d_qoff, d->d_matrix, d->sw16.prof};
+        void *ptrs[] = {d->d_query, d->d_qoff, d->d_matrix};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, d->stream);
+        for (auto &sp : d->sw16) if (sp.second.prof) cudaFreeAsync(sp.second.prof, d->stream);
         cudaSetDevice(cur);
         delete d;
     }
@@ -816,7 +979,7 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
     DevMem d_counter, d_bnd;
     PSB_TRY(d_counter.alloc(sizeof(int), c.stream));
     PSB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int), c.stream));
-    const bool wide = !(std::min(lq, db->maxlen) < 1024 && lq + db->maxlen < 4096);
+    const bool wide = !(std::min(lq, db->maxlen) < 1024 && lq + db->maxlen < 4096) || !fine;
     // a re-run list is almost always empty or tiny: a small persistent grid serves any count
     const int nwork = d_count ? (int)std::min<int64_t>(nsubset, (int64_t)g_ctx.sms * 2 * kWarpsPerBlock) : (d_subset ? nsubset : (int)db->n);
     long long bnd_stride = 0;
@@ -843,23 +1006,27 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
 }
 
 
-// (re)build the packed 16-bit profile when the gap-open penalty baked into it changes
-static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open, int gap) {
+// the packed 16-bit profile for this gap-open penalty: built once per (device, open) and then shared
+// read-only by every thread that scans with this profile (Profile: Send + Sync upstream)
+static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open, int gap, Sw16Profile *out) {
     Ctx &c = g_ctx;
     const HostMatrix &m = prof->matrix;
     if (m.type != PARASAIL_MATRIX_TYPE_SQUARE) return false;
     std::lock_guard<std::mutex> lk(prof->mu);
-    if (dp->sw16.prof && dp->sw16.open_baked == open) return sw16_supported(dp->sw16, open, gap);
+    auto it = dp->sw16.find(open);
+    if (it != dp->sw16.end()) { *out = it->second; return it->second.prof != nullptr && sw16_supported(it->second, open, gap); }
     Sw16Profile np_;
     std::vector<int8_t> host;
-    if (!sw16_build_profile(dp->mapped.data(), (int)dp->mapped.size(), m.table.data(), m.size, open, &np_, &host)) return false;
-    if (!sw16_supported(np_, open, gap)) return false;
-    if (dp->sw16.prof) { cudaFreeAsync(dp->sw16.prof, dp->stream); dp->sw16.prof = nullptr; }
+    if (!sw16_build_profile(dp->mapped.data(), (int)dp->mapped.size(), m.table.data(), m.size, open, &np_, &host)) {
+        dp->sw16[open] = Sw16Profile();   // remember that this penalty has no packed form
+        return false;
+    }
     if (cudaMallocAsync(&np_.prof, host.size(), c.stream) != cudaSuccess) { cudaGetLastError(); return false; }
     if (cudaMemcpyAsync(np_.prof, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return false;
-    cudaStreamSynchronize(c.stream);  // `host` goes out of scope
-    dp->sw16 = np_;
-    return true;
+    cudaStreamSynchronize(c.stream);  // `host` goes out of scope; other streams may use the buffer from here on
+    dp->sw16[open] = np_;
+    *out = np_;
+    return sw16_supported(np_, open, gap);
 }
 
 #ifdef PSB_SW16X
@@ -898,10 +1065,9 @@ static constexpr int kSw16WarpsPerBlock = SW16_WARPS_PER_BLOCK;
 // is -- what limits strong scaling at 8 GPUs.  Those few subjects ("head") are therefore swept by
 // a separate small launch of the same kernel, one warp per SM sub-partition on SMs it owns
 // outright, beside the main launch.
-static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, int open, int gap, psb_db *db,
+static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, const Sw16Profile &sp, int open, int gap, psb_db *db,
                      int *const d_out[6], int64_t *n_retried, int *retried_host) {
     Ctx &c = g_ctx;
-    const Sw16Profile &sp = dp->sw16;
     const HostMatrix &m = prof->matrix;
     const int lq = sp.lq;
     // one group step costs ~0.6 us when the SM is full; keep a subject's sweep under ~40 % of the
@@ -1099,13 +1265,15 @@ int psb_align_pairs(const char *fn_name, const parasail_matrix_t *matrix, int op
     req.q_cat = q_cat; req.q_off = q_off; req.r_cat = r_cat; req.r_off = r_off; req.n = n;
     const int rc = run_pairs(req, out);
     if (rc == PSB_OK && (cfg.width == 8 || cfg.width == 16)) {
-        // explicit narrow widths: flag pairs whose optimum does not fit
+        // explicit narrow widths: flag pairs whose values do not fit, the same rule as align_one
         psb_batch_t *b = *out;
-        const long long hi = cfg.width == 8 ? 127 : 32767;
-        for (int64_t i = 0; i < n; ++i)
-            if ((long long)b->score[i] + std::max(hm.max, 0) > hi || (long long)b->score[i] + std::min(hm.min, 0) < -hi - 1) {
+        const bool pssm = hm.type == PARASAIL_MATRIX_TYPE_PSSM;
+        for (int64_t i = 0; i < n; ++i) {
+            const int lq = pssm ? hm.length : (int)(q_off[i + 1] - q_off[i]), lr = (int)(r_off[i + 1] - r_off[i]);
+            if (saturates(cfg, hm, b->score[i], lq, lr, open, gap)) {
                 b->saturated[i] = 1; b->score[i] = 0; b->end_query[i] = 0; b->end_ref[i] = 0;
             }
+        }
     }
     return rc;
 }
@@ -1296,7 +1464,14 @@ psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const
     DbBuild B;
     psb_db *db = db_begin(B, cat, off, n, hm, false);
     if (!db) return nullptr;
-    if (db_finish(B) != PSB_OK) { cudaStreamSynchronize(g_ctx.stream); psb_db_free(db); return nullptr; }
+    // the caller's buffers must be free to go when this returns: wait for the uploads (not for the packing)
+    cudaEvent_t up = nullptr;
+    if (cudaEventCreateWithFlags(&up, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(up, g_ctx.stream);
+    db->host_len.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) db->host_len[(size_t)i] = (int)(off[i + 1] - off[i]);
+    const int rc = db_finish(B);
+    if (up) { cudaEventSynchronize(up); cudaEventDestroy(up); } else cudaStreamSynchronize(g_ctx.stream);
+    if (rc != PSB_OK) { cudaStreamSynchronize(g_ctx.stream); psb_db_free(db); return nullptr; }
     return db;
 }
 
@@ -1352,9 +1527,10 @@ static int scan_enqueue(ScanJob &job, const FnConfig &cfg, const parasail_profil
     PSB_CUDA(cudaEventCreate(&job.ev0));
     PSB_CUDA(cudaEventCreate(&job.ev1));
     PSB_CUDA(cudaEventRecord(job.ev0, c.stream));
-    const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 && sw16_prepare(profile, dp, open, gap);
+    Sw16Profile sp16;
+    const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 && sw16_prepare(profile, dp, open, gap, &sp16);
     int rc;
-    if (fast) rc = scan_sw16(cfg, profile, dp, open, gap, db, outp, &job.retried, job.retried_host);
+    if (fast) rc = scan_sw16(cfg, profile, dp, sp16, open, gap, db, outp, &job.retried, job.retried_host);
     else rc = scan_general(cfg, profile, dp, open, gap, db, nullptr, 0, nullptr, outp);
     if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); return rc; }
     PSB_CUDA(cudaEventRecord(job.ev1, c.stream));
@@ -1408,6 +1584,11 @@ int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, i
     if (rc == PSB_OK) rc = scan_finish(job);
     if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); free_batch(b); return rc; }
     b->n_retried = job.retried;
+    if (cfg.width == 8 || cfg.width == 16)
+        for (int64_t i = 0; i < db->n; ++i)
+            if (saturates(cfg, profile->matrix, b->score[i], (int)profile->query.size(), db->host_len.empty() ? db->maxlen : db->host_len[(size_t)i], open, gap)) {
+                b->saturated[i] = 1; b->score[i] = 0; b->end_query[i] = 0; b->end_ref[i] = 0;
+            }
     *out = b;
     return PSB_OK;
 }
@@ -1490,6 +1671,11 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
         if (rc == PSB_OK) rc = r;
     }
     if (rc != PSB_OK) { free_batch(b); return rc; }
+    if (cfg.width == 8 || cfg.width == 16)
+        for (int64_t i = 0; i < n; ++i)
+            if (saturates(cfg, hm, b->score[i], (int)profile->query.size(), (int)(off[i + 1] - off[i]), open, gap)) {
+                b->saturated[i] = 1; b->score[i] = 0; b->end_query[i] = 0; b->end_ref[i] = 0;
+            }
     *out = b;
     return PSB_OK;
 }

@@ -55,6 +55,8 @@ struct Gotoh32Params {
     const int *r_len;           // residues of each subject
     int r_bits;                 // 5 or 2
     const int *n_dev;           // when set, the number of work items is read from device memory
+    // parasail_nw_banded (coarse family only): cell (i, j) is reachable iff band_lo <= j - i <= band_hi
+    int banded, band_lo, band_hi;
 };
 
 // statistics word: matches | similar | length packed so that one add updates all three
@@ -160,7 +162,8 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                 rowq[k] = valid ? qi : -1;
                 rowbase[k] = valid ? (p.is_pssm ? i * size : qi * size) : -1;
                 // left boundary H[i][-1]
-                const int hl = left_free ? 0 : -o - i * e;
+                int hl = left_free ? 0 : -o - i * e;
+                if (!PROF && p.banded && -(i + 1) < p.band_lo) hl = NEG_INF32;   // column -1 of row i
                 T[k] = hl - o;
                 E[k] = NEG_INF32;
                 Hs[k] = 0; Es[k] = 0;
@@ -183,6 +186,7 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
             }
             // H[i0-1][-1]: corner of the whole table for i0 == 0, else the left boundary above
             int Tdiag_in = (i0 == 0) ? -o : ((left_free ? 0 : -o - (i0 - 1) * e) - o);
+            if (!PROF && p.banded && i0 > 0 && -i0 < p.band_lo) Tdiag_in = NEG_INF32 - o;
             SWord Hsdiag_in = 0;
             int Tout = 0, Fout = NEG_INF32;   // bottom row of this lane, previous step
             SWord Hsout = 0, Fsout = 0;
@@ -221,6 +225,7 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                 if (lane == 0 && active) {
                     if (strip == 0) {
                         Tup = (top_free ? 0 : -o - j * e) - o;
+                        if (!PROF && p.banded && j + 1 > p.band_hi) Tup = NEG_INF32 - o;   // row -1 of column j
                         Fup = NEG_INF32;
                         Hsup = 0; Fsup = 0;
                     } else {
@@ -257,6 +262,10 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                             Fn = viaddmax(Fu, -e, Tu);
                             const int h = viaddmax(Td, So, En);
                             H = is_sw ? vimax3(h, Fn, 0) : (h > Fn ? h : Fn);
+                            if (!PROF && p.banded) {
+                                const int d = j - (i0 + k);
+                                if (d < p.band_lo || d > p.band_hi) { H = NEG_INF32; En = NEG_INF32; Fn = NEG_INF32; }
+                            }
                         } else {
                             const int Eext = E[k] - e, Fext = Fu - e;
                             const bool eopen = Tl > Eext, fopen = Tu > Fext;

@@ -1,0 +1,547 @@
+// kern_pairs16.cuh -- many independent pairs in packed 16-bit lanes (DPX VIADDMNMX.S16x2 and friends):
+// every 32-bit register holds the same cell of TWO different pairs, a group of G lanes is a G-stage
+// systolic array over the query rows, and a warp runs 32/G groups -- 4 pairs per warp for G = 16.
+//
+// Replaces upstream parasail_{nw,sg*,sw}[_trace|_stats]_{striped,scan,diag}_{16,sat} for the many-pairs
+// entry point psb_align_pairs (SURVEY configs C1, C3, C4) [REF src/aligner/mod.rs:411-429 is the per-pair
+// call it batches]; results follow SURVEY.md Appendix A through the rule constants of psb_defs.h.
+//
+// Design notes (nothing here mirrors parasail's striped CPU layout):
+//   * true (unshifted) score space with the vertical gap carried as Fh = F + open, so that the only
+//     loop-carried dependency between the K rows of a lane is ONE instruction (needs open >= extend):
+//        E  = max(E - e, Tleft)           Tleft = H[i][j-1] - o
+//        h  = max(Tdiag + (S+o), E)       = max(H[i-1][j-1] + S, E)
+//        H  = max(Fh - o, h [, 0])        VIADDMNMX.S16x2[.RELU]
+//        Fh'= max(Fh - e, h)              equals max(Fh - e, H) wherever it can matter
+//        T  = H - o                       VIADD.16x2
+//   * every pair has its own query, so each group builds two int8 query profiles (one per half) of
+//     (S + open) in shared memory, [letter][lane][K rows]; a step fetches the two letters' slots and
+//     PRMT (sign-replicating selectors) interleaves them into one s16x2 score word per row.
+//   * the query is aligned to the BOTTOM of the G*K rows: the padding rows sit above row 0 and are made
+//     transparent (they reproduce the top boundary exactly: score -128 with a zero left boundary for
+//     nw-style tops, score 0 for free tops), so the last query row is always row K-1 of lane G-1 and the
+//     last row / corner candidates of nw and sg come out of a register that is live anyway.
+//   * 16-bit safety is decided on the host by a static bound on the pair's lengths (pairs16_fits);
+//     anything that does not fit goes to the 32-bit kernel, so there is no saturation to detect here.
+//   * TRACE: four raw decision bits per cell -- "E extends", "F extends", "diagonal is the maximum",
+//     "F >= E" -- taken from the sign bits of packed differences and packed eight rows to a byte, stored
+//     as 2*ceil(K/8) words per lane and step ([step][lane][word], one coalesced run per group and step:
+//     half a byte per cell).  The ZERO state of local alignment is not stored: the walk tracks the value
+//     of H along the path and stops when it reaches 0.  walk16_kernel turns the bits into the CIGAR run
+//     list or into (matches, similar, length) -- the statistics are those of the traceback path, which
+//     is how `_stats` results are produced for batches (same source priorities).
+#pragma once
+#include "psb_defs.h"
+#include "psb_simt.h"
+
+namespace psb {
+
+struct Pairs16Params {
+    const uint8_t *q;           // residues mapped to matrix indices
+    const long long *q_off;     // n+1 (shared_query: [0],[1])
+    const uint8_t *r;
+    const long long *r_off;
+    int shared_query;
+    const int *items;           // 2 pair ids per work item; the second is -1 when the item holds one pair
+    int nitems;
+    const int8_t *mat8;         // [33][32] int8, mat8[a*32 + x] = S(x, a) + open for query letter x and reference
+                                // letter a; column 31 = the padding row above the query, row `size` = the pad letter
+    int size;
+    int open, gap;
+    int mode, s1_beg, s1_end, s2_beg, s2_end;
+    int *score, *end_query, *end_ref;     // indexed by pair id
+    unsigned *trace;            // TRACE: decision bits
+    const long long *trace_off; // first word of each item's block
+    int *counter;               // dynamic work queue over warp slots
+};
+
+inline constexpr int pairs16_slot(int K) { return ((K + 3) / 4) * 4; }        // profile bytes per lane and letter
+inline constexpr int pairs16_trace_words(int K) { return 2 * ((K + 7) / 8); } // decision words per lane and step
+inline size_t pairs16_warp_smem(int K, int nletters, bool sw) {
+    const size_t prof = (size_t)64 * nletters * pairs16_slot(K);   // (32/G groups) x 2 halves x letters x G lanes x slot
+    const size_t park = sw ? (size_t)2 * 32 * pairs16_slot(K) * 4 : 0;
+    return 2 * 64 * 4 + 16 + park + prof;
+}
+inline size_t pairs16_smem_bytes(int K, int nletters, bool sw, int warps) {
+    return 33 * 32 + (size_t)warps * pairs16_warp_smem(K, nletters, sw);
+}
+// words of decision bits of one item
+inline long long pairs16_item_trace_words(int G, int K, int lr_max) {
+    return (((long long)(lr_max + G - 1) * G * pairs16_trace_words(K)) + 3) / 4 * 4;
+}
+// static 16-bit bound: every intermediate of the fill (and, with trace, every difference of two of
+// them) stays inside int16 for this pair in a G*K-row frame
+inline bool pairs16_fits(int rows, int lq, int lr, int smax, int smin, int open, int gap, bool trace) {
+    const long long pos = (long long)(lq < lr ? lq : lr) * (smax > 0 ? smax : 0) + 2ll * open + 256;
+    const long long neg = 3ll * open + (long long)(rows + lr + 4) * gap + 256 + (smin < 0 ? -smin : 0);
+    return trace ? pos + neg < 32000 : (pos < 32000 && neg < 32000);
+}
+// the kernel's preconditions on the scoring scheme (the int8 profile and the one-instruction F chain)
+inline bool pairs16_scheme_ok(int size, int mat_min, int mat_max, int open, int gap, bool pssm) {
+    return !pssm && size <= 30 && gap >= 0 && open >= gap && mat_max + open <= 127 && mat_min + open >= -127 && open <= 127;
+}
+// host-side build of the [33][32] score table; pad_top = score byte of the padding rows above the query
+inline void pairs16_build_mat8(const int *table, int size, int open, bool top_free, int8_t *out) {
+    for (int x = 0; x < 33 * 32; ++x) out[x] = (int8_t)-128;
+    for (int a = 0; a < size; ++a) {
+        for (int x = 0; x < size; ++x) out[a * 32 + x] = (int8_t)(table[(size_t)x * size + a] + open);
+        out[a * 32 + 31] = (int8_t)(top_free ? open : -128);
+    }
+}
+
+PSB_DEV unsigned p16_pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+PSB_DEV int p16_lo(unsigned w) { return (int)(short)(w & 0xffffu); }
+PSB_DEV int p16_hi(unsigned w) { return (int)(short)(w >> 16); }
+
+template <int G, int K, bool SW, bool TRACE>
+PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
+    constexpr int NG = 32 / G;
+    constexpr int SLOT = ((K + 3) / 4) * 4;
+    constexpr int NW4 = SLOT / 4;
+    constexpr unsigned LSTRIDE = (unsigned)G * SLOT;
+    constexpr int TW = 2 * ((K + 7) / 8);
+    constexpr int ROWS = G * K;
+    PSB_SHARED_DECL(smem_raw);
+    const int lane = lane_id();
+    const int lg = lane & (G - 1);
+    const int grp = lane / G;
+    const int NL = p.size + 1;
+    const int pad_code = p.size;
+    // ---- shared memory: the byte score table, then per warp: rings, published bests, parked columns, profiles
+    for (int x = thread_in_block(); x < 33 * 32 / 4; x += threads_per_block()) ((unsigned *)smem_raw)[x] = ((const unsigned *)p.mat8)[x];
+    sync_block();
+    const unsigned char *mot = smem_raw;
+    const size_t park_bytes = SW ? (size_t)2 * 32 * SLOT * 4 : 0;
+    const size_t warp_bytes = 2 * 64 * 4 + 16 + park_bytes + (size_t)64 * NL * SLOT;
+    unsigned char *wsm = smem_raw + 33 * 32 + (size_t)warp_in_block() * warp_bytes;
+    unsigned *ring = (unsigned *)wsm + (NG == 2 ? grp * 64 : 0);
+    volatile unsigned *gpub = (volatile unsigned *)(wsm + 2 * 64 * 4) + grp;
+    uint4 *park = (uint4 *)(wsm + 2 * 64 * 4 + 16);
+    unsigned char *prof = wsm + 2 * 64 * 4 + 16 + park_bytes + (size_t)grp * 2 * NL * LSTRIDE;   // this group's two profiles
+    const unsigned char *pa_base = prof + lg * SLOT;
+    const unsigned char *pb_base = prof + (size_t)NL * LSTRIDE + lg * SLOT;
+
+    const int o = p.open, e = p.gap;
+    const unsigned NEGE = p16_pack(-e, -e), NEGO = p16_pack(-o, -o);
+    const int mode = p.mode;
+    const bool top_free = SW || (mode == MODE_SG && p.s1_beg);
+    const bool left_free = SW || (mode == MODE_SG && p.s2_beg);
+    const bool row_ends = !SW && mode == MODE_SG && p.s1_end;
+    const bool col_ends = !SW && mode == MODE_SG && p.s2_end;
+    const int nslots = (p.nitems + NG - 1) / NG;
+
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomic_add(p.counter, 1);
+        slot = shfl(slot, 0);
+        if (slot >= nslots) break;
+        int item = slot * NG + grp;
+        const bool item_ok = item < p.nitems;
+        if (!item_ok) item = p.nitems - 1;
+        const int pidA = p.items[2 * item];
+        int pidB = p.items[2 * item + 1];
+        const bool hasB = pidB >= 0;
+        if (!hasB) pidB = pidA;
+        const long long qoA = p.shared_query ? p.q_off[0] : p.q_off[pidA], qoB = p.shared_query ? p.q_off[0] : p.q_off[pidB];
+        const int LqA = (int)((p.shared_query ? p.q_off[1] : p.q_off[pidA + 1]) - qoA);
+        const int LqB = (int)((p.shared_query ? p.q_off[1] : p.q_off[pidB + 1]) - qoB);
+        const long long roA = p.r_off[pidA], roB = p.r_off[pidB];
+        const int LrA = (int)(p.r_off[pidA + 1] - roA), LrB = (int)(p.r_off[pidB + 1] - roB);
+        const int padA = ROWS - LqA, padB = ROWS - LqB;     // padding rows above each query
+        const int Lmax = LrA > LrB ? LrA : LrB;
+        int nsteps = Lmax + G - 1;
+        if (NG == 2) { const int other = shfl_xor(nsteps, 16); nsteps = nsteps > other ? nsteps : other; }
+
+        // ---- the two query profiles of this group: lane t writes its own K rows for every letter ----------
+        sync_warp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint8_t *qs = p.q + (half ? qoB : qoA);
+            const int pad = half ? padB : padA;
+            int rowq[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = lg * K + k - pad;
+                rowq[k] = i >= 0 ? (int)qs[i] : 31;
+            }
+            unsigned char *dst = prof + (size_t)half * NL * LSTRIDE + lg * SLOT;
+            for (int a = 0; a < NL; ++a) {
+                const unsigned char *mrow = mot + a * 32;
+#pragma unroll
+                for (int c = 0; c < NW4; ++c) {
+                    unsigned w = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (4 * c + b < K) w |= (unsigned)mrow[rowq[4 * c + b]] << (8 * b);
+                    *(unsigned *)(dst + (size_t)a * LSTRIDE + 4 * c) = w;
+                }
+            }
+        }
+
+        // ---- boundaries ------------------------------------------------------------------------------------
+        unsigned T[K], E[K], T2[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int il = lg * K + k;
+            const int ia = il - padA, ib = il - padB;
+            const int la = (ia < 0 || left_free) ? 0 : -o - ia * e;
+            const int lb = (ib < 0 || left_free) ? 0 : -o - ib * e;
+            T[k] = p16_pack(la - o, lb - o);
+            E[k] = T[k];
+            T2[k] = T[k];
+        }
+        unsigned Tdiag_in;
+        {
+            const int il = lg * K - 1;   // the row above this lane's first row (lane 0: the corner)
+            const int ia = il - padA, ib = il - padB;
+            const int la = (il < 0 || ia < 0 || left_free) ? 0 : -o - ia * e;
+            const int lb = (il < 0 || ib < 0 || left_free) ? 0 : -o - ib * e;
+            Tdiag_in = p16_pack(la - o, lb - o);
+        }
+        unsigned Tout = Tdiag_in, Fout = 0, Xout = 0;
+        // local: per half, a column maximum must exceed `thr` to matter (see kern_sw16.cuh)
+        unsigned thr = 0, best = 0, bestj = 0;
+        // global / semi-global candidates, kept in T space (T = H - o)
+        unsigned rbest = 0x80008000u, rbestj = 0;      // last row, first maximum (lane G-1 only)
+        int colTa = -32768, colTb = -32768, colIa = 0, colIb = 0;   // last column
+        int cornTa = -32768, cornTb = -32768;          // (Lq-1, Lr-1), lane G-1 only
+        sync_warp();
+        if (SW && lg == 0) *gpub = 0;
+        const long long tr_base = TRACE ? p.trace_off[item] : 0;
+
+        for (int s0 = 0; s0 < nsteps; s0 += 32) {
+            sync_warp();
+            // stage the next 32 columns of both references as profile byte offsets
+#pragma unroll
+            for (int u = 0; u < NG; ++u) {
+                const int c = s0 + lg + u * G;
+                const unsigned ca = c < LrA ? (unsigned)p.r[roA + c] : (unsigned)pad_code;
+                const unsigned cb = c < LrB ? (unsigned)p.r[roB + c] : (unsigned)pad_code;
+                ring[c & 63] = (ca * LSTRIDE) | ((cb * LSTRIDE) << 16);
+            }
+            sync_warp();
+            const int send = (s0 + 32 < nsteps) ? s0 + 32 : nsteps;
+            auto step = [&](const int s, unsigned (&Tin)[K], unsigned (&Tnew)[K]) {
+                const int j = s - lg;
+                unsigned Tup = shfl_up(Tout, 1);
+                unsigned Fup = shfl_up(Fout, 1);
+                unsigned Xup = 0;
+                if (TRACE) Xup = shfl_up(Xout, 1);
+                if (lg == 0) {
+                    const int hb = top_free ? 0 : -o - j * e;     // H[-1][j]
+                    Tup = p16_pack(hb - o, hb - o);
+                    Fup = p16_pack(hb, hb);                        // Fh = F + o with F[0][j] = H[-1][j] - o: opened
+                    Xup = 0;
+                }
+                if (j >= 0 && j < Lmax) {
+                    const unsigned w = ring[j & 63];
+                    const unsigned char *pa = pa_base + (w & 0xffffu);
+                    const unsigned char *pb = pb_base + (w >> 16);
+                    unsigned wa[NW4], wb[NW4];
+#pragma unroll
+                    for (int c = 0; c < NW4; ++c) { wa[c] = *(const unsigned *)(pa + 4 * c); wb[c] = *(const unsigned *)(pb + 4 * c); }
+                    unsigned Td = Tdiag_in, Fu = Fup;
+                    unsigned cmax = 0, hprev = 0;
+                    unsigned accEF[TW / 2], accDX[TW / 2];
+                    unsigned sFin = Xup;
+                    if (TRACE) {
+#pragma unroll
+                        for (int x = 0; x < TW / 2; ++x) { accEF[x] = 0; accDX[x] = 0; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const unsigned So = prmt(wa[k >> 2], wb[k >> 2], 0xC480u + (unsigned)(k & 3) * 0x1111u);
+                        const unsigned Tl = Tin[k];
+                        unsigned Hn, Tn, En, Fn;
+                        if (!TRACE) {
+                            En = viaddmax2(E[k], NEGE, Tl);
+                            const unsigned h = viaddmax2(Td, So, En);
+                            Hn = SW ? viaddmax2_relu(Fu, NEGO, h) : viaddmax2(Fu, NEGO, h);
+                            Fn = viaddmax2(Fu, NEGE, h);
+                            Tn = vadd2(Hn, NEGO);
+                        } else {
+                            const unsigned Eext = vadd2(E[k], NEGE);
+                            En = vimax2(Eext, Tl);
+                            const unsigned hd = vadd2(Td, So);
+                            const unsigned h = vimax2(hd, En);
+                            const unsigned Fext = vadd2(Fu, NEGE);
+                            Fn = vimax2(Fext, h);
+                            const unsigned Fv = vadd2(Fu, NEGO);          // F of this cell
+                            Hn = SW ? vimax2_relu(h, Fv) : vimax2(h, Fv);
+                            Tn = vadd2(Hn, NEGO);
+                            // decisions from sign bits: sign(a + ~b) is set  <=>  a <= b   (rules: psb_defs.h)
+                            const unsigned sE = vadd2(Tl, ~Eext);           // E extends (opening is not strictly better)
+                            const unsigned sD = vadd2(Hn, ~hd);             // the diagonal is the maximum (diag wins ties)
+                            const unsigned sG = vadd2(En, ~Fv);             // F >= E (F wins ties over E)
+                            const unsigned rowbit = 0x01010101u << (k & 7);
+                            accEF[k >> 3] |= prmt(sE, sFin, 0xFDB9u) & rowbit;
+                            accDX[k >> 3] |= prmt(sD, sG, 0xFDB9u) & rowbit;
+                            sFin = vadd2(h, ~Fext);                          // for the row below: F extends
+                        }
+                        if (SW) {
+                            if (k & 1) cmax = vimax3_2(cmax, hprev, Hn);
+                            else hprev = Hn;
+                        }
+                        Td = Tl; Tnew[k] = Tn; E[k] = En; Fu = Fn;
+                    }
+                    if (SW && (K & 1)) cmax = vimax2(cmax, hprev);
+                    Tdiag_in = Tup; Tout = Tnew[K - 1]; Fout = Fu;
+                    if (TRACE) {
+                        Xout = sFin;
+                        unsigned *dst = p.trace + tr_base + ((long long)s * G + lg) * TW;
+                        if (TW % 4 == 0) {
+#pragma unroll
+                            for (int x = 0; x < TW / 4; ++x) {
+                                uint4 v; v.x = accEF[2 * x]; v.y = accDX[2 * x]; v.z = accEF[2 * x + 1]; v.w = accDX[2 * x + 1];
+                                st_cg((uint4 *)dst + x, v);
+                            }
+                        } else {
+#pragma unroll
+                            for (int x = 0; x < TW / 2; ++x) {
+                                uint2 v; v.x = accEF[x]; v.y = accDX[x];
+                                st_cg((uint2 *)dst + x, v);
+                            }
+                        }
+                    }
+                    if (SW) {
+                        thr = vimax2(thr, *gpub);
+                        const unsigned m = vimax2(thr, cmax);
+                        if (m != thr) {
+                            // cold: a half beat the threshold -- record score and column, park the column of T values
+                            const unsigned diff = m ^ thr;
+                            const unsigned mask = ((diff & 0xffffu) ? 0xffffu : 0u) | ((diff >> 16) ? 0xffff0000u : 0u);
+                            best = (best & ~mask) | (cmax & mask);
+                            bestj = (bestj & ~mask) | (((unsigned)j * 0x10001u) & mask);
+                            thr = m;
+#pragma unroll
+                            for (int c4 = 0; c4 < NW4; ++c4) {
+                                uint4 v;
+                                v.x = Tnew[4 * c4];
+                                v.y = 4 * c4 + 1 < K ? Tnew[4 * c4 + 1] : 0u;
+                                v.z = 4 * c4 + 2 < K ? Tnew[4 * c4 + 2] : 0u;
+                                v.w = 4 * c4 + 3 < K ? Tnew[4 * c4 + 3] : 0u;
+                                if (mask & 0xffffu) park[(0 * NW4 + c4) * 32 + lane] = v;
+                                if (mask >> 16) park[(1 * NW4 + c4) * 32 + lane] = v;
+                            }
+                            const unsigned pub = vimax2(*gpub, vimax2(best, 0x00010001u) - 0x00010001u);
+                            *gpub = pub;
+                        }
+                    } else {
+                        if (row_ends && lg == G - 1) {
+                            // last row, left to right, the first maximum wins (strict >), real columns only
+                            const unsigned m = vimax2(rbest, Tout);
+                            if (m != rbest) {
+                                const unsigned diff = m ^ rbest;
+                                unsigned mask = ((diff & 0xffffu) ? 0xffffu : 0u) | ((diff >> 16) ? 0xffff0000u : 0u);
+                                mask &= (j < LrA ? 0xffffu : 0u) | (j < LrB ? 0xffff0000u : 0u);
+                                rbest = (rbest & ~mask) | (Tout & mask);
+                                rbestj = (rbestj & ~mask) | (((unsigned)j * 0x10001u) & mask);
+                            }
+                        }
+                        if (j == LrA - 1 || j == LrB - 1) {
+                            // cold: the last column of a half (top to bottom, strict >) and its corner cell
+                            const bool atA = j == LrA - 1, atB = j == LrB - 1;
+                            if (col_ends) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k) {
+                                    const int il = lg * K + k;
+                                    const int ta = p16_lo(Tnew[k]), tb = p16_hi(Tnew[k]);
+                                    if (atA && il >= padA && ta > colTa) { colTa = ta; colIa = il - padA; }
+                                    if (atB && il >= padB && tb > colTb) { colTb = tb; colIb = il - padB; }
+                                }
+                            }
+                            if (lg == G - 1) {
+                                if (atA) cornTa = p16_lo(Tout);
+                                if (atB) cornTb = p16_hi(Tout);
+                            }
+                        }
+                    }
+                }
+            };
+            // ping-pong column copies (even steps read T and write T2, odd steps the reverse); a chunk starts
+            // on an even step and a trailing odd step past the end has no active lane
+            for (int s = s0; s < send; s += 2) {
+                step(s, T, T2);
+                step(s + 1, T2, T);
+            }
+        }
+
+        // ---- results ---------------------------------------------------------------------------------------
+        sync_warp();
+        if (SW) {
+            unsigned long long comps[2];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const unsigned sc = half ? (best >> 16) : (best & 0xffffu);
+                const unsigned col = half ? (bestj >> 16) : (bestj & 0xffffu);
+                unsigned rowk = 0;
+                if (sc != 0) {
+                    const unsigned *pk = (const unsigned *)park;
+                    const unsigned want = (sc - (unsigned)o) & 0xffffu;   // the parked words hold T = H - o
+                    for (int k = K - 1; k >= 0; --k) {
+                        const unsigned wv = pk[(((half * NW4 + (k >> 2)) * 32 + lane) << 2) + (k & 3)];
+                        if ((half ? (wv >> 16) : (wv & 0xffffu)) == want) rowk = (unsigned)k;
+                    }
+                }
+                const unsigned row = (unsigned)(lg * K) + rowk;
+                // score | inverted column | inverted row: the maximum is (score, smaller end_ref, smaller end_query)
+                unsigned long long comp = ((unsigned long long)sc << 26) | ((unsigned long long)(0xffffu - col) << 10) |
+                                          (unsigned long long)(1023u - row);
+#pragma unroll
+                for (int m = G / 2; m >= 1; m >>= 1) {
+                    const unsigned long long other = (unsigned long long)shfl_xor((long long)comp, m);
+                    comp = other > comp ? other : comp;
+                }
+                comps[half] = comp;
+            }
+            if (lg == 0 && item_ok) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (half && !hasB) continue;
+                    const int pid = half ? pidB : pidA;
+                    const unsigned long long comp = comps[half];
+                    const int sc = (int)(comp >> 26);
+                    if (sc == 0) { p.score[pid] = 0; p.end_query[pid] = 0; p.end_ref[pid] = 0; }
+                    else {
+                        p.score[pid] = sc;
+                        p.end_ref[pid] = (int)(0xffffu - (unsigned)((comp >> 10) & 0xffffu));
+                        p.end_query[pid] = 1023 - (int)(comp & 1023u) - (half ? padB : padA);
+                    }
+                }
+            }
+        } else {
+            // last row / corner live in lane G-1; the last column is spread over the lanes
+            const int src = grp * G + (G - 1);
+            const unsigned rb = shfl(rbest, src), rbj = shfl(rbestj, src);
+            const int cta = shfl(cornTa, src), ctb = shfl(cornTb, src);
+            if (col_ends) {
+#pragma unroll
+                for (int m = G / 2; m >= 1; m >>= 1) {
+                    const int ta = shfl_xor(colTa, m), ia = shfl_xor(colIa, m), tb = shfl_xor(colTb, m), ib = shfl_xor(colIb, m);
+                    if (ta > colTa || (ta == colTa && ia < colIa)) { colTa = ta; colIa = ia; }
+                    if (tb > colTb || (tb == colTb && ib < colIb)) { colTb = tb; colIb = ib; }
+                }
+            }
+            if (lg == 0 && item_ok) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (half && !hasB) continue;
+                    const int pid = half ? pidB : pidA;
+                    const int Lq = half ? LqB : LqA, Lr = half ? LrB : LrA;
+                    int bT, bJ, bI = Lq - 1;
+                    if (row_ends) { bT = half ? p16_hi(rb) : p16_lo(rb); bJ = (int)(half ? (rbj >> 16) : (rbj & 0xffffu)); }
+                    else { bT = col_ends ? -32768 : (half ? ctb : cta); bJ = Lr - 1; }
+                    const int cT = half ? colTb : colTa, cI = half ? colIb : colIa;
+                    // the last column beats the last row only when strictly better (rules::SG_COL_WINS_TIE)
+                    if (col_ends && (!row_ends || cT > bT)) { bT = cT; bJ = Lr - 1; bI = cI; }
+                    p.score[pid] = bT + o; p.end_query[pid] = bI; p.end_ref[pid] = bJ;
+                }
+            }
+        }
+    }
+}
+
+// ---- walk over the decision bits ---------------------------------------------------------------
+// One thread per pair.  CIGAR mode writes the run-length list in reverse into the pair's scratch region
+// (compact_cigar_kernel reverses it into the CSR); STATS mode counts (matches, similar, length) of the path.
+struct Walk16Params {
+    const uint8_t *q;
+    const long long *q_off;
+    const uint8_t *r;
+    const long long *r_off;
+    int shared_query;
+    const int *pair_ids;         // pairs of this launch
+    const int *pair_slot;        // per pair id: item * 2 + half
+    int n;
+    int G, K;
+    const unsigned *trace;
+    const long long *trace_off;  // per item
+    const int *matrix;           // size x size substitution scores (no open added)
+    int size;
+    int open, gap;
+    int is_sw;
+    const int *score, *end_query, *end_ref;   // per pair id
+    // CIGAR outputs (walk16_kernel<false>)
+    unsigned *rev_ops;
+    const long long *rev_off;
+    int *nops, *beg_query, *beg_ref;
+    // statistics outputs (walk16_kernel<true>)
+    int *matches, *similar, *length;
+};
+
+template <bool STATS>
+PSB_KERNEL void walk16_kernel(Walk16Params p) {
+    const long long tid = (long long)block_id() * threads_per_block() + thread_in_block();
+    if (tid >= p.n) return;
+    const int pid = p.pair_ids[tid];
+    const int slot = p.pair_slot[pid];
+    const int item = slot >> 1, half = slot & 1;
+    const long long qo = p.shared_query ? p.q_off[0] : p.q_off[pid];
+    const int Lq = (int)((p.shared_query ? p.q_off[1] : p.q_off[pid + 1]) - qo);
+    const uint8_t *q = p.q + qo;
+    const uint8_t *r = p.r + p.r_off[pid];
+    const int G = p.G, K = p.K, TW = 2 * ((K + 7) / 8);
+    const int pad = G * K - Lq;
+    const unsigned *tr = p.trace + p.trace_off[item];
+    unsigned *out = STATS ? nullptr : p.rev_ops + p.rev_off[pid];
+    int i = p.end_query[pid], j = p.end_ref[pid];
+    int v = p.score[pid];            // local alignment: the value of the state we are in
+    int state = 0;                   // 0 = H, 1 = E (horizontal, consumes reference), 2 = F (vertical, consumes query)
+    int cur = -1, n = 0;
+    unsigned len = 0;
+    int nm = 0, ns = 0, nl = 0;
+    while (i >= 0 || j >= 0) {
+        int op;
+        if (i < 0 || j < 0) {
+            // off the table: statistics stop here (boundary gaps are not counted); the CIGAR takes the rest
+            // of the other sequence as one run (rules::CIGAR_WALK_TO_ORIGIN)
+            if (STATS) break;
+            if (i < 0) { op = (int)rules::CIGAR_OP_D; --j; }
+            else { op = (int)rules::CIGAR_OP_I; --i; }
+        } else {
+            if (state == 0 && p.is_sw && v <= 0) break;   // ZERO: the alignment starts after this cell
+            const int il = i + pad, t = il / K, k = il - t * K;
+            const unsigned *w = tr + ((long long)(j + t) * G + t) * TW + 2 * (k >> 3);
+            const int bit = (k & 7) + 8 * half;
+            if (state == 0) {
+                const unsigned dx = w[1];
+                if ((dx >> bit) & 1u) {
+                    const int a = q[i], b = r[j];
+                    const int sub = p.matrix[a * p.size + b];
+                    op = (a == b) ? (int)rules::CIGAR_OP_EQ : (int)rules::CIGAR_OP_X;
+                    nm += (a == b); ns += (sub > 0);
+                    v -= sub; --i; --j;
+                } else {
+                    state = ((dx >> (bit + 16)) & 1u) ? 2 : 1;   // F >= E: vertical, else horizontal
+                    continue;
+                }
+            } else if (state == 1) {
+                op = (int)rules::CIGAR_OP_D;
+                if ((w[0] >> bit) & 1u) v += p.gap; else { v += p.open; state = 0; }
+                --j;
+            } else {
+                op = (int)rules::CIGAR_OP_I;
+                if ((w[0] >> (bit + 16)) & 1u) v += p.gap; else { v += p.open; state = 0; }
+                --i;
+            }
+        }
+        ++nl;
+        if (!STATS) {
+            if (op == cur) ++len;
+            else {
+                if (cur >= 0) out[n++] = (len << 4) | (unsigned)cur;
+                cur = op; len = 1;
+            }
+        }
+    }
+    if (STATS) {
+        p.matches[pid] = nm; p.similar[pid] = ns; p.length[pid] = nl;
+    } else {
+        if (cur >= 0) out[n++] = (len << 4) | (unsigned)cur;
+        p.nops[pid] = n;
+        p.beg_query[pid] = i + 1;
+        p.beg_ref[pid] = j + 1;
+    }
+}
+
+}  // namespace psb

@@ -47,6 +47,18 @@ static constexpr int SW16_G = 16;  // lanes per group
 #ifndef SW16_PROF32
 #define SW16_PROF32 1
 #endif
+// SW16_DECOUPLE=1: the recurrence is kept in true (unshifted) space with the vertical gap carried as
+// Fh = F + open, so that the only loop-carried dependency between the rows of a lane is ONE instruction:
+//    E  = max(E - e, Tleft)            Tleft = H[i][j-1] - o
+//    h  = max(Tdiag + (S+o), E)        = max(H[i-1][j-1] + S, E)
+//    H  = max(Fh - o, h, 0)            VIADDMNMX.S16x2.RELU
+//    Fh'= max(Fh - e, h)               the chain; equals max(Fh - e, H) wherever it can matter (needs o >= e)
+//    T  = H - o                        VIADD.16x2, off the chain
+// (4 DPX + 1 packed add per two cells, as before, but the X -> T -> F' chain of three dependent
+// instructions per row becomes one, so a warp needs far fewer partners to keep its scheduler busy.)
+#ifndef SW16_DECOUPLE
+#define SW16_DECOUPLE 1
+#endif
 // rows of one letter that one LDS.128 fetches for a lane
 static constexpr int SW16_ROWS_PER_LOAD = SW16_PROF32 ? 4 : 16;
 inline constexpr int sw16_chunks(int K) { return (K + SW16_ROWS_PER_LOAD - 1) / SW16_ROWS_PER_LOAD; }
@@ -69,6 +81,7 @@ inline int sw16_pick_k(int lq) {
     return 0;
 }
 inline bool sw16_supported(const Sw16Profile &p, int open, int gap) {
+    if (SW16_DECOUPLE && open < gap) return false;
     return p.K > 0 && open >= 0 && gap >= 0 && gap <= 4096 && open + p.max_score <= 127 && open + p.min_score >= -127;
 }
 inline size_t sw16_letter_stride(int chunks) { return (size_t)chunks * SW16_G * 16; }
@@ -189,8 +202,11 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
     const int pad_code = p.nletters - 1;
     const unsigned O2 = (unsigned)p.open * 0x10001u;
     const unsigned NEGE = ((unsigned)(-p.gap) & 0xffffu) * 0x10001u;
-    const unsigned NEGO = 0u - O2;
+    const unsigned NEGO = SW16_DECOUPLE ? ((unsigned)(-p.open) & 0xffffu) * 0x10001u   // (-o, -o) as two halves
+                                        : 0u - O2;                                       // 32-bit -(o, o): X - o never borrows
+    (void)O2;
     const unsigned one = p.mul_one;
+    (void)one;
     const unsigned m64k = p.mul_64k;
     (void)m64k;
     const long long nitems = (p.n + 1) >> 1;
@@ -211,15 +227,17 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
         const int Lother = shfl_xor(Lmax, 16);
         const int nsteps = (Lmax > Lother ? Lmax : Lother) + G - 1;  // warp-uniform
 
+        // boundary values of a local alignment: H = 0, so T = H - o (decoupled form) or T = H (shifted form)
+        const unsigned TB = SW16_DECOUPLE ? NEGO : 0u;
         unsigned T[K], E[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) { T[k] = 0; E[k] = 0; }
+        for (int k = 0; k < K; ++k) { T[k] = TB; E[k] = TB; }
 #if SW16_PINGPONG
         unsigned T2[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) T2[k] = 0;
+        for (int k = 0; k < K; ++k) T2[k] = TB;
 #endif
-        unsigned Tdiag_in = 0, Tout = 0, Fout = 0;
+        unsigned Tdiag_in = TB, Tout = TB, Fout = 0;
         unsigned thr = 0;                     // per half: a column maximum must exceed this to matter
         unsigned best = 0, bestj = 0;         // per half: own best score and its column
         sync_warp();
@@ -243,7 +261,7 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                 const int j = s - lg;
                 unsigned Tup = shfl_up(Tout, 1);
                 unsigned Fup = shfl_up(Fout, 1);
-                if (lg == 0) { Tup = 0; Fup = 0; }
+                if (lg == 0) { Tup = TB; Fup = 0; }
                 if (j >= 0 && j < Lmax) {
                     const unsigned w = ring[j & 63];
                     const unsigned char *pa = lane_base + (w & 0xffffu);
@@ -269,12 +287,21 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
 #endif
                         const unsigned Tl = Tin[k];
                         const unsigned En = viaddmax2(E[k], NEGE, Tl);
+#if SW16_DECOUPLE
+                        const unsigned h = viaddmax2(Td, So, En);
+                        const unsigned Hn = viaddmax2_relu(Fu, NEGO, h);
+                        const unsigned Fn = viaddmax2(Fu, NEGE, h);
+                        const unsigned Tn = vadd2(Hn, NEGO);
+                        if (k & 1) cmax = vimax3_2(cmax, tprev, Hn);
+                        else tprev = Hn;
+#else
                         const unsigned Fn = viaddmax2(Fu, NEGE, Tu);
                         const unsigned h = viaddmax2(Td, So, En);
                         const unsigned X = vimax3_2(h, Fn, O2);
                         const unsigned Tn = X * one + NEGO;
                         if (k & 1) cmax = vimax3_2(cmax, tprev, Tn);
                         else tprev = Tn;
+#endif
                         Td = Tl; Tnew[k] = Tn; E[k] = En; Tu = Tn; Fu = Fn;
                     }
                     if (K & 1) cmax = vimax2(cmax, tprev);
@@ -330,9 +357,11 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
             unsigned rowk = 0;
             if (sc != 0) {
                 const unsigned *pk = (const unsigned *)park;
+                // the parked words hold T: H itself (shifted form) or H - o (decoupled form)
+                const unsigned want = SW16_DECOUPLE ? ((sc - (unsigned)p.open) & 0xffffu) : sc;
                 for (int k = K - 1; k >= 0; --k) {
                     const unsigned wv = pk[(((half * (PARKW / 4) + (k >> 2)) * 32 + lane) << 2) + (k & 3)];
-                    if ((half ? (wv >> 16) : (wv & 0xffffu)) == sc) rowk = (unsigned)k;
+                    if ((half ? (wv >> 16) : (wv & 0xffffu)) == want) rowk = (unsigned)k;
                 }
             }
             const unsigned row = (unsigned)(lg * K) + rowk;

@@ -18,6 +18,7 @@ struct FnConfig {
     int strategy = 0;  // 0 striped, 1 scan, 2 diag: echoed in the result flags only
     bool profile = false;
     int width = 0;  // 8, 16, 32, 64, or 0 for "sat"
+    int band = 0;   // parasail_nw_banded only: half-width of the diagonal band (0 = full table)
     int flag() const;
 };
 // true iff `name` (with or without "parasail_") is a function upstream parasail defines
@@ -83,6 +84,10 @@ struct PairsRequest {
 int run_pairs(const PairsRequest &req, psb_batch_t **out);
 void free_batch(psb_batch_t *b);
 void release_profile_resident(parasail_profile *p);
+
+// true when an explicit _8/_16 request cannot hold this pair's values; the one rule every
+// entry point (single pair, psb_align_pairs, psb_scan, psb_scan_host) applies
+bool saturates(const FnConfig &cfg, const HostMatrix &m, int score, int qlen, int rlen, int open, int gap);
 
 // one pair through the batch path, wrapped as a parasail_result_t (never NULL)
 parasail_result_t *align_one(const FnConfig &cfg, const HostMatrix &m, const uint8_t *q, int qlen, const uint8_t *r,

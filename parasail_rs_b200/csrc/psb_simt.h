@@ -38,8 +38,12 @@ PSB_DEV int viaddmax(int a, int b, int c) { return __viaddmax_s32(a, b, c); }   
 PSB_DEV int viaddmax_relu(int a, int b, int c) { return __viaddmax_s32_relu(a, b, c); }  // max(a+b, c, 0)
 PSB_DEV int vimax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 PSB_DEV unsigned viaddmax2(unsigned a, unsigned b, unsigned c) { return __viaddmax_s16x2(a, b, c); }
+PSB_DEV unsigned viaddmax2_relu(unsigned a, unsigned b, unsigned c) { return __viaddmax_s16x2_relu(a, b, c); }
 PSB_DEV unsigned vimax3_2(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
 PSB_DEV unsigned vimax2(unsigned a, unsigned b) { return __vmaxs2(a, b); }
+PSB_DEV unsigned vimax2_relu(unsigned a, unsigned b) { return __vimax_s16x2_relu(a, b); }   // max(a, b, 0) per half
+PSB_DEV void st_cg(uint4 *p, uint4 v) { __stcg(p, v); }
+PSB_DEV void st_cg(uint2 *p, uint2 v) { __stcg(p, v); }
 PSB_DEV unsigned vadd2(unsigned a, unsigned b) { return __vadd2(a, b); }
 // prmt.b32 with the sign-replicate selector bit (the __byte_perm intrinsic masks it off)
 PSB_DEV unsigned prmt(unsigned a, unsigned b, unsigned sel) {
@@ -62,6 +66,7 @@ PSB_DEV unsigned prmt(unsigned a, unsigned b, unsigned sel) {
 #define PSB_SHARED_DECL(name) unsigned char *name = psb::emu::tls().smem
 
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
 namespace psb {
 namespace emu {
 struct Block {
@@ -141,6 +146,11 @@ inline unsigned viaddmax2(unsigned a, unsigned b, unsigned c) {
     int h = std::max((int)(int16_t)(hi16(a) + hi16(b)), (int)hi16(c));
     return pack16(l, h);
 }
+inline unsigned viaddmax2_relu(unsigned a, unsigned b, unsigned c) {
+    int l = std::max(std::max((int)(int16_t)(lo16(a) + lo16(b)), (int)lo16(c)), 0);
+    int h = std::max(std::max((int)(int16_t)(hi16(a) + hi16(b)), (int)hi16(c)), 0);
+    return pack16(l, h);
+}
 inline unsigned vimax3_2(unsigned a, unsigned b, unsigned c) {
     return pack16(std::max((int)lo16(a), std::max((int)lo16(b), (int)lo16(c))),
                   std::max((int)hi16(a), std::max((int)hi16(b), (int)hi16(c))));
@@ -149,6 +159,11 @@ inline unsigned vimax2(unsigned a, unsigned b) {
     return pack16(std::max((int)lo16(a), (int)lo16(b)), std::max((int)hi16(a), (int)hi16(b)));
 }
 inline unsigned vadd2(unsigned a, unsigned b) { return pack16(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
+inline unsigned vimax2_relu(unsigned a, unsigned b) {
+    return pack16(std::max(std::max((int)lo16(a), (int)lo16(b)), 0), std::max(std::max((int)hi16(a), (int)hi16(b)), 0));
+}
+inline void st_cg(uint4 *p, uint4 v) { *p = v; }
+inline void st_cg(uint2 *p, uint2 v) { *p = v; }
 inline unsigned prmt(unsigned a, unsigned b, unsigned sel) {
     unsigned long long src = ((unsigned long long)b << 32) | a;
     unsigned d = 0;

@@ -16,7 +16,7 @@ void set_error(const std::string &msg) { g_error = msg; }
 
 // an explicit 8/16-bit request whose true optimum does not fit that width is
 // reported saturated (score/ends zeroed); "sat" and 32/64 return the exact result.
-static bool saturates(const FnConfig &cfg, const HostMatrix &m, int score, int qlen, int rlen, int open, int gap) {
+bool saturates(const FnConfig &cfg, const HostMatrix &m, int score, int qlen, int rlen, int open, int gap) {
     if (cfg.width != 8 && cfg.width != 16) return false;
     const long long hi = cfg.width == 8 ? 127 : 32767, lo = -hi - 1;
     if ((long long)score + std::max(m.max, 0) > hi) return true;
@@ -240,12 +240,15 @@ void parasail_traceback_generic(const char *seqA, int lena, const char *seqB, in
     parasail_traceback_free(tb);
 }
 
-// ---- side APIs outside the accelerated path ----------------------------
+// ---- side APIs ----------------------------------------------------------------
+// [REF src/aligner/mod.rs:457-489] banded global alignment: the fill is restricted to the diagonal band
+// of half-width k (widened by the length difference so that the corner stays reachable); cells outside
+// the band are unreachable (-inf).  Runs on the GPU through the general kernel's band mask.
 parasail_result_t *parasail_nw_banded(const char *s1, int s1Len, const char *s2, int s2Len, int open, int gap, int k,
                                       const parasail_matrix_t *matrix) {
-    (void)k;  // the band only prunes work upstream; the full fill is its k = max(len) limit
     psb::FnConfig cfg;
     cfg.mode = 0; cfg.width = 32; cfg.strategy = 0;
+    cfg.band = k > 0 ? k : 0;
     psb::HostMatrix hm;
     if (matrix) hm = psb::HostMatrix(matrix);
     parasail_result_t *r = psb::align_one(cfg, hm, (const uint8_t *)s1, s1Len, (const uint8_t *)s2, s2Len, open, gap);
@@ -254,13 +257,36 @@ parasail_result_t *parasail_nw_banded(const char *s1, int s1Len, const char *s2,
     return r;
 }
 
-parasail_result_ssw_t *parasail_ssw(const char *, int, const char *, int, int, int, const parasail_matrix_t *) {
-    psb::set_error("parasail_ssw: the SSW emulation is outside the accelerated path (not implemented)");
-    return nullptr;
+// [REF src/aligner/mod.rs:491-529; src/alignment/mod.rs:507-551] the SSW-compatible call: a local
+// alignment with traceback, reported as score + begin/end coordinates + BAM-style CIGAR words.  The fill,
+// the walk and the begin coordinates all come from the GPU trace path (sw_trace).  Never NULL: the
+// reference dereferences the pointer unconditionally; a failed call returns a zeroed result.
+parasail_result_ssw_t *parasail_ssw(const char *s1, int s1Len, const char *s2, int s2Len, int open, int gap,
+                                    const parasail_matrix_t *matrix) {
+    parasail_result_ssw_t *out = (parasail_result_ssw_t *)std::calloc(1, sizeof(parasail_result_ssw_t));
+    if (!out) std::abort();
+    if (!matrix || !s1 || !s2 || s1Len <= 0 || s2Len <= 0) { psb::set_error("parasail_ssw: empty sequence or NULL matrix"); return out; }
+    psb::FnConfig cfg;
+    cfg.mode = 2; cfg.trace = true; cfg.width = 0; cfg.strategy = 0;
+    psb::HostMatrix hm(matrix);
+    parasail_result_t *r = psb::align_one(cfg, hm, (const uint8_t *)s1, s1Len, (const uint8_t *)s2, s2Len, open, gap);
+    if (!(r->flag & PARASAIL_FLAG_SATURATED) && r->extra) {
+        out->score1 = (uint16_t)std::min(std::max(r->score, 0), 65535);
+        out->ref_end1 = r->end_ref; out->read_end1 = r->end_query;
+        out->ref_begin1 = r->extra->beg_ref; out->read_begin1 = r->extra->beg_query;
+        const std::vector<uint32_t> &ops = r->extra->cigar_ops;
+        out->cigarLen = (int32_t)ops.size();
+        out->cigar = (uint32_t *)std::malloc(sizeof(uint32_t) * std::max<size_t>(ops.size(), 1));
+        if (out->cigar && !ops.empty()) std::memcpy(out->cigar, ops.data(), sizeof(uint32_t) * ops.size());
+    }
+    parasail_result_free(r);
+    return out;
 }
-parasail_profile_t *parasail_ssw_init(const char *, int, const parasail_matrix_t *, int8_t) {
-    psb::set_error("parasail_ssw_init: the SSW emulation is outside the accelerated path (not implemented)");
-    return nullptr;
+// [REF src/profile/mod.rs:337-358] score_size 0 / 1 / 2 = 8 bit / 16 bit / both upstream; every width is the
+// same resident profile here (the kernels pick their own width and re-run on overflow)
+parasail_profile_t *parasail_ssw_init(const char *s1, int s1Len, const parasail_matrix_t *matrix, int8_t score_size) {
+    (void)score_size;
+    return parasail_profile_create_sat(s1, s1Len, matrix);
 }
 void parasail_result_ssw_free(parasail_result_ssw_t *r) {
     if (!r) return;

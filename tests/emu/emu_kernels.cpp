@@ -98,3 +98,71 @@ extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams 
 }
 extern "C" int emu_sizeof_wave32() { return (int)sizeof(Wave32Params); }
 extern "C" int emu_sizeof_wavereduce() { return (int)sizeof(WaveReduceParams); }
+
+// ---- packed 16-bit many-pairs kernel + walk -------------------------------------------------------------
+#include "../../parasail_rs_b200/csrc/kern_pairs16.cuh"
+
+template <int G, int K> static void run_p16(const Pairs16Params &p, bool sw, bool trace, int nblocks, size_t smem) {
+    if (sw && trace) emu::launch(nblocks, smem, [&]() { pairs16_kernel<G, K, true, true>(p); });
+    else if (sw) emu::launch(nblocks, smem, [&]() { pairs16_kernel<G, K, true, false>(p); });
+    else if (trace) emu::launch(nblocks, smem, [&]() { pairs16_kernel<G, K, false, true>(p); });
+    else emu::launch(nblocks, smem, [&]() { pairs16_kernel<G, K, false, false>(p); });
+}
+
+// pairs are taken two at a time in the given order; q / r are already mapped to matrix indices.
+// what: 0 = score only, 1 = trace + CIGAR walk (rev_ops: per pair region of lq+lr+2 words, reversed run list),
+// 2 = trace + statistics walk.  Returns 0, -1 for an unsupported class, -2 when a pair does not fit 16 bit.
+extern "C" int emu_pairs16(int G, int K, int mode, int s1_beg, int s1_end, int s2_beg, int s2_end, int what, int n,
+                           const uint8_t *q, const long long *q_off, const uint8_t *r, const long long *r_off,
+                           const int *table, int size, int mat_min, int mat_max, int open, int gap, int nblocks,
+                           int *score, int *end_query, int *end_ref, int *matches, int *similar, int *length,
+                           unsigned *rev_ops, const long long *rev_off, int *nops, int *beg_query, int *beg_ref) {
+    const bool sw = mode == MODE_SW, trace = what != 0;
+    if (!pairs16_scheme_ok(size, mat_min, mat_max, open, gap, false)) return -2;
+    std::vector<int> items;
+    for (int i = 0; i < n; i += 2) { items.push_back(i); items.push_back(i + 1 < n ? i + 1 : -1); }
+    const int nitems = (int)items.size() / 2;
+    std::vector<long long> toff(nitems + 1, 0);
+    std::vector<int> slot_of(n);
+    for (int w = 0; w < nitems; ++w) {
+        int lrmax = 0;
+        for (int h = 0; h < 2; ++h) {
+            const int pid = items[2 * w + h];
+            if (pid < 0) continue;
+            const int lq = (int)(q_off[pid + 1] - q_off[pid]), lr = (int)(r_off[pid + 1] - r_off[pid]);
+            if (lq > G * K || !pairs16_fits(G * K, lq, lr, mat_max, mat_min, open, gap, trace)) return -2;
+            lrmax = std::max(lrmax, lr);
+            slot_of[pid] = 2 * w + h;
+        }
+        toff[w + 1] = toff[w] + (trace ? pairs16_item_trace_words(G, K, lrmax) : 0);
+    }
+    std::vector<unsigned> tr((size_t)toff[nitems] + 16, 0xdeadbeefu);
+    std::vector<int8_t> mat8(33 * 32);
+    const bool top_free = sw || (mode == MODE_SG && s1_beg);
+    pairs16_build_mat8(table, size, open, top_free, mat8.data());
+    int counter = 0;
+    Pairs16Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.q = q; p.q_off = q_off; p.r = r; p.r_off = r_off; p.shared_query = 0;
+    p.items = items.data(); p.nitems = nitems; p.mat8 = mat8.data(); p.size = size; p.open = open; p.gap = gap;
+    p.mode = mode; p.s1_beg = s1_beg; p.s1_end = s1_end; p.s2_beg = s2_beg; p.s2_end = s2_end;
+    p.score = score; p.end_query = end_query; p.end_ref = end_ref;
+    p.trace = tr.data(); p.trace_off = toff.data(); p.counter = &counter;
+    const size_t smem = pairs16_smem_bytes(K, size + 1, sw, 1);
+#define PCASE(GG, KK) if (G == GG && K == KK) { run_p16<GG, KK>(p, sw, trace, nblocks, smem); } else
+    PCASE(16, 1) PCASE(16, 3) PCASE(16, 4) PCASE(16, 8) PCASE(16, 10) PCASE(16, 19) PCASE(32, 2) PCASE(32, 9) PCASE(32, 16) { return -1; }
+    if (trace) {
+        std::vector<int> ids(n);
+        for (int i = 0; i < n; ++i) ids[i] = i;
+        Walk16Params w;
+        std::memset(&w, 0, sizeof(w));
+        w.q = q; w.q_off = q_off; w.r = r; w.r_off = r_off; w.pair_ids = ids.data(); w.pair_slot = slot_of.data(); w.n = n;
+        w.G = G; w.K = K; w.trace = tr.data(); w.trace_off = toff.data(); w.matrix = table; w.size = size;
+        w.open = open; w.gap = gap; w.is_sw = sw ? 1 : 0; w.score = score; w.end_query = end_query; w.end_ref = end_ref;
+        w.rev_ops = rev_ops; w.rev_off = rev_off; w.nops = nops; w.beg_query = beg_query; w.beg_ref = beg_ref;
+        w.matches = matches; w.similar = similar; w.length = length;
+        if (what == 2) emu::launch((n + 31) / 32, 64, [&]() { walk16_kernel<true>(w); });
+        else emu::launch((n + 31) / 32, 64, [&]() { walk16_kernel<false>(w); });
+    }
+    return 0;
+}

@@ -33,7 +33,8 @@ class Gotoh32Params(C.Structure):
                 ("bnd_stride", C.c_longlong), ("trace", C.c_void_p), ("trace_off", C.c_void_p),
                 ("counter", C.c_void_p), ("out_map", C.c_void_p), ("tabH", C.c_void_p), ("tabM", C.c_void_p),
                 ("tabS", C.c_void_p), ("tabL", C.c_void_p), ("tab_off", C.c_void_p), ("r_words", C.c_void_p),
-                ("r_word_off", C.c_void_p), ("r_len", C.c_void_p), ("r_bits", C.c_int), ("n_dev", C.c_void_p)]
+                ("r_word_off", C.c_void_p), ("r_len", C.c_void_p), ("r_bits", C.c_int), ("n_dev", C.c_void_p),
+                ("banded", C.c_int), ("band_lo", C.c_int), ("band_hi", C.c_int)]
 
 
 def trace_to_rowmajor(blob, off, K, lq, lr):
@@ -81,7 +82,7 @@ def gotoh32(qs, rs, mat, K, mode, open, gap, flags=(1, 1, 1, 1), stats=False, tr
                       mat.size, int(mat.is_pssm), open, gap, mode, flags[0], flags[1], flags[2], flags[3],
                       ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(outs["matches"]),
                       ptr(outs["similar"]), ptr(outs["length"]), ptr(bnd), per_col * maxlr, ptr(blob),
-                      ptr(trace_off), ptr(counter), None, None, None, None, None, None, None, None, None, 0, None)
+                      ptr(trace_off), ptr(counter), None, None, None, None, None, None, None, None, None, 0, None, 0, 0, 0)
     if packed_bits:
         # subjects from the bit-packed store, in the store's (length-sorted) order; work count from memory
         words, word_off, lens, perm = pack_db(rm, packed_bits)
@@ -221,4 +222,35 @@ def wave32_multi(q, subjects, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nbloc
                           ptr(roff), None, 0)
     rc = lib().emu_wave32(K, C.byref(p), C.byref(rp), nblocks)
     assert rc == 0
+    return outs
+
+
+def pairs16(qs, rs, mat, G, K, mode, open, gap, flags=(1, 1, 1, 1), what=0, nblocks=1):
+    """Run the emulated packed 16-bit many-pairs kernel (csrc/kern_pairs16.cuh), two pairs per word in the
+    given order.  what: 0 score only, 1 trace + CIGAR walk, 2 trace + statistics walk.  Returns a dict of
+    arrays (plus 'cigar_ops' lists in forward order and beg_query / beg_ref for what == 1), or None when
+    the class / 16-bit bound does not admit the batch."""
+    mapper = mat.mapper.astype(np.uint8)
+    qm = [mapper[np.asarray(q, dtype=np.uint8)] for q in qs]
+    rm = [mapper[np.asarray(r, dtype=np.uint8)] for r in rs]
+    n = len(qm)
+    qcat = np.ascontiguousarray(np.concatenate(qm)); rcat = np.ascontiguousarray(np.concatenate(rm))
+    qoff = np.zeros(n + 1, dtype=np.int64); qoff[1:] = np.cumsum([len(x) for x in qm])
+    roff = np.zeros(n + 1, dtype=np.int64); roff[1:] = np.cumsum([len(x) for x in rm])
+    table = np.ascontiguousarray(mat.table, dtype=np.int32)
+    outs = {k: np.full(n, -777, dtype=np.int32) for k in ("score", "end_query", "end_ref", "matches", "similar", "length",
+                                                          "nops", "beg_query", "beg_ref")}
+    rev_off = np.zeros(n + 1, dtype=np.int64); rev_off[1:] = np.cumsum([len(a) + len(b) + 2 for a, b in zip(qm, rm)])
+    rev = np.zeros(int(rev_off[-1]) + 4, dtype=np.uint32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emu_pairs16(G, K, mode, flags[0], flags[1], flags[2], flags[3], what, n, ptr(qcat), ptr(qoff), ptr(rcat),
+                           ptr(roff), ptr(table), mat.size, int(table.min()), int(table.max()), open, gap, nblocks,
+                           ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(outs["matches"]),
+                           ptr(outs["similar"]), ptr(outs["length"]), ptr(rev), ptr(rev_off), ptr(outs["nops"]),
+                           ptr(outs["beg_query"]), ptr(outs["beg_ref"]))
+    if rc == -2:
+        return None
+    assert rc == 0, rc
+    if what == 1:
+        outs["cigar_ops"] = [rev[rev_off[i]: rev_off[i] + outs["nops"][i]][::-1].copy() for i in range(n)]
     return outs

@@ -17,6 +17,9 @@ def seq(seed, idx, n, protein):
 @given(seed=st.integers(1, 10**6), lq=st.integers(1, 420), nsub=st.integers(1, 7), o=st.integers(0, 14), e=st.integers(0, 9),
        protein=st.booleans(), related=st.booleans(), lens=st.lists(st.integers(1, 140), min_size=7, max_size=7))
 def test_sw16_scan_random(oracle, blosum62, seed, lq, nsub, o, e, protein, related, lens):
+    # the packed kernels carry the vertical gap in a one-instruction chain that needs open >= extend; the
+    # engine sends every other penalty pair to the 32-bit kernel (sw16_supported), so the emulation does too
+    e = min(e, o)
     mat = blosum62 if protein else oracle.Matrix.create(b"ACGT", 2, -3)
     q = seq(seed, 0, lq, protein)
     subs = []

@@ -387,3 +387,57 @@ def test_edge_cases(ps, oracle, blosum62):
     assert res.is_saturated()
     res = builder(ps, 2, b62, 10, 1).build().align(q, q)
     assert not res.is_saturated() and res.get_score() > 2000
+
+
+# ---- packed 16-bit many-pairs kernels (csrc/kern_pairs16.cuh) -----------------------------------------
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_pairs16_all_classes_vs_oracle(ps, oracle, blosum62, mode, wide, monkeypatch):
+    # query lengths 1..512 walk through every (G, K) class; ragged lengths share words
+    monkeypatch.setenv("PSB_P16_WIDE", wide)
+    qs, rs = mixed_pairs(201, 240, (1, 513), (1, 400), True)
+    got = builder(ps, mode, ps.Matrix.from_name("blosum62"), 10, 1).build().align_batch(qs, rs)
+    assert_same(got, oracle_batch(oracle, qs, rs, blosum62, mode, 10, 1), KEYS3, f"mode {mode} wide {wide}")
+    got = builder(ps, mode, ps.Matrix.from_name("blosum62"), 10, 1).use_trace().build().align_batch(qs, rs)
+    exp = oracle_batch(oracle, qs, rs, blosum62, mode, 10, 1, cigar=True)
+    assert_same(got, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"), f"trace mode {mode} wide {wide}")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pairs16_stats_by_walk_vs_oracle(ps, oracle, mode):
+    qs, rs = mixed_pairs(202, 300, (1, 400), (1, 600), False)
+    for gaps in ((5, 2), (0, 0), (4, 4)):
+        got = builder(ps, mode, ps.Matrix.create(b"ACGT", 2, -3), *gaps).use_stats().build().align_batch(qs, rs)
+        exp = oracle_batch(oracle, qs, rs, oracle.Matrix.create(b"ACGT", 2, -3), mode, *gaps, stats=True)
+        assert_same(got, exp, KEYS6, f"mode {mode} gaps {gaps}")
+
+
+def test_pairs16_equals_32bit_path(ps, monkeypatch):
+    # the same batch through the packed kernels and (PSB_NO_P16=1) through the 32-bit kernels
+    qs, rs = mixed_pairs(203, 500, (1, 513), (1, 300), True)
+    b62 = ps.Matrix.from_name("blosum62")
+    for mode in (0, 1, 2):
+        for kind in ("score", "stats", "trace"):
+            bl = builder(ps, mode, b62, 11, 1)
+            bl = bl.use_stats() if kind == "stats" else (bl.use_trace() if kind == "trace" else bl)
+            a = bl.build()
+            monkeypatch.delenv("PSB_NO_P16", raising=False)
+            g16 = a.align_batch(qs, rs)
+            monkeypatch.setenv("PSB_NO_P16", "1")
+            g32 = a.align_batch(qs, rs)
+            monkeypatch.delenv("PSB_NO_P16", raising=False)
+            keys = KEYS6 if kind == "stats" else (KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops") if kind == "trace" else KEYS3)
+            for k in keys:
+                assert np.array_equal(getattr(g16, k), getattr(g32, k)), (mode, kind, k)
+
+
+def test_pairs16_sixteen_bit_bound_routes_long_pairs_away(ps, oracle):
+    # +100 matches: 300 matching residues exceed the static 16-bit bound, so these pairs must take the 32-bit path
+    mat, omat = ps.Matrix.create(b"ACGT", 100, -90), oracle.Matrix.create(b"ACGT", 100, -90)
+    qs = [psb_data.random_seq(204, i, 380, protein=False) for i in range(6)]
+    rs = [q.copy() if i % 2 == 0 else psb_data.mutate(q, 204, 10 + i, 0.1, 0.02, protein=False) for i, q in enumerate(qs)]
+    for mode in (0, 2):
+        got = builder(ps, mode, mat, 20, 2).use_stats().build().align_batch(qs, rs)
+        exp = oracle_batch(oracle, qs, rs, omat, mode, 20, 2, stats=True)
+        assert_same(got, exp, KEYS6, f"mode {mode}")
+        assert int(got.score[0]) == 38000

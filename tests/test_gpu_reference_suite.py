@@ -139,3 +139,89 @@ def test_banded_nw(ps):
     # [REF 725-736]
     res = ps.Aligner.new().bandwidth(4).build().banded_nw(b"ACGT", b"ACGT")
     assert res.get_score() == 4 and res.is_banded()
+
+
+def test_banded_nw_bandwidth_2(ps):
+    # the reference's own case: bandwidth(2), ACGT vs ACGT, score = len [REF 726-736]
+    res = ps.Aligner.new().bandwidth(2).build().banded_nw(b"ACGT", b"ACGT")
+    assert res.get_score() == 4
+
+
+def test_ssw_alignment(ps):
+    # [REF 738-757]
+    result = ps.Aligner.new().build().ssw(b"ACGT", b"ACGT")
+    assert result.score() == 4
+    assert result.query_end() == 3 and result.ref_end() == 3
+    assert result.query_start() == 0 and result.ref_start() == 0
+    assert result.cigar_len() == 1 and int(result.cigar()[0]) == (4 << 4 | 7)
+
+
+def test_ssw_init(ps):
+    # [REF 759-766]
+    p = ps.Profile.new_ssw(b"ACGT", ps.Matrix.default(), 2)
+    assert not p.is_null()
+
+
+def test_ssw_matches_sw_trace(ps, oracle, blosum62):
+    # SSW = sw_trace + begin coordinates + CIGAR words, against the oracle's local alignment
+    import psb_data
+    b62 = ps.Matrix.from_name("blosum62")
+    a = ps.Aligner.new().matrix(b62).gap_open(10).gap_extend(1).build()
+    for i in range(6):
+        q = psb_data.random_seq(301, 2 * i, 80 + 17 * i)
+        r = np.concatenate([psb_data.random_seq(301, 2 * i + 1, 20), psb_data.mutate(q[10:70], 301, 50 + i, 0.15, 0.05),
+                            psb_data.random_seq(302, i, 15)])
+        exp = oracle.align(q, r, blosum62, mode=2, open=10, gap=1, trace=True)
+        got = a.ssw(q, r)
+        assert (got.score(), got.query_end(), got.ref_end()) == (exp["score"], exp["end_query"], exp["end_ref"])
+        assert (got.query_start(), got.ref_start()) == (exp["beg_query"], exp["beg_ref"])
+        assert np.array_equal(got.cigar(), exp["cigar_ops"])
+
+
+def test_banded_nw_band_excludes_optimum(ps, oracle):
+    # a 12-residue insertion: a band of 4 cannot follow the optimal path, so the banded score is lower than
+    # the full one, and equal to the oracle's banded fill for every k
+    import psb_data
+    dna, odna = ps.Matrix.create(b"ACGT", 2, -3), oracle.Matrix.create(b"ACGT", 2, -3)
+    q = psb_data.random_seq(303, 0, 120, protein=False)
+    r = np.concatenate([q[:60], psb_data.random_seq(303, 1, 12, protein=False), q[60:]])[:120]
+    full = oracle.align(q, r, odna, mode=0, open=5, gap=2)["score"]
+    seen_lower = False
+    for k in (1, 2, 4, 8, 16, 64, 200):
+        exp = oracle.align(q, r, odna, mode=0, open=5, gap=2, band=k)
+        got = ps.Aligner.new().matrix(dna).gap_open(5).gap_extend(2).bandwidth(k).build().banded_nw(q, r)
+        assert got.get_score() == exp["score"], k
+        assert (got.get_end_query(), got.get_end_ref()) == (len(q) - 1, len(r) - 1)
+        seen_lower |= exp["score"] < full
+    assert seen_lower and exp["score"] == full
+    # unequal lengths: the band is widened by the length difference so the corner stays reachable
+    r2 = np.concatenate([r, psb_data.random_seq(303, 2, 25, protein=False)])
+    for k in (1, 3, 10):
+        exp = oracle.align(q, r2, odna, mode=0, open=5, gap=2, band=k)
+        got = ps.Aligner.new().matrix(dna).gap_open(5).gap_extend(2).bandwidth(k).build().banded_nw(q, r2)
+        assert got.get_score() == exp["score"], k
+
+
+def test_coarse_family_stats_multistrip(ps, oracle, blosum62):
+    # `_stats` with a PSSM / large-valued matrix and a query of several strips used to size
+    # the strip-boundary scratch for the narrow statistics word while the coarse kernels carry the wide one
+    import psb_data
+    big = oracle.Matrix.create(b"ACGT", 200, -150)       # S + open does not fit a byte: coarse family
+    pbig = ps.Matrix.create(b"ACGT", 200, -150)
+    qs = [psb_data.random_seq(304, i, L, protein=False) for i, L in enumerate((600, 900, 1500))]
+    rs = [psb_data.mutate(q, 304, 10 + i, 0.1, 0.04, protein=False)[:700] for i, q in enumerate(qs)]
+    for mode, name in ((0, "global_"), (1, "semi_global"), (2, "local")):
+        got = getattr(ps.Aligner.new(), name)().matrix(pbig).gap_open(30).gap_extend(4).use_stats().build().align_batch(qs, rs)
+        qc, qo = psb_data.concat(qs)
+        rc, ro = psb_data.concat(rs)
+        exp = oracle.align_batch(qc, qo, rc, ro, big, mode=mode, open=30, gap=4, stats=True)
+        for k in ("score", "end_query", "end_ref", "matches", "similar", "length"):
+            assert np.array_equal(getattr(got, k), exp[k]), (name, k)
+    # the same through a PSSM (query 700 rows)
+    q = psb_data.random_seq(305, 0, 700)
+    pssm = ps.Matrix.from_name("blosum62").to_pssm(q)
+    r = psb_data.mutate(q, 305, 1, 0.2, 0.05)[:650]
+    for mode, name in ((0, "global_"), (2, "local")):
+        a = getattr(ps.Aligner.new(), name)().matrix(pssm).gap_open(10).gap_extend(1).use_stats().build().align(q, r)
+        exp = oracle.align(q, r, blosum62, mode=mode, open=10, gap=1)
+        assert (a.get_score(), a.get_matches(), a.get_similar(), a.get_length()) == (exp["score"], exp["matches"], exp["similar"], exp["length"])

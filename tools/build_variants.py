@@ -9,6 +9,7 @@ variants:
   sw16x     split-column scan kernel (csrc/kern_sw16x.cuh): two half-columns per lane, one column apart
   prof8     scan kernel with the int8 profile joined by PRMT (SW16_PROF32=0)
   nopp      scan kernel without the ping-pong column copies (SW16_PINGPONG=0)
+  shifted   scan kernel with round 1's shifted recurrence (three dependent instructions per row)
 """
 import os
 import subprocess
@@ -22,6 +23,7 @@ VARIANTS = {
     "sw16x": ["PSB_SW16X"],
     "prof8": ["SW16_PROF32=0"],
     "nopp": ["SW16_PINGPONG=0"],
+    "shifted": ["SW16_DECOUPLE=0"],
 }
 
 
