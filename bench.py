@@ -222,9 +222,15 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ------------------------------------------------------
+    # SURVEY 8d protocol: database resident; query profile upload + kernels + results D2H inside the timed
+    # region, so every step builds a fresh Profile (host profile + H2D of query, matrix and packed profile)
+    def resident_step():
+        p = ps.Profile.new(query, False, blosum)
+        a = ps.Aligner.new().local().gap_open(OPEN).gap_extend(GAP).profile(p).build()
+        return a.scan(db)
     res = None
     for _ in range(args.warmup):
-        res = aligner.scan(db)
+        res = resident_step()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -233,7 +239,7 @@ def main():
     kernel_ms, launches = 0.0, 0
     ev0.record(stream)
     for _ in range(args.steps):
-        res = aligner.scan(db)
+        res = resident_step()
         kernel_ms += ps.kernel_ms()
         launches += ps.launches()
     ev1.record(stream)
@@ -299,12 +305,26 @@ def main():
         # scan (profiles/r1e_ncu_full_sw16_keymetrics.csv: 51.76 MB + 0.16 MB for 47.6 MB of packed
         # residues + 2.4 MB of results), scaled to this launch's algorithmic bytes
         "traffic": packed_bytes * (51.761152e6 + 0.164352e6) / (47.589941e6 + 2.4e6),
+        "traffic_source": "ncu --set full capture of round 1 (200k subjects), scaled by algorithmic bytes; not measured in this run",
         "kernel": "sw16_scan_kernel<25> (packed s16x2 DPX, 16-lane groups)", "kernel_ms_per_launch": float(kms.item()),
         "peak_basis": f"148 SM x {LANE_OPS_PER_CLK_SM} lane-ops/clk x {sm_mhz:.0f} MHz (sampled) / {OPS_PER_CELL} ops per cell x 2 cells per s16x2 op",
         "peak_at_max_clock": 148 * LANE_OPS_PER_CLK_SM * 1.965 / OPS_PER_CELL * 2,
         "hbm": {"algorithmic_bytes_per_launch": packed_bytes, "achieved_gbs": packed_bytes / (float(kms.item()) * 1e-3) / 1e9,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }
+
+    # ---- every subject against the cached CPU result (tests/golden/c2_block_hashes.json) -----------------
+    verified_all = None
+    gpath = os.path.join(ROOT, "tests", "golden", "c2_block_hashes.json" if args.db == 1000000 else f"c2_block_hashes_{args.db}.json")
+    if world == 1 and os.path.exists(gpath):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from make_c2_golden import block_hashes
+        gold = json.load(open(gpath))
+        mine_h = block_hashes(scan_scores, scan_eq, scan_er, gold["block"])
+        bad = [i for i, (a, b2) in enumerate(zip(mine_h, gold["hashes"])) if a != b2]
+        if bad or len(mine_h) != len(gold["hashes"]):
+            raise SystemExit(f"GPU scan disagrees with the cached CPU result in {len(bad)} blocks of {gold['block']} subjects (first: block {bad[:1]}) -- refusing to report a number")
+        verified_all = f"all {args.db} subjects equal to the cached CPU result ({len(mine_h)} block hashes, {gold['generated_by']})"
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + cross-check of the GPU results ----------------
     cpu = None
@@ -326,7 +346,8 @@ def main():
         "config": {"workload": workload_name(args.db), "sharding": f"residue-balanced over {world} GPU(s), no collective",
                    "cells_per_step": total_cells, "l2": "packed database (5 bit/residue) exceeds L2; not flushed between steps"
                    if float(off[-1]) * 5 / 8 / world > 126e6 else "shard fits L2; HBM traffic is not the bound (0.002 B/cell)",
-                   "subjects_rerun_at_32bit": int(nretry.item())},
+                   "subjects_rerun_at_32bit": int(nretry.item()), "verified": verified_all,
+                   "timed_region": "per step: Profile::new (host profile + H2D), scan kernels, results D2H; database resident"},
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": args.e2e_steps, "what": "profile create + psb_scan_host (piecewise H2D from pinned host memory overlapped with device packing and the scan kernels) + results D2H"},
         "gpu_launches": int(nl.item()), "clocks": clocks, "roofline": roofline,

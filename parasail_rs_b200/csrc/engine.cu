@@ -393,7 +393,8 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     // the single-pair trace-table export stay on the 32-bit kernels.
     const bool p16_walk = cfg.trace || cfg.stats;
     const bool p16_on = !std::getenv("PSB_NO_P16") && pairs16_scheme_ok(m.size, m.min, m.max, req.open, req.gap, pssm) && !want_table &&
-                        !banded && cfg.width != 32 && cfg.width != 64 && !(req.extra && cfg.trace);
+                        !banded && cfg.width != 32 && cfg.width != 64 && !(req.extra && cfg.trace) &&
+                        (!p16_walk || pairs16_trace_ok(m.min, m.max, req.open));
     std::vector<std::vector<int>> p16_ids(p16_on ? p16_num_classes() : 0);
     long long n_p16 = 0;
     std::vector<int> wave_ids;   // long score-only pairs: spread over the whole GPU one at a time
@@ -423,7 +424,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         else if (lq != first_lq || lr != first_lr) uniform = false;
         if (p16_on && lq <= 512) {
             const int c16 = c16_of[lq];
-            if (c16 >= 0 && pairs16_fits(p16_class(c16).G * p16_class(c16).K, lq, lr, m.max, m.min, req.open, req.gap, p16_walk)) {
+            if (c16 >= 0 && pairs16_fits(p16_class(c16).G * p16_class(c16).K, lq, lr, m.max, m.min, req.open, req.gap)) {
                 p16_ids[c16].push_back((int)i);
                 ++n_p16;
                 b->cells += (double)lq * lr;
@@ -467,21 +468,6 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     PSB_CUDA(cudaMemcpyAsync(d_qoff.p, qoff_rel.data(), qoff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
     PSB_CUDA(cudaMemcpyAsync(d_roff.p, roff_rel.data(), roff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
     PSB_CUDA(cudaMemcpyAsync(d_matrix.p, m.table.data(), m.table.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-    PSB_CUDA(cudaEventRecord(c.ev0, c.stream));
-    {
-        MapParams mp;
-        fill_lut(mp.lut, m.mapper);
-        const int blocks = c.sms * 8;
-        if (!(pssm && m.query.size() != (size_t)m.length)) {
-            mp.data = d_q.as<uint8_t>(); mp.n = (long long)qbytes;
-            map_residues_kernel<<<blocks, 256, 0, c.stream>>>(mp);
-            c.launches++;
-        }
-        mp.data = d_r.as<uint8_t>(); mp.n = (long long)(r_hi - r_lo);
-        map_residues_kernel<<<blocks, 256, 0, c.stream>>>(mp);
-        c.launches++;
-    }
-
     // outputs
     DevMem d_out[6], d_counter, d_bnd;
     const int nout = cfg.stats || want_table ? 6 : 3;
@@ -562,12 +548,13 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     std::vector<int> h_items, h_slot16, h_ids16;   // kept alive until the stream has consumed them
     std::vector<long long> h_toff16;
     std::vector<int8_t> h_mat8(33 * 32);
+    const bool sw = cfg.mode == MODE_SW;
+    const bool top_free = sw || (cfg.mode == MODE_SG && cfg.s1_beg);
+    std::vector<int> cls_item0(p16_ids.size() + 1, 0), cls_id0(p16_ids.size() + 1, 0);
     if (n_p16 > 0) {
-        const bool sw = cfg.mode == MODE_SW;
         h_items.reserve((size_t)n_p16 + 2 * p16_ids.size());
         h_ids16.reserve((size_t)n_p16);
         if (p16_walk) h_slot16.assign((size_t)n, 0);
-        std::vector<int> cls_item0(p16_ids.size() + 1, 0), cls_id0(p16_ids.size() + 1, 0);
         h_toff16.push_back(0);
         for (int c16 = 0; c16 < (int)p16_ids.size(); ++c16) {
             std::vector<int> &ids = p16_ids[c16];
@@ -595,7 +582,6 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         }
         cls_item0[p16_ids.size()] = (int)(h_items.size() / 2);
         cls_id0[p16_ids.size()] = (int)h_ids16.size();
-        const bool top_free = sw || (cfg.mode == MODE_SG && cfg.s1_beg);
         pairs16_build_mat8(m.table.data(), m.size, req.open, top_free, h_mat8.data());
         PSB_TRY(d_items.alloc(h_items.size() * sizeof(int), c.stream));
         PSB_TRY(d_mat8.alloc(h_mat8.size(), c.stream));
@@ -612,6 +598,33 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             PSB_CUDA(cudaMemcpyAsync(d_slot16.p, h_slot16.data(), h_slot16.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
             PSB_CUDA(cudaMemcpyAsync(d_ids16.p, h_ids16.data(), h_ids16.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
         }
+    }
+    // every host->device copy of this pass is queued: the timed region (psb_last_kernel_ms) starts here
+    PSB_CUDA(cudaEventRecord(c.ev0, c.stream));
+    {
+        MapParams mp;
+        fill_lut(mp.lut, m.mapper);
+        const int blocks = c.sms * 8;
+        if (!(pssm && m.query.size() != (size_t)m.length)) {
+            mp.data = d_q.as<uint8_t>(); mp.n = (long long)qbytes;
+            map_residues_kernel<<<blocks, 256, 0, c.stream>>>(mp);
+            c.launches++;
+        }
+        mp.data = d_r.as<uint8_t>(); mp.n = (long long)(r_hi - r_lo);
+        map_residues_kernel<<<blocks, 256, 0, c.stream>>>(mp);
+        c.launches++;
+    }
+
+    const bool dbg_time = std::getenv("PSB_DEBUG_TIMING") != nullptr;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> dbg_ev;
+    auto dbg_mark = [&](const std::string &what, bool begin) {
+        if (!dbg_time) return;
+        cudaEvent_t ev = nullptr;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, c.stream);
+        if (begin) dbg_ev.push_back({what, {ev, nullptr}}); else dbg_ev.back().second.second = ev;
+    };
+    if (n_p16 > 0) {
         std::string err;
         for (int c16 = 0; c16 < (int)p16_ids.size(); ++c16) {
             const int nitems = cls_item0[c16 + 1] - cls_item0[c16];
@@ -625,7 +638,11 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             pp.score = p.score; pp.end_query = p.end_query; pp.end_ref = p.end_ref;
             pp.trace = d_trace16.as<unsigned>(); pp.trace_off = p16_walk ? d_toff16.as<long long>() + cls_item0[c16] : nullptr;
             pp.counter = d_cnt16.as<int>() + c16;
-            const int rc16 = p16_launch(c16, sw, p16_walk, pp, c.sms, c.stream, &err);
+            int wps = 0;
+            dbg_mark("pairs16 fill G" + std::to_string(p16_class(c16).G) + " K" + std::to_string(p16_class(c16).K) + " items " + std::to_string(nitems), true);
+            const int rc16 = p16_launch(c16, sw, p16_walk, pp, c.sms, c.stream, &err, &wps);
+            dbg_mark("", false);
+            if (dbg_time) dbg_ev.back().first += " warps/SM " + std::to_string(wps);
             if (rc16 != PSB_OK) { set_error(err); return rc16; }
             c.launches++;
             if (p16_walk) {
@@ -636,16 +653,18 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
                 w.G = p16_class(c16).G; w.K = p16_class(c16).K;
                 w.trace = d_trace16.as<unsigned>(); w.trace_off = d_toff16.as<long long>();
                 w.matrix = p.matrix; w.size = m.size; w.open = req.open; w.gap = req.gap; w.is_sw = sw ? 1 : 0;
+                w.top_free = top_free ? 1 : 0; w.left_free = (sw || (cfg.mode == MODE_SG && cfg.s2_beg)) ? 1 : 0;
                 w.score = p.score; w.end_query = p.end_query; w.end_ref = p.end_ref;
                 w.rev_ops = d_rev.as<unsigned>(); w.rev_off = d_revoff.as<long long>();
                 w.nops = d_nops.as<int>(); w.beg_query = d_beg[0].as<int>(); w.beg_ref = d_beg[1].as<int>();
                 w.matches = p.matches; w.similar = p.similar; w.length = p.length;
+                dbg_mark("walk16", true);
                 const int rcw = p16_launch_walk(w, !cfg.trace, c.stream, &err);
+                dbg_mark("", false);
                 if (rcw != PSB_OK) { set_error(err); return rcw; }
                 c.launches++;
             }
         }
-        b->n_retried += 0;
     }
 
     std::vector<DevMem> d_orders(kNumClass);
@@ -778,6 +797,14 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     PSB_CUDA(cudaStreamSynchronize(c.stream));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_ms += ms;
+    for (auto &d : dbg_ev) {
+        float t = 0.f;
+        if (d.second.second && cudaEventElapsedTime(&t, d.second.first, d.second.second) == cudaSuccess)
+            std::fprintf(stderr, "[psb] %-48s %9.3f ms\n", d.first.c_str(), t);
+        cudaEventDestroy(d.second.first);
+        if (d.second.second) cudaEventDestroy(d.second.second);
+    }
+    if (dbg_time) std::fprintf(stderr, "[psb] pass of %lld pairs: timed region %.3f ms\n", (long long)n, ms);
     return PSB_OK;
 }
 
@@ -847,7 +874,7 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
     }
     const HostMatrix &hm0 = *req.matrix;
     const bool p16_scheme = !std::getenv("PSB_NO_P16") && pairs16_scheme_ok(hm0.size, hm0.min, hm0.max, req.open, req.gap, hm0.type == PARASAIL_MATRIX_TYPE_PSSM) &&
-                            req.cfg.width != 32 && req.cfg.width != 64 && !req.extra;
+                            pairs16_trace_ok(hm0.min, hm0.max, req.open) && req.cfg.width != 32 && req.cfg.width != 64 && !req.extra;
     int64_t csr_used = 0;
     int64_t lo = 0;
     while (lo < req.n) {
@@ -859,7 +886,7 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
                 const int64_t lq = req.shared_query ? req.q_off[1] - req.q_off[0] : req.q_off[hi + 1] - req.q_off[hi];
                 const int64_t lr = req.r_off[hi + 1] - req.r_off[hi];
                 int64_t need;
-                if (p16_scheme && lq <= 512) need = (lr + 32) * (lq + 288) / 2 + 8 * (lq + lr);   // half a byte per cell of the padded frame
+                if (p16_scheme && lq <= 512) need = (lr + 32) * (lq + 96) * 5 / 4 + 8 * (lq + lr);   // one byte of H per cell of the padded frame
                 else if (req.cfg.trace) {
                     const int K = 16;  // upper bound on rows per lane of any class
                     need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);

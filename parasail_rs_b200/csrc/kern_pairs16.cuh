@@ -23,13 +23,18 @@
 //     last row / corner candidates of nw and sg come out of a register that is live anyway.
 //   * 16-bit safety is decided on the host by a static bound on the pair's lengths (pairs16_fits);
 //     anything that does not fit goes to the 32-bit kernel, so there is no saturation to detect here.
-//   * TRACE: four raw decision bits per cell -- "E extends", "F extends", "diagonal is the maximum",
-//     "F >= E" -- taken from the sign bits of packed differences and packed eight rows to a byte, stored
-//     as 2*ceil(K/8) words per lane and step ([step][lane][word], one coalesced run per group and step:
-//     half a byte per cell).  The ZERO state of local alignment is not stored: the walk tracks the value
-//     of H along the path and stops when it reaches 0.  walk16_kernel turns the bits into the CIGAR run
-//     list or into (matches, similar, length) -- the statistics are those of the traceback path, which
-//     is how `_stats` results are produced for batches (same source priorities).
+//   * TRACE: the low byte of H of every cell -- nothing else.  Neighbouring cells of a Gotoh table differ by
+//     less than 2*(max|S| + open) <= 127 (pairs16_trace_ok), so a walk that knows H exactly at one cell
+//     recovers it exactly at any neighbour from that byte, and every decision of the traceback follows from
+//     exact H values: the diagonal was taken iff H[i-1][j-1] + S == H[i][j] (it wins ties); otherwise a
+//     vertical gap of length k iff H[i-k][j] - o - (k-1)e == H[i][j] for some k (F wins ties over E), with the
+//     LARGEST such k, which is what "extend on ties" means for a flag-driven walk; otherwise the same test
+//     along the row.  The fill therefore pays ONE PRMT per two rows for the trace (the low bytes of two rows
+//     x two pairs make one word) instead of a dozen instructions of per-cell decision bits, and stores
+//     2*ceil(K/2) bytes per lane and step, one coalesced run per group and step (1 byte per cell).
+//     walk16_kernel turns the bytes into the CIGAR run list or into (matches, similar, length) -- the
+//     statistics are those of the traceback path, which is how `_stats` results are produced for batches
+//     (same source priorities).
 #pragma once
 #include "psb_defs.h"
 #include "psb_simt.h"
@@ -50,13 +55,13 @@ struct Pairs16Params {
     int open, gap;
     int mode, s1_beg, s1_end, s2_beg, s2_end;
     int *score, *end_query, *end_ref;     // indexed by pair id
-    unsigned *trace;            // TRACE: decision bits
+    unsigned *trace;            // TRACE: low bytes of H, [step][lane][row pair][pair A, pair B]
     const long long *trace_off; // first word of each item's block
     int *counter;               // dynamic work queue over warp slots
 };
 
 inline constexpr int pairs16_slot(int K) { return ((K + 3) / 4) * 4; }        // profile bytes per lane and letter
-inline constexpr int pairs16_trace_words(int K) { return 2 * ((K + 7) / 8); } // decision words per lane and step
+inline constexpr int pairs16_trace_words(int K) { return (((K + 1) / 2) + 1) & ~1; } // H-byte words per lane and step (even)
 inline size_t pairs16_warp_smem(int K, int nletters, bool sw) {
     const size_t prof = (size_t)64 * nletters * pairs16_slot(K);   // (32/G groups) x 2 halves x letters x G lanes x slot
     const size_t park = sw ? (size_t)2 * 32 * pairs16_slot(K) * 4 : 0;
@@ -69,12 +74,16 @@ inline size_t pairs16_smem_bytes(int K, int nletters, bool sw, int warps) {
 inline long long pairs16_item_trace_words(int G, int K, int lr_max) {
     return (((long long)(lr_max + G - 1) * G * pairs16_trace_words(K)) + 3) / 4 * 4;
 }
-// static 16-bit bound: every intermediate of the fill (and, with trace, every difference of two of
-// them) stays inside int16 for this pair in a G*K-row frame
-inline bool pairs16_fits(int rows, int lq, int lr, int smax, int smin, int open, int gap, bool trace) {
+// static 16-bit bound: every intermediate of the fill stays inside int16 for this pair in a G*K-row frame
+inline bool pairs16_fits(int rows, int lq, int lr, int smax, int smin, int open, int gap) {
     const long long pos = (long long)(lq < lr ? lq : lr) * (smax > 0 ? smax : 0) + 2ll * open + 256;
     const long long neg = 3ll * open + (long long)(rows + lr + 4) * gap + 256 + (smin < 0 ? -smin : 0);
-    return trace ? pos + neg < 32000 : (pos < 32000 && neg < 32000);
+    return pos < 32000 && neg < 32000;
+}
+// trace / stats: neighbouring cells must differ by less than 128 so that one byte of H per cell is enough
+inline bool pairs16_trace_ok(int mat_min, int mat_max, int open) {
+    const int m = (mat_max > -mat_min ? mat_max : -mat_min);
+    return 2 * (m + open) <= 127;
 }
 // the kernel's preconditions on the scoring scheme (the int8 profile and the one-instruction F chain)
 inline bool pairs16_scheme_ok(int size, int mat_min, int mat_max, int open, int gap, bool pssm) {
@@ -99,7 +108,7 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
     constexpr int SLOT = ((K + 3) / 4) * 4;
     constexpr int NW4 = SLOT / 4;
     constexpr unsigned LSTRIDE = (unsigned)G * SLOT;
-    constexpr int TW = 2 * ((K + 7) / 8);
+    constexpr int TW = (((K + 1) / 2) + 1) & ~1;   // = pairs16_trace_words(K)
     constexpr int ROWS = G * K;
     PSB_SHARED_DECL(smem_raw);
     const int lane = lane_id();
@@ -198,7 +207,7 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
             const int lb = (il < 0 || ib < 0 || left_free) ? 0 : -o - ib * e;
             Tdiag_in = p16_pack(la - o, lb - o);
         }
-        unsigned Tout = Tdiag_in, Fout = 0, Xout = 0;
+        unsigned Tout = Tdiag_in, Fout = 0;
         // local: per half, a column maximum must exceed `thr` to matter (see kern_sw16.cuh)
         unsigned thr = 0, best = 0, bestj = 0;
         // global / semi-global candidates, kept in T space (T = H - o)
@@ -225,13 +234,10 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
                 const int j = s - lg;
                 unsigned Tup = shfl_up(Tout, 1);
                 unsigned Fup = shfl_up(Fout, 1);
-                unsigned Xup = 0;
-                if (TRACE) Xup = shfl_up(Xout, 1);
                 if (lg == 0) {
                     const int hb = top_free ? 0 : -o - j * e;     // H[-1][j]
                     Tup = p16_pack(hb - o, hb - o);
-                    Fup = p16_pack(hb, hb);                        // Fh = F + o with F[0][j] = H[-1][j] - o: opened
-                    Xup = 0;
+                    Fup = p16_pack(hb, hb);                        // Fh = F + o with F[0][j] = H[-1][j] - o
                 }
                 if (j >= 0 && j < Lmax) {
                     const unsigned w = ring[j & 63];
@@ -242,41 +248,20 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
                     for (int c = 0; c < NW4; ++c) { wa[c] = *(const unsigned *)(pa + 4 * c); wb[c] = *(const unsigned *)(pb + 4 * c); }
                     unsigned Td = Tdiag_in, Fu = Fup;
                     unsigned cmax = 0, hprev = 0;
-                    unsigned accEF[TW / 2], accDX[TW / 2];
-                    unsigned sFin = Xup;
-                    if (TRACE) {
-#pragma unroll
-                        for (int x = 0; x < TW / 2; ++x) { accEF[x] = 0; accDX[x] = 0; }
-                    }
+                    unsigned hb8[TW];   // TRACE: low bytes of H, two rows x two pairs per word
+                    unsigned heven = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const unsigned So = prmt(wa[k >> 2], wb[k >> 2], 0xC480u + (unsigned)(k & 3) * 0x1111u);
                         const unsigned Tl = Tin[k];
-                        unsigned Hn, Tn, En, Fn;
-                        if (!TRACE) {
-                            En = viaddmax2(E[k], NEGE, Tl);
-                            const unsigned h = viaddmax2(Td, So, En);
-                            Hn = SW ? viaddmax2_relu(Fu, NEGO, h) : viaddmax2(Fu, NEGO, h);
-                            Fn = viaddmax2(Fu, NEGE, h);
-                            Tn = vadd2(Hn, NEGO);
-                        } else {
-                            const unsigned Eext = vadd2(E[k], NEGE);
-                            En = vimax2(Eext, Tl);
-                            const unsigned hd = vadd2(Td, So);
-                            const unsigned h = vimax2(hd, En);
-                            const unsigned Fext = vadd2(Fu, NEGE);
-                            Fn = vimax2(Fext, h);
-                            const unsigned Fv = vadd2(Fu, NEGO);          // F of this cell
-                            Hn = SW ? vimax2_relu(h, Fv) : vimax2(h, Fv);
-                            Tn = vadd2(Hn, NEGO);
-                            // decisions from sign bits: sign(a + ~b) is set  <=>  a <= b   (rules: psb_defs.h)
-                            const unsigned sE = vadd2(Tl, ~Eext);           // E extends (opening is not strictly better)
-                            const unsigned sD = vadd2(Hn, ~hd);             // the diagonal is the maximum (diag wins ties)
-                            const unsigned sG = vadd2(En, ~Fv);             // F >= E (F wins ties over E)
-                            const unsigned rowbit = 0x01010101u << (k & 7);
-                            accEF[k >> 3] |= prmt(sE, sFin, 0xFDB9u) & rowbit;
-                            accDX[k >> 3] |= prmt(sD, sG, 0xFDB9u) & rowbit;
-                            sFin = vadd2(h, ~Fext);                          // for the row below: F extends
+                        const unsigned En = viaddmax2(E[k], NEGE, Tl);
+                        const unsigned h = viaddmax2(Td, So, En);
+                        const unsigned Hn = SW ? viaddmax2_relu(Fu, NEGO, h) : viaddmax2(Fu, NEGO, h);
+                        const unsigned Fn = viaddmax2(Fu, NEGE, h);
+                        const unsigned Tn = vadd2(Hn, NEGO);
+                        if (TRACE) {
+                            if (k & 1) hb8[k >> 1] = prmt(heven, Hn, 0x6420u);
+                            else heven = Hn;
                         }
                         if (SW) {
                             if (k & 1) cmax = vimax3_2(cmax, hprev, Hn);
@@ -284,22 +269,26 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
                         }
                         Td = Tl; Tnew[k] = Tn; E[k] = En; Fu = Fn;
                     }
+                    if (TRACE) {
+                        if (K & 1) hb8[K >> 1] = prmt(heven, 0u, 0x6420u);
+#pragma unroll
+                        for (int x = (K + 1) / 2; x < TW; ++x) hb8[x] = 0;
+                    }
                     if (SW && (K & 1)) cmax = vimax2(cmax, hprev);
                     Tdiag_in = Tup; Tout = Tnew[K - 1]; Fout = Fu;
                     if (TRACE) {
-                        Xout = sFin;
                         unsigned *dst = p.trace + tr_base + ((long long)s * G + lg) * TW;
                         if (TW % 4 == 0) {
 #pragma unroll
                             for (int x = 0; x < TW / 4; ++x) {
-                                uint4 v; v.x = accEF[2 * x]; v.y = accDX[2 * x]; v.z = accEF[2 * x + 1]; v.w = accDX[2 * x + 1];
-                                st_cg((uint4 *)dst + x, v);
+                                uint4 v; v.x = hb8[4 * x]; v.y = hb8[4 * x + 1]; v.z = hb8[4 * x + 2]; v.w = hb8[4 * x + 3];
+                                st_cs((uint4 *)dst + x, v);
                             }
                         } else {
 #pragma unroll
                             for (int x = 0; x < TW / 2; ++x) {
-                                uint2 v; v.x = accEF[x]; v.y = accDX[x];
-                                st_cg((uint2 *)dst + x, v);
+                                uint2 v; v.x = hb8[2 * x]; v.y = hb8[2 * x + 1];
+                                st_cs((uint2 *)dst + x, v);
                             }
                         }
                     }
@@ -441,9 +430,10 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
     }
 }
 
-// ---- walk over the decision bits ---------------------------------------------------------------
-// One thread per pair.  CIGAR mode writes the run-length list in reverse into the pair's scratch region
-// (compact_cigar_kernel reverses it into the CSR); STATS mode counts (matches, similar, length) of the path.
+// ---- walk over the H bytes ---------------------------------------------------------------------
+// One thread per pair.  walk16_kernel<false> writes the CIGAR run-length list in reverse into the pair's
+// scratch region (compact_cigar_kernel reverses it into the CSR); walk16_kernel<true> counts (matches,
+// similar, length) of the path.  Every decision is re-derived from exact H values (see the header).
 struct Walk16Params {
     const uint8_t *q;
     const long long *q_off;
@@ -459,7 +449,7 @@ struct Walk16Params {
     const int *matrix;           // size x size substitution scores (no open added)
     int size;
     int open, gap;
-    int is_sw;
+    int is_sw, top_free, left_free;
     const int *score, *end_query, *end_ref;   // per pair id
     // CIGAR outputs (walk16_kernel<false>)
     unsigned *rev_ops;
@@ -480,59 +470,70 @@ PSB_KERNEL void walk16_kernel(Walk16Params p) {
     const int Lq = (int)((p.shared_query ? p.q_off[1] : p.q_off[pid + 1]) - qo);
     const uint8_t *q = p.q + qo;
     const uint8_t *r = p.r + p.r_off[pid];
-    const int G = p.G, K = p.K, TW = 2 * ((K + 7) / 8);
+    const int G = p.G, K = p.K, TW = (((K + 1) / 2) + 1) & ~1;   // = pairs16_trace_words(K)
     const int pad = G * K - Lq;
-    const unsigned *tr = p.trace + p.trace_off[item];
+    const int o = p.open, e = p.gap;
+    const uint8_t *tr = (const uint8_t *)(p.trace + p.trace_off[item]);
     unsigned *out = STATS ? nullptr : p.rev_ops + p.rev_off[pid];
+    // exact H of cell (i, j) from its stored byte and the exact value `ref` of a neighbouring cell
+    auto cell = [&](int i, int j, int ref) -> int {
+        const int il = i + pad, t = il / K, k = il - t * K;
+        const unsigned byte = tr[((long long)(j + t) * G + t) * (TW * 4) + 2 * k + half];
+        return ref + (int)(signed char)(unsigned char)(byte - (unsigned)ref);
+    };
+    auto top = [&](int j) -> int { return (j < 0 || p.top_free) ? 0 : -o - j * e; };     // H[-1][j], corner 0
+    auto left = [&](int i) -> int { return (i < 0 || p.left_free) ? 0 : -o - i * e; };   // H[i][-1]
     int i = p.end_query[pid], j = p.end_ref[pid];
-    int v = p.score[pid];            // local alignment: the value of the state we are in
-    int state = 0;                   // 0 = H, 1 = E (horizontal, consumes reference), 2 = F (vertical, consumes query)
+    int v = p.score[pid];            // exact H[i][j]
     int cur = -1, n = 0;
     unsigned len = 0;
     int nm = 0, ns = 0, nl = 0;
+    auto emit = [&](int op, int count) {
+        if (STATS || count <= 0) return;
+        if (op == cur) len += (unsigned)count;
+        else {
+            if (cur >= 0) out[n++] = (len << 4) | (unsigned)cur;
+            cur = op; len = (unsigned)count;
+        }
+    };
     while (i >= 0 || j >= 0) {
-        int op;
         if (i < 0 || j < 0) {
-            // off the table: statistics stop here (boundary gaps are not counted); the CIGAR takes the rest
-            // of the other sequence as one run (rules::CIGAR_WALK_TO_ORIGIN)
-            if (STATS) break;
-            if (i < 0) { op = (int)rules::CIGAR_OP_D; --j; }
-            else { op = (int)rules::CIGAR_OP_I; --i; }
-        } else {
-            if (state == 0 && p.is_sw && v <= 0) break;   // ZERO: the alignment starts after this cell
-            const int il = i + pad, t = il / K, k = il - t * K;
-            const unsigned *w = tr + ((long long)(j + t) * G + t) * TW + 2 * (k >> 3);
-            const int bit = (k & 7) + 8 * half;
-            if (state == 0) {
-                const unsigned dx = w[1];
-                if ((dx >> bit) & 1u) {
-                    const int a = q[i], b = r[j];
-                    const int sub = p.matrix[a * p.size + b];
-                    op = (a == b) ? (int)rules::CIGAR_OP_EQ : (int)rules::CIGAR_OP_X;
-                    nm += (a == b); ns += (sub > 0);
-                    v -= sub; --i; --j;
-                } else {
-                    state = ((dx >> (bit + 16)) & 1u) ? 2 : 1;   // F >= E: vertical, else horizontal
-                    continue;
-                }
-            } else if (state == 1) {
-                op = (int)rules::CIGAR_OP_D;
-                if ((w[0] >> bit) & 1u) v += p.gap; else { v += p.open; state = 0; }
-                --j;
-            } else {
-                op = (int)rules::CIGAR_OP_I;
-                if ((w[0] >> (bit + 16)) & 1u) v += p.gap; else { v += p.open; state = 0; }
-                --i;
-            }
+            // off the table: statistics stop here (boundary gaps are not counted); the CIGAR takes the rest of
+            // the other sequence as one run (rules::CIGAR_WALK_TO_ORIGIN)
+            if (i < 0) { emit((int)rules::CIGAR_OP_D, j + 1); j = -1; }
+            else { emit((int)rules::CIGAR_OP_I, i + 1); i = -1; }
+            break;
         }
-        ++nl;
-        if (!STATS) {
-            if (op == cur) ++len;
-            else {
-                if (cur >= 0) out[n++] = (len << 4) | (unsigned)cur;
-                cur = op; len = 1;
-            }
+        if (p.is_sw && v <= 0) break;   // ZERO: the alignment starts after this cell
+        const int a = q[i], b = r[j];
+        const int sub = p.matrix[a * p.size + b];
+        // the diagonal wins ties: taken iff H[i-1][j-1] + S == H[i][j]
+        const int hd = i == 0 ? top(j - 1) : (j == 0 ? left(i - 1) : cell(i - 1, j - 1, v - sub));
+        if (hd + sub == v) {
+            emit((a == b) ? (int)rules::CIGAR_OP_EQ : (int)rules::CIGAR_OP_X, 1);
+            nm += (a == b); ns += (sub > 0); ++nl;
+            v = hd; --i; --j;
+            continue;
         }
+        // vertical gap (F wins ties over E): the largest k with H[i-k][j] - o - (k-1)e == H[i][j]
+        int kbest = 0, vbest = 0, u = v;
+        for (int k = 1; k <= i + 1; ++k) {
+            u = (i - k < 0) ? top(j) : cell(i - k, j, u);
+            if (u - o - (k - 1) * e == v) { kbest = k; vbest = u; if (rules::GAP_OPEN_ON_TIE) break; }
+        }
+        if (kbest) {
+            emit((int)rules::CIGAR_OP_I, kbest);
+            nl += kbest; i -= kbest; v = vbest;
+            continue;
+        }
+        u = v;
+        for (int k = 1; k <= j + 1; ++k) {
+            u = (j - k < 0) ? left(i) : cell(i, j - k, u);
+            if (u - o - (k - 1) * e == v) { kbest = k; vbest = u; if (rules::GAP_OPEN_ON_TIE) break; }
+        }
+        if (!kbest) break;   // cannot happen for a table the fill produced
+        emit((int)rules::CIGAR_OP_D, kbest);
+        nl += kbest; j -= kbest; v = vbest;
     }
     if (STATS) {
         p.matches[pid] = nm; p.similar[pid] = ns; p.length[pid] = nl;

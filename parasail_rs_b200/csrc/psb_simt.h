@@ -42,6 +42,8 @@ PSB_DEV unsigned viaddmax2_relu(unsigned a, unsigned b, unsigned c) { return __v
 PSB_DEV unsigned vimax3_2(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
 PSB_DEV unsigned vimax2(unsigned a, unsigned b) { return __vmaxs2(a, b); }
 PSB_DEV unsigned vimax2_relu(unsigned a, unsigned b) { return __vimax_s16x2_relu(a, b); }   // max(a, b, 0) per half
+PSB_DEV void st_cs(uint4 *p, uint4 v) { __stcs(p, v); }   // streaming: written once, read by a later kernel
+PSB_DEV void st_cs(uint2 *p, uint2 v) { __stcs(p, v); }
 PSB_DEV void st_cg(uint4 *p, uint4 v) { __stcg(p, v); }
 PSB_DEV void st_cg(uint2 *p, uint2 v) { __stcg(p, v); }
 PSB_DEV unsigned vadd2(unsigned a, unsigned b) { return __vadd2(a, b); }
@@ -162,6 +164,8 @@ inline unsigned vadd2(unsigned a, unsigned b) { return pack16(lo16(a) + lo16(b),
 inline unsigned vimax2_relu(unsigned a, unsigned b) {
     return pack16(std::max(std::max((int)lo16(a), (int)lo16(b)), 0), std::max(std::max((int)hi16(a), (int)hi16(b)), 0));
 }
+inline void st_cs(uint4 *p, uint4 v) { *p = v; }
+inline void st_cs(uint2 *p, uint2 v) { *p = v; }
 inline void st_cg(uint4 *p, uint4 v) { *p = v; }
 inline void st_cg(uint2 *p, uint2 v) { *p = v; }
 inline unsigned prmt(unsigned a, unsigned b, unsigned sel) {

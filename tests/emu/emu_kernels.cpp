@@ -118,7 +118,7 @@ extern "C" int emu_pairs16(int G, int K, int mode, int s1_beg, int s1_end, int s
                            int *score, int *end_query, int *end_ref, int *matches, int *similar, int *length,
                            unsigned *rev_ops, const long long *rev_off, int *nops, int *beg_query, int *beg_ref) {
     const bool sw = mode == MODE_SW, trace = what != 0;
-    if (!pairs16_scheme_ok(size, mat_min, mat_max, open, gap, false)) return -2;
+    if (!pairs16_scheme_ok(size, mat_min, mat_max, open, gap, false) || (what != 0 && !pairs16_trace_ok(mat_min, mat_max, open))) return -2;
     std::vector<int> items;
     for (int i = 0; i < n; i += 2) { items.push_back(i); items.push_back(i + 1 < n ? i + 1 : -1); }
     const int nitems = (int)items.size() / 2;
@@ -130,7 +130,7 @@ extern "C" int emu_pairs16(int G, int K, int mode, int s1_beg, int s1_end, int s
             const int pid = items[2 * w + h];
             if (pid < 0) continue;
             const int lq = (int)(q_off[pid + 1] - q_off[pid]), lr = (int)(r_off[pid + 1] - r_off[pid]);
-            if (lq > G * K || !pairs16_fits(G * K, lq, lr, mat_max, mat_min, open, gap, trace)) return -2;
+            if (lq > G * K || !pairs16_fits(G * K, lq, lr, mat_max, mat_min, open, gap)) return -2;
             lrmax = std::max(lrmax, lr);
             slot_of[pid] = 2 * w + h;
         }
@@ -158,7 +158,7 @@ extern "C" int emu_pairs16(int G, int K, int mode, int s1_beg, int s1_end, int s
         std::memset(&w, 0, sizeof(w));
         w.q = q; w.q_off = q_off; w.r = r; w.r_off = r_off; w.pair_ids = ids.data(); w.pair_slot = slot_of.data(); w.n = n;
         w.G = G; w.K = K; w.trace = tr.data(); w.trace_off = toff.data(); w.matrix = table; w.size = size;
-        w.open = open; w.gap = gap; w.is_sw = sw ? 1 : 0; w.score = score; w.end_query = end_query; w.end_ref = end_ref;
+        w.open = open; w.gap = gap; w.is_sw = sw ? 1 : 0; w.top_free = top_free ? 1 : 0; w.left_free = (sw || (mode == MODE_SG && s2_beg)) ? 1 : 0; w.score = score; w.end_query = end_query; w.end_ref = end_ref;
         w.rev_ops = rev_ops; w.rev_off = rev_off; w.nops = nops; w.beg_query = beg_query; w.beg_ref = beg_ref;
         w.matches = matches; w.similar = similar; w.length = length;
         if (what == 2) emu::launch((n + 31) / 32, 64, [&]() { walk16_kernel<true>(w); });
