@@ -260,28 +260,42 @@ def main():
     scan_eq, scan_er = res.end_query.copy(), res.end_ref.copy()
 
     # ---- end to end: host buffers in, host results out, every step ---------------------------------
+    # N = 1: one C call with HOST buffers, psb_scan_host (piecewise upload from pinned memory on a copy
+    # stream, device-side sort + packing, scan kernels, results D2H, all pipelined).
+    # N > 1: ONE process drives the whole box through psb_scan_box: rank 0 hands the full host database to
+    # the library, which cuts it into N residue-balanced ranges, runs one worker thread per device and
+    # returns ONE caller-order batch; the other ranks idle at the barrier meanwhile.
+    e2e_res = None
+    if world == 1:
+        e2e_cat, e2e_off = pin_cat.numpy(), pin_off.numpy()
+    elif rank == 0:
+        full_cat = torch.empty(len(cat), dtype=torch.uint8, pin_memory=True)
+        full_cat.numpy()[:] = cat
+        full_off = torch.empty(len(off), dtype=torch.int64, pin_memory=True)
+        full_off.numpy()[:] = off
+        e2e_cat, e2e_off = full_cat.numpy(), full_off.numpy()
+
     def e2e_step():
-        # one C call with HOST buffers: psb_scan_host uploads the residues piecewise from pinned
-        # memory (copy stream), packs them on the device and scans, then copies the results back
         p = ps.Profile.new(query, False, blosum)
         a = ps.Aligner.new().local().gap_open(OPEN).gap_extend(GAP).profile(p).build()
-        r = a.scan_host((pin_cat.numpy(), pin_off.numpy()))
-        return int(r.score[0])
-    for _ in range(3):   # warm-up: pool growth, pinned result blocks, first-touch of the copy stream
-        e2e_step()
+        return a.scan_host((e2e_cat, e2e_off)) if world == 1 else a.scan_box((e2e_cat, e2e_off), world)
+    if rank == 0:
+        for _ in range(3):   # warm-up: contexts of the worker threads, pool growth, pinned result blocks
+            e2e_res = e2e_step()
     barrier()
-    t0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    ev1.record(stream)
+    e2e_wall = 0.0
+    if rank == 0:
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_res = e2e_step()
+        e2e_wall = (time.perf_counter() - t0) * 1e3
     barrier()
-    e2e_ms = torch.tensor([max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)], dtype=torch.float64, device="cuda")
+    e2e_ms = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = total_cells * args.e2e_steps / (float(e2e_ms.item()) * 1e-3) / 1e9
-    h2d = int(len(my_cat) + 8 * len(my_off) + 8 * len(my_off) + 4 * 2 * len(mine) + QUERY_LEN + 26 * 512)
-    d2h = int(12 * len(mine) + 4)
+    h2d = int(len(cat) + 8 * len(off) + QUERY_LEN + 26 * 512 * 4 * world)
+    d2h = int(12 * len(lens) + 4 * world)
 
     if rank != 0:
         if world > 1:
@@ -316,15 +330,20 @@ def main():
     # ---- every subject against the cached CPU result (tests/golden/c2_block_hashes.json) -----------------
     verified_all = None
     gpath = os.path.join(ROOT, "tests", "golden", "c2_block_hashes.json" if args.db == 1000000 else f"c2_block_hashes_{args.db}.json")
-    if world == 1 and os.path.exists(gpath):
+    if os.path.exists(gpath):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         from make_c2_golden import block_hashes
         gold = json.load(open(gpath))
-        mine_h = block_hashes(scan_scores, scan_eq, scan_er, gold["block"])
-        bad = [i for i, (a, b2) in enumerate(zip(mine_h, gold["hashes"])) if a != b2]
-        if bad or len(mine_h) != len(gold["hashes"]):
-            raise SystemExit(f"GPU scan disagrees with the cached CPU result in {len(bad)} blocks of {gold['block']} subjects (first: block {bad[:1]}) -- refusing to report a number")
-        verified_all = f"all {args.db} subjects equal to the cached CPU result ({len(mine_h)} block hashes, {gold['generated_by']})"
+        checks = [("end-to-end call", e2e_res.score, e2e_res.end_query, e2e_res.end_ref)]
+        if world == 1:
+            checks.append(("resident scan", scan_scores, scan_eq, scan_er))
+        for what, sc, eq, er in checks:
+            mine_h = block_hashes(sc, eq, er, gold["block"])
+            bad = [i for i, (a, b2) in enumerate(zip(mine_h, gold["hashes"])) if a != b2]
+            if bad or len(mine_h) != len(gold["hashes"]):
+                raise SystemExit(f"{what}: GPU results disagree with the cached CPU result in {len(bad)} blocks of {gold['block']} subjects (first: block {bad[:1]}) -- refusing to report a number")
+        verified_all = (f"all {args.db} subjects of {' and '.join(c[0] for c in checks)} equal to the cached CPU result "
+                        f"({len(gold['hashes'])} block hashes, {gold['generated_by']})")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + cross-check of the GPU results ----------------
     cpu = None
@@ -349,7 +368,11 @@ def main():
                    "subjects_rerun_at_32bit": int(nretry.item()), "verified": verified_all,
                    "timed_region": "per step: Profile::new (host profile + H2D), scan kernels, results D2H; database resident"},
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": args.e2e_steps, "what": "profile create + psb_scan_host (piecewise H2D from pinned host memory overlapped with device packing and the scan kernels) + results D2H"},
+                "steps": args.e2e_steps,
+                "what": ("profile create + psb_scan_host (piecewise H2D from pinned host memory overlapped with device packing and the scan kernels) + results D2H"
+                         if world == 1 else
+                         f"ONE process, one call: profile create + psb_scan_box over {world} GPUs (contiguous residue-balanced ranges, one worker thread per device, "
+                         "piecewise H2D from the caller's pinned arrays, device packing, scan kernels, caller-order results D2H into one batch); wall clock on rank 0")},
         "gpu_launches": int(nl.item()), "clocks": clocks, "roofline": roofline,
     }
     if cpu:

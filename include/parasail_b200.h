@@ -271,17 +271,36 @@ int psb_align_pairs(const char *fn_name, const parasail_matrix_t *matrix, int op
                     int64_t n, psb_batch_t **out);
 
 /* a database resident on the current device: residues mapped through `matrix`'s mapper and
- * bit-packed on the GPU (5 bit/residue, 2 bit when the alphabet has <= 4 letters), sorted by
- * length, with the permutation kept so results come back in the caller's order. */
+ * bit-packed on the GPU -- 5 bit/residue for protein alphabets, 3 bit for alphabets of up to 8 letters,
+ * 2 bit when every residue present maps to one of the first four columns (A/C/G/T without wildcards) --
+ * sorted by length, with the permutation kept so results come back in the caller's order.  The caller's
+ * buffers may be reused as soon as psb_db_create returns. */
 typedef struct psb_db psb_db_t;
 psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const parasail_matrix_t *matrix);
 int64_t psb_db_count(const psb_db_t *db);
 int64_t psb_db_residues(const psb_db_t *db);
 int64_t psb_db_device_bytes(const psb_db_t *db);
+int psb_db_bits(const psb_db_t *db);      /* bits per packed residue: 2, 3 or 5 */
 void psb_db_free(psb_db_t *db);
 
+/* the step before the hot path (no reference counterpart -- parasail-rs callers hand
+ * &[u8] to every call): FASTA -> (residues, offsets, names), FASTA -> resident database, and the packed,
+ * length-sorted database as one file (layout in csrc/db_io.cu) so that a service does not sort and pack
+ * at every start.  psb_db_load checks the file's alphabet against `matrix` when one is given. */
+typedef struct psb_fasta psb_fasta_t;
+psb_fasta_t *psb_fasta_read(const char *path);
+int64_t psb_fasta_count(const psb_fasta_t *fa);
+const uint8_t *psb_fasta_residues(const psb_fasta_t *fa);
+const int64_t *psb_fasta_offsets(const psb_fasta_t *fa);      /* count + 1 entries */
+const char *psb_fasta_name(const psb_fasta_t *fa, int64_t i, int *len);   /* header line of record i, not NUL-terminated */
+void psb_fasta_free(psb_fasta_t *fa);
+psb_db_t *psb_db_from_fasta(const char *path, const parasail_matrix_t *matrix);
+int psb_db_save(const psb_db_t *db, const char *path);
+psb_db_t *psb_db_load(const char *path, const parasail_matrix_t *matrix);
+
 /* one resident profile against a resident database (config C2).  fn_name follows the grammar
- * with "_profile"; top_k > 0 additionally fills out->impl-side top-k (see psb_batch_topk). */
+ * with "_profile".  Every subject's result comes back in the caller's order; psb_batch_topk selects the
+ * best k of them on the host. */
 int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const psb_db_t *db,
              psb_batch_t **out);
 /* the same scan for a database that lives in HOST memory (pinned or pageable): the residues are cut
@@ -289,6 +308,12 @@ int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, i
  * host-to-device copy hides under the kernels.  Nothing stays resident afterwards. */
 int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
                   const int64_t *off, int64_t n, psb_batch_t **out);
+/* the whole box in one call from one process: the host database is cut into n_gpus contiguous ranges of
+ * equal residue count, one resident worker thread per device runs the pipelined host scan of its range
+ * straight out of / into the caller-order arrays, and ONE batch comes back in the caller's subject order.
+ * n_gpus <= 0 means every visible device.  No collective is involved. */
+int psb_scan_box(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
+                 const int64_t *off, int64_t n, int n_gpus, psb_batch_t **out);
 /* indices (caller order) of the k best scores of a scan, ties by smaller index; host-side merge */
 int psb_batch_topk(const psb_batch_t *batch, int k, int64_t *idx_out, int *score_out);
 

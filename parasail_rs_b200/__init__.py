@@ -437,15 +437,33 @@ def _concat(seqs):
 class Database:
     """a subject database resident on the current GPU, bit-packed and length-sorted on the device"""
 
-    def __init__(self, subjects, matrix):
-        cat, off = _concat(subjects)
+    def __init__(self, subjects, matrix, _inner=None):
         self._keep = matrix
-        self.n = len(off) - 1
-        self.inner = lib().psb_db_create(cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), self.n, matrix.inner)
+        if _inner is None:
+            cat, off = _concat(subjects)
+            _inner = lib().psb_db_create(cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(off) - 1, matrix.inner)
+        self.inner = _inner
         if not self.inner:
             raise DeviceError(last_error())
+        self.n = int(lib().psb_db_count(self.inner))
         self.residues = int(lib().psb_db_residues(self.inner))
         self.device_bytes = int(lib().psb_db_device_bytes(self.inner))
+        self.bits = int(lib().psb_db_bits(self.inner))
+
+    @staticmethod
+    def from_fasta(path, matrix):
+        """FASTA file -> resident packed database (psb_db_from_fasta)"""
+        return Database(None, matrix, _inner=lib().psb_db_from_fasta(str(path).encode(), matrix.inner) or 0)
+
+    @staticmethod
+    def load(path, matrix):
+        """a database saved with save(): no sorting or packing, one upload (psb_db_load)"""
+        return Database(None, matrix, _inner=lib().psb_db_load(str(path).encode(), matrix.inner) or 0)
+
+    def save(self, path):
+        rc = lib().psb_db_save(self.inner, str(path).encode())
+        if rc != 0:
+            raise Error(f"psb_db_save failed ({rc}): {last_error()}")
 
     def __del__(self):
         try:
@@ -656,6 +674,42 @@ def _scan_host(self, subjects):
 
 
 Aligner.scan_host = _scan_host
+
+
+def _scan_box(self, subjects, n_gpus=0):
+    """the aligner's profile against a host database over n_gpus devices of this box from ONE process
+    (psb_scan_box): contiguous residue-balanced ranges, one worker thread per device, caller-order results"""
+    if self._profile.is_null():
+        raise Panic("scan_box() needs an aligner built with .profile(...)")
+    cat, off = _concat(subjects)
+    out = C.POINTER(CBatch)()
+    rc_ = lib().psb_scan_box(self.fn_name.encode(), self._profile.inner, self.gap_open, self.gap_extend,
+                             cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(off) - 1, int(n_gpus), C.byref(out))
+    if rc_ != 0:
+        raise DeviceError(f"psb_scan_box failed ({rc_}): {last_error()}")
+    return BatchResult(out)
+
+
+Aligner.scan_box = _scan_box
+
+
+def read_fasta(path):
+    """FASTA file -> (residues uint8 array, int64 offsets, list of header lines) (psb_fasta_read)"""
+    fa = lib().psb_fasta_read(str(path).encode())
+    if not fa:
+        raise Error(last_error())
+    try:
+        n = int(lib().psb_fasta_count(fa))
+        off = np.ctypeslib.as_array(lib().psb_fasta_offsets(fa), shape=(n + 1,)).copy()
+        cat = np.ctypeslib.as_array(lib().psb_fasta_residues(fa), shape=(int(off[-1]),)).copy() if off[-1] else np.zeros(0, dtype=np.uint8)
+        names = []
+        ln = C.c_int()
+        for i in range(n):
+            ptr = lib().psb_fasta_name(fa, i, C.byref(ln))
+            names.append(C.string_at(ptr, ln.value).decode(errors="replace") if ptr and ln.value else "")
+        return cat, off, names
+    finally:
+        lib().psb_fasta_free(fa)
 
 
 def shard_plan(offsets, n_shards):

@@ -168,11 +168,34 @@ def lib():
     L.psb_db_device_bytes.argtypes = [C.c_void_p]
     L.psb_db_free.restype = None
     L.psb_db_free.argtypes = [C.c_void_p]
+    L.psb_db_bits.restype = C.c_int
+    L.psb_db_bits.argtypes = [C.c_void_p]
+    L.psb_fasta_read.restype = C.c_void_p
+    L.psb_fasta_read.argtypes = [C.c_char_p]
+    L.psb_fasta_count.restype = C.c_int64
+    L.psb_fasta_count.argtypes = [C.c_void_p]
+    L.psb_fasta_residues.restype = C.POINTER(C.c_uint8)
+    L.psb_fasta_residues.argtypes = [C.c_void_p]
+    L.psb_fasta_offsets.restype = C.POINTER(C.c_int64)
+    L.psb_fasta_offsets.argtypes = [C.c_void_p]
+    L.psb_fasta_name.restype = C.c_void_p
+    L.psb_fasta_name.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int)]
+    L.psb_fasta_free.restype = None
+    L.psb_fasta_free.argtypes = [C.c_void_p]
+    L.psb_db_from_fasta.restype = C.c_void_p
+    L.psb_db_from_fasta.argtypes = [C.c_char_p, C.POINTER(CMatrix)]
+    L.psb_db_save.restype = C.c_int
+    L.psb_db_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.psb_db_load.restype = C.c_void_p
+    L.psb_db_load.argtypes = [C.c_char_p, C.POINTER(CMatrix)]
     L.psb_scan.restype = C.c_int
     L.psb_scan.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.POINTER(CBatch))]
     L.psb_scan_host.restype = C.c_int
     L.psb_scan_host.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.POINTER(C.POINTER(CBatch))]
+    L.psb_scan_box.restype = C.c_int
+    L.psb_scan_box.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                               C.POINTER(C.POINTER(CBatch))]
     L.psb_batch_topk.restype = C.c_int
     L.psb_batch_topk.argtypes = [C.POINTER(CBatch), C.c_int, C.c_void_p, C.c_void_p]
     L.psb_shard_plan.restype = C.c_int

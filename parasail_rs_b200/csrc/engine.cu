@@ -18,7 +18,10 @@
 #include <map>
 #include <mutex>
 #include <numeric>
+#include <condition_variable>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kern_gotoh32.cuh"
@@ -26,6 +29,7 @@
 #include "kern_util.cuh"
 #include "kern_wave32.cuh"
 #include "pairs16_host.h"
+#include "psb_db.h"
 #include "psb_internal.h"
 
 namespace psb {
@@ -906,24 +910,6 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
 // ---- resident database ----------------------------------------------------------------------------
 }  // namespace psb
 
-struct psb_db {
-    int device = 0;
-    cudaStream_t stream = nullptr;  // stream the buffers were allocated on (stream-ordered pool)
-    int64_t n = 0, residues = 0, words = 0;
-    int bits = 5;
-    int msize = 0;
-    int maxlen = 0;                 // longest subject
-    int nlong = 0;                  // subjects longer than 65535 (sorted first)
-    std::vector<int> top_len;       // lengths of the (up to 4096) longest subjects, descending
-    std::vector<int> host_len;      // caller-order lengths (psb_db_create only; explicit-width saturation flags)
-    uint8_t mapper[256];
-    unsigned *d_words = nullptr;
-    long long *d_word_off = nullptr;  // n+1, sorted order (length descending, stable)
-    int *d_perm = nullptr;            // sorted position -> caller's subject id
-    int *d_len = nullptr;             // sorted order
-    std::mutex mu;
-};
-
 namespace psb {
 
 struct DevProfile {
@@ -1243,6 +1229,15 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
 
 }  // namespace psb
 
+namespace psb {
+int db_io_ensure_ctx(int *device, cudaStream_t *stream) {
+    const int rc = ensure_ctx();
+    if (rc != PSB_OK) return rc;
+    *device = g_ctx.device; *stream = g_ctx.stream;
+    return PSB_OK;
+}
+}  // namespace psb
+
 using namespace psb;
 
 extern "C" {
@@ -1383,14 +1378,15 @@ struct DbBuild {
     }
 };
 
-static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int64_t n, const HostMatrix &hm, bool use_copy_stream) {
+static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int64_t n, const HostMatrix &hm, bool use_copy_stream, int force_bits = 0) {
     Ctx &c = g_ctx;
     if (hm.size > 32) { set_error("psb_db_create: alphabets above 32 letters cannot be 5-bit packed"); return nullptr; }
     psb_db *db = new psb_db();
     db->device = c.device; db->stream = c.stream; db->n = n; db->msize = hm.size;
     std::memcpy(db->mapper, hm.mapper, 256);
-    db->bits = hm.size <= 4 ? 2 : 5;
-    const int rpw = db->bits == 2 ? 16 : 6;
+    // 2 bit for alphabets of up to 4 letters, 3 bit up to 8 (ACGT + wildcard: DNA ships at 3 bit), else 5
+    db->bits = force_bits ? force_bits : db_bits_for(hm.size);
+    const int rpw = db_residues_per_word(db->bits);
     db->residues = off[n] - off[0];
     auto fail = [&](const std::string &what) {
         set_error(what);
@@ -1456,7 +1452,7 @@ static int db_finish(DbBuild &B) {
     psb_db *db = B.db;
     const int64_t n = db->n;
     const size_t n1 = (size_t)n + 1;
-    const int rpw = db->bits == 2 ? 16 : 6;
+    const int rpw = db_residues_per_word(db->bits);
     if (B.uploaded) PSB_CUDA(cudaStreamWaitEvent(c.stream, B.uploaded, 0));
     db_lengths_kernel<<<c.sms * 4, 256, 0, c.stream>>>(B.offs(), n, B.d_len0.as<int>(), B.d_idx0.as<int>());
     size_t tb = 0, tb2 = 0;
@@ -1488,8 +1484,16 @@ psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const
     if (off[n] <= off[0]) { set_error("psb_db_create: offsets are not increasing"); return nullptr; }
     if (ensure_ctx() != PSB_OK) return nullptr;
     HostMatrix hm(matrix);
+    // bits per residue from the residues actually present: a DNA database whose residues are all A/C/G/T
+    // (no wildcard, which maps to column 4) packs at 2 bit even though its matrix has 5 columns
+    int force_bits = 0;
+    if (db_bits_for(hm.size) == 3) {
+        bool small = true;
+        for (int64_t x = off[0]; x < off[n] && small; ++x) small = hm.mapper[cat[x]] < 4;
+        if (small) force_bits = 2;
+    }
     DbBuild B;
-    psb_db *db = db_begin(B, cat, off, n, hm, false);
+    psb_db *db = db_begin(B, cat, off, n, hm, false, force_bits);
     if (!db) return nullptr;
     // the caller's buffers must be free to go when this returns: wait for the uploads (not for the packing)
     cudaEvent_t up = nullptr;
@@ -1503,6 +1507,7 @@ psb_db_t *psb_db_create(const uint8_t *cat, const int64_t *off, int64_t n, const
 }
 
 int64_t psb_db_count(const psb_db_t *db) { return db ? db->n : 0; }
+int psb_db_bits(const psb_db_t *db) { return db ? db->bits : 0; }
 int64_t psb_db_residues(const psb_db_t *db) { return db ? db->residues : 0; }
 int64_t psb_db_device_bytes(const psb_db_t *db) {
     return db ? db->words * 4 + (db->n + 1) * 8 + db->n * 8 : 0;
@@ -1620,16 +1625,16 @@ int psb_scan(const char *fn_name, const parasail_profile_t *profile, int open, i
     return PSB_OK;
 }
 
-int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
-                  const int64_t *off, int64_t n, psb_batch_t **out) {
-    if (out) *out = nullptr;
-    FnConfig cfg;
-    PSB_TRY(scan_check("psb_scan_host", fn_name, profile, &cfg));
-    if (!cat || !off || n <= 0 || !out || off[n] <= off[0]) { set_error("psb_scan_host: NULL argument or empty database"); return PSB_EINVAL; }
-    if (n > 0x7ffffffe) { set_error("psb_scan_host: more than 2^31-2 subjects"); return PSB_EUNSUPPORTED; }
-    PSB_TRY(ensure_ctx());
+}  // extern "C"
+
+namespace psb {
+// The scan of a database that lives in HOST memory, on the calling thread's device: the residues are cut
+// into pieces whose upload (copy stream), device-side sort + packing and scan are pipelined, and the
+// per-subject results land in hosts[k][base ...] (pinned).  Used by psb_scan_host (one device, base 0) and by
+// the per-device workers of psb_scan_box (each with its own range of the caller's arrays).
+static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
+                          const int64_t *off, int64_t n, int *const hosts[6], int64_t base, int64_t *n_retried) {
     Ctx &c = g_ctx;
-    c.last_ms = 0.0; c.launches = 0;
     const HostMatrix &hm = profile->matrix;
     // pieces: the upload of piece k+1 (copy stream) runs under the scan of piece k, and nothing on the
     // host waits for the GPU until the last piece is queued.  The first piece is small so the scan
@@ -1650,10 +1655,6 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
         cut[k] = std::lower_bound(off, off + n + 1, target) - off;
         if (cut[k] <= cut[k - 1]) cut[k] = std::min<int64_t>(n, cut[k - 1] + 1);
     }
-    psb_batch_t *b = new_batch(n, cfg);
-    if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
-    b->cells = (double)profile->query.size() * (double)total;
-    int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
     int rc = PSB_OK;
     std::vector<std::unique_ptr<DbBuild>> builds(npieces);
     std::vector<std::unique_ptr<ScanJob>> jobs(npieces);
@@ -1668,7 +1669,7 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
     auto retire = [&](int k) -> int {
         if (k < 0 || !jobs[k]) return PSB_OK;
         int r = PSB_OK;
-        if (jobs[k]->ev0) { r = scan_finish(*jobs[k]); b->n_retried += jobs[k]->retried; }
+        if (jobs[k]->ev0) { r = scan_finish(*jobs[k]); *n_retried += jobs[k]->retried; }
         if (builds[k] && builds[k]->db) { psb_db_free(builds[k]->db); builds[k]->db = nullptr; }
         jobs[k].reset(); builds[k].reset();
         return r;
@@ -1677,12 +1678,12 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
     const auto t_in = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count(); };
     rc = begin(0);
-    if (dbg) std::fprintf(stderr, "[psb] scan_host: %d pieces, first upload queued at %.3f ms\n", npieces, since());
+    if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): %d pieces, first upload queued at %.3f ms\n", c.device, npieces, since());
     for (int k = 0; k < npieces && rc == PSB_OK; ++k) {
         if (!builds[k]->db) continue;
         rc = db_finish(*builds[k]);
-        if (rc == PSB_OK) rc = scan_enqueue(*jobs[k], cfg, profile, open, gap, builds[k]->db, hosts, cut[k]);
-        if (dbg) std::fprintf(stderr, "[psb] scan_host: piece %d queued at %.3f ms\n", k, since());
+        if (rc == PSB_OK) rc = scan_enqueue(*jobs[k], cfg, profile, open, gap, builds[k]->db, hosts, base + cut[k]);
+        if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): piece %d queued at %.3f ms\n", c.device, k, since());
         // while this piece is being scanned: host pass over the next piece's offsets and its upload
         if (rc == PSB_OK && k + 1 < npieces) {
             if (k + 1 >= kDepth) rc = retire(k + 1 - kDepth);
@@ -1690,19 +1691,155 @@ int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int op
         }
     }
     cudaStreamSynchronize(c.copy);
-    if (dbg) std::fprintf(stderr, "[psb] scan_host: uploads done at %.3f ms\n", since());
+    if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): uploads done at %.3f ms\n", c.device, since());
     cudaStreamSynchronize(c.stream);
-    if (dbg) std::fprintf(stderr, "[psb] scan_host: all done at %.3f ms\n", since());
+    if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): all done at %.3f ms\n", c.device, since());
     for (int k = 0; k < npieces; ++k) {
         const int r = retire(k);
         if (rc == PSB_OK) rc = r;
     }
+    return rc;
+}
+
+static void flag_saturated(const FnConfig &cfg, const HostMatrix &hm, int lq, const int64_t *off, int64_t n, int open, int gap, psb_batch_t *b) {
+    if (cfg.width != 8 && cfg.width != 16) return;
+    for (int64_t i = 0; i < n; ++i)
+        if (saturates(cfg, hm, b->score[i], lq, (int)(off[i + 1] - off[i]), open, gap)) {
+            b->saturated[i] = 1; b->score[i] = 0; b->end_query[i] = 0; b->end_ref[i] = 0;
+        }
+}
+
+// ---- one worker thread per device for psb_scan_box: the thread keeps its context (streams, memory pool,
+// staging blocks) warm across calls -----------------------------------------------------------------------
+struct BoxWorker {
+    int device = 0;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, quit = false;
+    void loop() {
+        psb_set_device(device);
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            std::function<void()> j = std::move(job);
+            lk.unlock();
+            j();
+            lk.lock();
+            has_job = false;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<void()> j) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !has_job; });
+        job = std::move(j); has_job = true;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !has_job; });
+    }
+};
+static std::mutex g_box_mu;
+static std::vector<BoxWorker *> g_box;   // index = device; never destroyed (the threads live as long as the process)
+static BoxWorker *box_worker(int device) {
+    std::lock_guard<std::mutex> lk(g_box_mu);
+    if ((int)g_box.size() <= device) g_box.resize(device + 1, nullptr);
+    if (!g_box[device]) {
+        BoxWorker *w = new BoxWorker();
+        w->device = device;
+        w->th = std::thread([w] { w->loop(); });
+        w->th.detach();
+        g_box[device] = w;
+    }
+    return g_box[device];
+}
+}  // namespace psb
+
+extern "C" {
+
+int psb_scan_host(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
+                  const int64_t *off, int64_t n, psb_batch_t **out) {
+    if (out) *out = nullptr;
+    FnConfig cfg;
+    PSB_TRY(scan_check("psb_scan_host", fn_name, profile, &cfg));
+    if (!cat || !off || n <= 0 || !out || off[n] <= off[0]) { set_error("psb_scan_host: NULL argument or empty database"); return PSB_EINVAL; }
+    if (n > 0x7ffffffe) { set_error("psb_scan_host: more than 2^31-2 subjects"); return PSB_EUNSUPPORTED; }
+    PSB_TRY(ensure_ctx());
+    Ctx &c = g_ctx;
+    c.last_ms = 0.0; c.launches = 0;
+    psb_batch_t *b = new_batch(n, cfg);
+    if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
+    b->cells = (double)profile->query.size() * (double)(off[n] - off[0]);
+    int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
+    const int rc = scan_host_into(cfg, profile, open, gap, cat, off, n, hosts, 0, &b->n_retried);
     if (rc != PSB_OK) { free_batch(b); return rc; }
-    if (cfg.width == 8 || cfg.width == 16)
-        for (int64_t i = 0; i < n; ++i)
-            if (saturates(cfg, hm, b->score[i], (int)profile->query.size(), (int)(off[i + 1] - off[i]), open, gap)) {
-                b->saturated[i] = 1; b->score[i] = 0; b->end_query[i] = 0; b->end_ref[i] = 0;
+    flag_saturated(cfg, profile->matrix, (int)profile->query.size(), off, n, open, gap, b);
+    *out = b;
+    return PSB_OK;
+}
+
+// The whole box from one process and one call: the database is cut into n_gpus contiguous
+// ranges of equal residue count (contiguous, so every device uploads straight from the caller's arrays and
+// writes straight into the caller-order result arrays -- no gather on either side), one resident worker
+// thread per device runs the pipelined host scan on its range, and the call returns ONE batch in the
+// caller's subject order.  No data-path collective: the ranges are independent.
+int psb_scan_box(const char *fn_name, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
+                 const int64_t *off, int64_t n, int n_gpus, psb_batch_t **out) {
+    if (out) *out = nullptr;
+    FnConfig cfg;
+    PSB_TRY(scan_check("psb_scan_box", fn_name, profile, &cfg));
+    if (!cat || !off || n <= 0 || !out || off[n] <= off[0]) { set_error("psb_scan_box: NULL argument or empty database"); return PSB_EINVAL; }
+    if (n > 0x7ffffffe) { set_error("psb_scan_box: more than 2^31-2 subjects"); return PSB_EUNSUPPORTED; }
+    const int ndev = psb_device_count();
+    if (ndev <= 0) { set_error("no CUDA device available: libparasail_b200 has no CPU fallback (needs an sm_100a GPU)"); return PSB_ENODEV; }
+    if (n_gpus <= 0 || n_gpus > ndev) n_gpus = ndev;
+    if ((int64_t)n_gpus > n) n_gpus = (int)n;
+    PSB_TRY(ensure_ctx());   // the batch's pinned arrays are allocated by the calling thread
+    psb_batch_t *b = new_batch(n, cfg);
+    if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
+    const int64_t total = off[n] - off[0];
+    b->cells = (double)profile->query.size() * (double)total;
+    std::vector<int64_t> cut(n_gpus + 1, n);
+    cut[0] = 0;
+    for (int d = 1; d < n_gpus; ++d) {
+        cut[d] = std::lower_bound(off, off + n + 1, off[0] + total * d / n_gpus) - off;
+        if (cut[d] <= cut[d - 1]) cut[d] = std::min<int64_t>(n, cut[d - 1] + 1);
+    }
+    int *hosts[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
+    std::vector<int> rcs(n_gpus, PSB_OK), launches(n_gpus, 0);
+    std::vector<int64_t> retried(n_gpus, 0);
+    std::vector<double> ms(n_gpus, 0.0);
+    std::vector<std::string> errs(n_gpus);
+    for (int d = 0; d < n_gpus; ++d) {
+        if (cut[d + 1] <= cut[d]) continue;
+        box_worker(d)->submit([&, d] {
+            int rc = ensure_ctx();
+            if (rc == PSB_OK) {
+                g_ctx.last_ms = 0.0; g_ctx.launches = 0;
+                rc = scan_host_into(cfg, profile, open, gap, cat, off + cut[d], cut[d + 1] - cut[d], hosts, cut[d], &retried[d]);
+                ms[d] = g_ctx.last_ms; launches[d] = g_ctx.launches;
             }
+            rcs[d] = rc;
+            if (rc != PSB_OK) errs[d] = psb_last_error();
+        });
+    }
+    int rc = PSB_OK;
+    Ctx &c = g_ctx;
+    c.last_ms = 0.0; c.launches = 0;
+    for (int d = 0; d < n_gpus; ++d) {
+        if (cut[d + 1] <= cut[d]) continue;
+        box_worker(d)->wait();
+        if (rcs[d] != PSB_OK && rc == PSB_OK) { rc = rcs[d]; set_error("psb_scan_box (device " + std::to_string(d) + "): " + errs[d]); }
+        b->n_retried += retried[d];
+        c.last_ms = std::max(c.last_ms, ms[d]);   // the devices run side by side: the slowest one
+        c.launches += launches[d];
+    }
+    if (rc != PSB_OK) { free_batch(b); return rc; }
+    flag_saturated(cfg, profile->matrix, (int)profile->query.size(), off, n, open, gap, b);
     *out = b;
     return PSB_OK;
 }

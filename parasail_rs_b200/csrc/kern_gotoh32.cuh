@@ -53,7 +53,7 @@ struct Gotoh32Params {
     const unsigned *r_words;    // packed residues (kern_util.cuh layout), NULL for byte subjects
     const long long *r_word_off;  // first word of each subject (indexed by pair id)
     const int *r_len;           // residues of each subject
-    int r_bits;                 // 5 or 2
+    int r_bits;                 // 5, 3 or 2
     const int *n_dev;           // when set, the number of work items is read from device memory
     // parasail_nw_banded (coarse family only): cell (i, j) is reachable iff band_lo <= j - i <= band_hi
     int banded, band_lo, band_hi;
@@ -200,10 +200,16 @@ PSB_KERNEL void gotoh32_kernel(Gotoh32Params p) {
                     const int c = s + lane;
                     if (c < Lr) {
                         if (packed) {
-                            const unsigned word = p.r_bits == 2 ? p.r_words[ro + (c >> 4)]
-                                                                : p.r_words[ro + (int)(((unsigned long long)(unsigned)c * 0xAAAAAAABull) >> 34)];
-                            const int within = p.r_bits == 2 ? (c & 15) : c - 6 * (int)(((unsigned long long)(unsigned)c * 0xAAAAAAABull) >> 34);
-                            ringL[c & 63] = (uint8_t)((word >> (p.r_bits * within)) & ((1u << p.r_bits) - 1u));
+                            unsigned code;
+                            if (p.r_bits == 2) code = (p.r_words[ro + (c >> 4)] >> (2 * (c & 15))) & 3u;
+                            else if (p.r_bits == 3) {
+                                const int w = (int)(((unsigned long long)(unsigned)c * 0xCCCCCCCDull) >> 35);   // c / 10
+                                code = (p.r_words[ro + w] >> (3 * (c - 10 * w))) & 7u;
+                            } else {
+                                const int w = (int)(((unsigned long long)(unsigned)c * 0xAAAAAAABull) >> 34);   // c / 6
+                                code = (p.r_words[ro + w] >> (5 * (c - 6 * w))) & 31u;
+                            }
+                            ringL[c & 63] = (uint8_t)code;
                         } else {
                             ringL[c & 63] = r[c];
                         }

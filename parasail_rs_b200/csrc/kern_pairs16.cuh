@@ -459,8 +459,15 @@ struct Walk16Params {
     int *matches, *similar, *length;
 };
 
+// dynamic shared memory: size*size ints (the substitution matrix)
+inline size_t walk16_smem_bytes(int size) { return (size_t)size * size * sizeof(int); }
+
 template <bool STATS>
 PSB_KERNEL void walk16_kernel(Walk16Params p) {
+    PSB_SHARED_DECL(smem_raw);
+    int *smat = (int *)smem_raw;
+    for (int x = thread_in_block(); x < p.size * p.size; x += threads_per_block()) smat[x] = p.matrix[x];
+    sync_block();
     const long long tid = (long long)block_id() * threads_per_block() + thread_in_block();
     if (tid >= p.n) return;
     const int pid = p.pair_ids[tid];
@@ -471,16 +478,17 @@ PSB_KERNEL void walk16_kernel(Walk16Params p) {
     const uint8_t *q = p.q + qo;
     const uint8_t *r = p.r + p.r_off[pid];
     const int G = p.G, K = p.K, TW = (((K + 1) / 2) + 1) & ~1;   // = pairs16_trace_words(K)
+    const int TWB = TW * 4;
     const int pad = G * K - Lq;
     const int o = p.open, e = p.gap;
-    const uint8_t *tr = (const uint8_t *)(p.trace + p.trace_off[item]);
+    const uint8_t *tr = (const uint8_t *)(p.trace + p.trace_off[item]) + half;
     unsigned *out = STATS ? nullptr : p.rev_ops + p.rev_off[pid];
-    // exact H of cell (i, j) from its stored byte and the exact value `ref` of a neighbouring cell
-    auto cell = [&](int i, int j, int ref) -> int {
+    // byte of cell (i, j); exact H from a byte and the exact value `ref` of a neighbouring cell
+    auto load = [&](int i, int j) -> unsigned {
         const int il = i + pad, t = il / K, k = il - t * K;
-        const unsigned byte = tr[((long long)(j + t) * G + t) * (TW * 4) + 2 * k + half];
-        return ref + (int)(signed char)(unsigned char)(byte - (unsigned)ref);
+        return tr[((long long)(j + t) * G + t) * TWB + 2 * k];
     };
+    auto recon = [](unsigned byte, int ref) -> int { return ref + (int)(signed char)(unsigned char)(byte - (unsigned)ref); };
     auto top = [&](int j) -> int { return (j < 0 || p.top_free) ? 0 : -o - j * e; };     // H[-1][j], corner 0
     auto left = [&](int i) -> int { return (i < 0 || p.left_free) ? 0 : -o - i * e; };   // H[i][-1]
     int i = p.end_query[pid], j = p.end_ref[pid];
@@ -496,7 +504,9 @@ PSB_KERNEL void walk16_kernel(Walk16Params p) {
             cur = op; len = (unsigned)count;
         }
     };
-    while (i >= 0 || j >= 0) {
+    constexpr int D = 8;   // loads in flight per round trip
+    bool done = false;
+    while (!done && (i >= 0 || j >= 0)) {
         if (i < 0 || j < 0) {
             // off the table: statistics stop here (boundary gaps are not counted); the CIGAR takes the rest of
             // the other sequence as one run (rules::CIGAR_WALK_TO_ORIGIN)
@@ -504,32 +514,65 @@ PSB_KERNEL void walk16_kernel(Walk16Params p) {
             else { emit((int)rules::CIGAR_OP_I, i + 1); i = -1; }
             break;
         }
-        if (p.is_sw && v <= 0) break;   // ZERO: the alignment starts after this cell
-        const int a = q[i], b = r[j];
-        const int sub = p.matrix[a * p.size + b];
-        // the diagonal wins ties: taken iff H[i-1][j-1] + S == H[i][j]
-        const int hd = i == 0 ? top(j - 1) : (j == 0 ? left(i - 1) : cell(i - 1, j - 1, v - sub));
-        if (hd + sub == v) {
-            emit((a == b) ? (int)rules::CIGAR_OP_EQ : (int)rules::CIGAR_OP_X, 1);
-            nm += (a == b); ns += (sub > 0); ++nl;
-            v = hd; --i; --j;
-            continue;
+        // ---- a run of diagonal steps: the next D cells of the diagonal are fetched together --------------
+        unsigned hb[D], qa[D], rb[D];
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            const bool in = i - m >= 0 && j - m >= 0;
+            qa[m] = in ? q[i - m] : 0u;
+            rb[m] = in ? r[j - m] : 0u;
+            hb[m] = (i - m - 1 >= 0 && j - m - 1 >= 0) ? load(i - m - 1, j - m - 1) : 0u;
         }
-        // vertical gap (F wins ties over E): the largest k with H[i-k][j] - o - (k-1)e == H[i][j]
-        int kbest = 0, vbest = 0, u = v;
-        for (int k = 1; k <= i + 1; ++k) {
-            u = (i - k < 0) ? top(j) : cell(i - k, j, u);
-            if (u - o - (k - 1) * e == v) { kbest = k; vbest = u; if (rules::GAP_OPEN_ON_TIE) break; }
+        bool gap_here = false;
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            if (gap_here || done) break;
+            if (i < 0 || j < 0) break;
+            if (p.is_sw && v <= 0) { done = true; break; }   // ZERO: the alignment starts after this cell
+            const int a = (int)qa[m], b = (int)rb[m];
+            const int sub = smat[a * p.size + b];
+            // the diagonal wins ties: taken iff H[i-1][j-1] + S == H[i][j]
+            const int hd = i == 0 ? top(j - 1) : (j == 0 ? left(i - 1) : recon(hb[m], v - sub));
+            if (hd + sub == v) {
+                emit((a == b) ? (int)rules::CIGAR_OP_EQ : (int)rules::CIGAR_OP_X, 1);
+                nm += (a == b); ns += (sub > 0); ++nl;
+                v = hd; --i; --j;
+            } else gap_here = true;
+        }
+        if (!gap_here || done) continue;
+        // ---- vertical gap (F wins ties over E): the largest k with H[i-k][j] - o - (k-1)e == H[i][j] --------
+        int kbest = 0, vbest = 0, u = v, k = 1;
+        while (k <= i + 1) {
+            unsigned bt[D];
+#pragma unroll
+            for (int m = 0; m < D; ++m) bt[m] = (i - k - m >= 0) ? load(i - k - m, j) : 0u;
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                if (k > i + 1) break;
+                u = (i - k < 0) ? top(j) : recon(bt[m], u);
+                if (u - o - (k - 1) * e == v) { kbest = k; vbest = u; }
+                ++k;
+            }
+            if (rules::GAP_OPEN_ON_TIE && kbest) break;
         }
         if (kbest) {
             emit((int)rules::CIGAR_OP_I, kbest);
             nl += kbest; i -= kbest; v = vbest;
             continue;
         }
-        u = v;
-        for (int k = 1; k <= j + 1; ++k) {
-            u = (j - k < 0) ? left(i) : cell(i, j - k, u);
-            if (u - o - (k - 1) * e == v) { kbest = k; vbest = u; if (rules::GAP_OPEN_ON_TIE) break; }
+        u = v; k = 1;
+        while (k <= j + 1) {
+            unsigned bt[D];
+#pragma unroll
+            for (int m = 0; m < D; ++m) bt[m] = (j - k - m >= 0) ? load(i, j - k - m) : 0u;
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                if (k > j + 1) break;
+                u = (j - k < 0) ? left(i) : recon(bt[m], u);
+                if (u - o - (k - 1) * e == v) { kbest = k; vbest = u; }
+                ++k;
+            }
+            if (rules::GAP_OPEN_ON_TIE && kbest) break;
         }
         if (!kbest) break;   // cannot happen for a table the fill produced
         emit((int)rules::CIGAR_OP_D, kbest);

@@ -132,7 +132,7 @@ struct Sw16Params {
     const unsigned *words;        // packed database (sorted by length, descending)
     const long long *word_off;    // n+1
     const int *len;               // n
-    int bits;                     // 5 or 2
+    int bits;                     // 5, 3 or 2
     long long n;                  // subjects; work item w = subjects 2w and 2w+1
     const int *out_map;           // sorted position -> caller's subject id
     int *score, *end_query, *end_ref;
@@ -154,6 +154,10 @@ inline size_t sw16_smem_bytes(int nletters, int K, int warps) {
 PSB_DEV unsigned sw16_fetch_code(const unsigned *words, long long w0, int len, int c, int bits, int pad_code) {
     if (c >= len) return (unsigned)pad_code;
     if (bits == 2) return (words[w0 + (c >> 4)] >> (2 * (c & 15))) & 3u;
+    if (bits == 3) {
+        const int w = (int)(((unsigned long long)(unsigned)c * 0xCCCCCCCDull) >> 35);  // c / 10
+        return (words[w0 + w] >> (3 * (c - 10 * w))) & 7u;
+    }
     const int w = (int)(((unsigned long long)(unsigned)c * 0xAAAAAAABull) >> 34);  // c / 6
     return (words[w0 + w] >> (5 * (c - 6 * w))) & 31u;
 }

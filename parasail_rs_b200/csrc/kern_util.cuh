@@ -21,9 +21,19 @@ PSB_KERNEL void map_residues_kernel(MapParams p) {
 }
 
 // ---- database packing -----------------------------------------------------------------------
-// A subject is stored as 32-bit words of RPW residues of BITS bits each (5 bit: 6 per word,
-// 2 bit: 16 per word), first residue in the low bits, each subject starting on a fresh word.
-PSB_DEV constexpr int residues_per_word(int bits) { return bits == 2 ? 16 : 6; }
+// A subject is stored as 32-bit words of RPW residues of BITS bits each (5 bit: 6 per word, 3 bit: 10 per
+// word, 2 bit: 16 per word), first residue in the low bits, each subject starting on a fresh word.
+PSB_DEV constexpr int residues_per_word(int bits) { return bits == 2 ? 16 : (bits == 3 ? 10 : 6); }
+// residue c of a packed subject whose first word is words[w0]
+PSB_DEV unsigned packed_residue(const unsigned *words, long long w0, int c, int bits) {
+    if (bits == 2) return (words[w0 + (c >> 4)] >> (2 * (c & 15))) & 3u;
+    if (bits == 3) {
+        const int w = (int)(((unsigned long long)(unsigned)c * 0xCCCCCCCDull) >> 35);   // c / 10
+        return (words[w0 + w] >> (3 * (c - 10 * w))) & 7u;
+    }
+    const int w = (int)(((unsigned long long)(unsigned)c * 0xAAAAAAABull) >> 34);       // c / 6
+    return (words[w0 + w] >> (5 * (c - 6 * w))) & 31u;
+}
 
 struct PackParams {
     const uint8_t *raw;          // original residues (caller order), unmapped

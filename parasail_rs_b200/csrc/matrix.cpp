@@ -125,7 +125,28 @@ const parasail_matrix_t *parasail_matrix_lookup(const char *matrixname) {
     if (!matrixname) return nullptr;
     std::string nm(matrixname);
     for (auto &c : nm) c = (char)std::tolower((unsigned char)c);
-    if (nm != "blosum62") return nullptr;  // other tables: values unavailable here
+    if (nm != "blosum62") {
+        // The other built-in tables of upstream (blosum*/pam*/dnafull/nuc44 ...) exist nowhere in this
+        // environment and are not fabricated from memory.  The lookup is data-driven instead:
+        // a file <PSB_MATRIX_DIR>/<name>[.txt|.mat] in NCBI format (what parasail_matrix_from_file parses)
+        // is loaded once and then lives as long as the process, like a built-in.
+        const char *dir = std::getenv("PSB_MATRIX_DIR");
+        if (!dir || !*dir || nm.find('/') != std::string::npos || nm.find("..") != std::string::npos) return nullptr;
+        static std::mutex mu;
+        static std::map<std::string, const parasail_matrix_t *> cache;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(nm);
+        if (it != cache.end()) return it->second;
+        const parasail_matrix_t *found = nullptr;
+        for (const char *ext : {"", ".txt", ".mat"}) {
+            const std::string path = std::string(dir) + "/" + nm + ext;
+            parasail_matrix_t *m = parasail_matrix_from_file(path.c_str());
+            if (m && m->type == PARASAIL_MATRIX_TYPE_SQUARE) { found = m; break; }
+            if (m) parasail_matrix_free(m);
+        }
+        cache[nm] = found;
+        return found;
+    }
     std::call_once(g_blosum62_once, []() {
         fill_mapper(g_blosum62_mapper, kBlosum62Alphabet, 24);
         g_blosum62.name = "blosum62";

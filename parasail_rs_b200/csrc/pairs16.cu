@@ -91,8 +91,9 @@ int p16_launch(int cls, bool sw, bool trace, const Pairs16Params &p, int sms, cu
 
 int p16_launch_walk(const Walk16Params &w, bool stats, cudaStream_t stream, std::string *err) {
     if (w.n <= 0) return PSB_OK;
-    if (stats) walk16_kernel<true><<<(unsigned)((w.n + 127) / 128), 128, 0, stream>>>(w);
-    else walk16_kernel<false><<<(unsigned)((w.n + 127) / 128), 128, 0, stream>>>(w);
+    const size_t smem = walk16_smem_bytes(w.size);
+    if (stats) walk16_kernel<true><<<(unsigned)((w.n + 127) / 128), 128, smem, stream>>>(w);
+    else walk16_kernel<false><<<(unsigned)((w.n + 127) / 128), 128, smem, stream>>>(w);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("walk16 launch: ") + cudaGetErrorString(e); return PSB_ECUDA; }
     return PSB_OK;

@@ -161,8 +161,8 @@ extern "C" int emu_pairs16(int G, int K, int mode, int s1_beg, int s1_end, int s
         w.open = open; w.gap = gap; w.is_sw = sw ? 1 : 0; w.top_free = top_free ? 1 : 0; w.left_free = (sw || (mode == MODE_SG && s2_beg)) ? 1 : 0; w.score = score; w.end_query = end_query; w.end_ref = end_ref;
         w.rev_ops = rev_ops; w.rev_off = rev_off; w.nops = nops; w.beg_query = beg_query; w.beg_ref = beg_ref;
         w.matches = matches; w.similar = similar; w.length = length;
-        if (what == 2) emu::launch((n + 31) / 32, 64, [&]() { walk16_kernel<true>(w); });
-        else emu::launch((n + 31) / 32, 64, [&]() { walk16_kernel<false>(w); });
+        if (what == 2) emu::launch((n + 31) / 32, walk16_smem_bytes(size), [&]() { walk16_kernel<true>(w); });
+        else emu::launch((n + 31) / 32, walk16_smem_bytes(size), [&]() { walk16_kernel<false>(w); });
     }
     return 0;
 }

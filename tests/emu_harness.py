@@ -111,7 +111,7 @@ class Sw16Params(C.Structure):
 
 def pack_db(subjects_mapped, bits):
     """host mirror of pack_db_kernel: sorted by length (descending, stable), rpw residues per word"""
-    rpw = 16 if bits == 2 else 6
+    rpw = {2: 16, 3: 10}.get(bits, 6)
     n = len(subjects_mapped)
     perm = sorted(range(n), key=lambda i: -len(subjects_mapped[i]))
     word_off = np.zeros(n + 1, dtype=np.int64)

@@ -441,3 +441,70 @@ def test_pairs16_sixteen_bit_bound_routes_long_pairs_away(ps, oracle):
         exp = oracle_batch(oracle, qs, rs, omat, mode, 20, 2, stats=True)
         assert_same(got, exp, KEYS6, f"mode {mode}")
         assert int(got.score[0]) == 38000
+
+
+# ---- loader, on-disk format, packing widths, whole-box scan -----------------------------------------------
+def test_dna_database_packs_at_2_and_3_bit(ps, oracle):
+    # ACGT only -> 2 bit although the matrix has a wildcard column; one N anywhere -> 3 bit; both scan bit-exact
+    dna, odna = ps.Matrix.create(b"ACGT", 2, -3), oracle.Matrix.create(b"ACGT", 2, -3)
+    query = psb_data.random_seq(401, 0, 150, protein=False)
+    subs = [psb_data.random_seq(401, 1 + i, 40 + 13 * i, protein=False) for i in range(40)]
+    subs[3] = np.concatenate([subs[3][:20], psb_data.mutate(query[20:120], 401, 99, 0.05, 0.02, protein=False)])
+    for with_n, bits in ((False, 2), (True, 3)):
+        ss = [s.copy() for s in subs]
+        if with_n:
+            ss[7][5] = ord("N"); ss[3][30] = ord("n")
+        cat, off = psb_data.concat(ss)
+        db = ps.Database((cat, off), dna)
+        assert db.bits == bits
+        prof = ps.Profile.new(query, False, dna)
+        for mode, om in (("local", 2), ("semi_global", 1), ("global_", 0)):
+            a = getattr(ps.Aligner.new(), mode)().gap_open(5).gap_extend(2).profile(prof).build()
+            got = a.scan(db)
+            exp = oracle.align_batch(query, np.array([0, len(query)]), cat, off, odna, mode=om, open=5, gap=2, shared_query=True)
+            assert_same(got, exp, KEYS3, f"{bits}-bit {mode}")
+
+
+def test_fasta_and_packed_file_round_trip(ps, oracle, blosum62, tmp_path):
+    b62 = ps.Matrix.from_name("blosum62")
+    query = psb_data.random_seq(402, 0, 200)
+    cat, off = psb_data.protein_db(403, 404, 300, query=query, planted_frac=0.05)
+    fa = tmp_path / "db.fa"
+    with open(fa, "wb") as f:
+        for i in range(len(off) - 1):
+            seq = bytes(cat[off[i]:off[i + 1]])
+            f.write(b">seq%d some description\n" % i)
+            for a in range(0, len(seq), 60):
+                f.write(seq[a:a + 60] + b"\n")
+    db1 = ps.Database.from_fasta(fa, b62)
+    assert db1.n == len(off) - 1 and db1.residues == int(off[-1]) and db1.bits == 5
+    packed = tmp_path / "db.psbdb"
+    db1.save(packed)
+    db2 = ps.Database.load(packed, b62)
+    assert (db2.n, db2.residues, db2.bits) == (db1.n, db1.residues, db1.bits)
+    prof = ps.Profile.new(query, False, b62)
+    a = ps.Aligner.new().local().gap_open(10).gap_extend(1).profile(prof).build()
+    exp = oracle.align_batch(query, np.array([0, len(query)]), cat, off, blosum62, mode=2, open=10, gap=1, shared_query=True)
+    assert_same(a.scan(db1), exp, KEYS3, "from_fasta")
+    assert_same(a.scan(db2), exp, KEYS3, "load")
+    with pytest.raises(ps.DeviceError):
+        ps.Database.load(packed, ps.Matrix.create(b"ACGT", 2, -3))     # packed with another alphabet
+    with pytest.raises(ps.DeviceError):
+        ps.Database.load(fa, b62)                                      # not a packed file
+
+
+def test_scan_box_equals_resident_scan(ps, oracle, blosum62):
+    # the single-process whole-box entry point (here: however many GPUs the box has) returns caller-order results
+    b62 = ps.Matrix.from_name("blosum62")
+    query = psb_data.random_seq(405, 0, 400)
+    cat, off = psb_data.protein_db(406, 407, 3000, query=query, planted_frac=0.02)
+    prof = ps.Profile.new(query, False, b62)
+    a = ps.Aligner.new().local().gap_open(10).gap_extend(1).profile(prof).build()
+    ref = a.scan(ps.Database((cat, off), b62))
+    for ng in (0, 1):
+        got = a.scan_box((cat, off), ng)
+        for k in KEYS3:
+            assert np.array_equal(getattr(got, k), getattr(ref, k)), (ng, k)
+    exp = oracle.align_batch(query, np.array([0, len(query)]), cat, off[:301], blosum62, mode=2, open=10, gap=1, shared_query=True)
+    for k in KEYS3:
+        assert np.array_equal(getattr(ref, k)[:300], exp[k]), k
