@@ -428,7 +428,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         else if (lq != first_lq || lr != first_lr) uniform = false;
         if (p16_on && lq <= 512) {
             const int c16 = c16_of[lq];
-            if (c16 >= 0 && pairs16_fits(p16_class(c16).G * p16_class(c16).K, lq, lr, m.max, m.min, req.open, req.gap)) {
+            if (c16 >= 0 && pairs16_fits(p16_class(c16).G * p16_class(c16).K, lq, lr, m.max, m.min, req.open, req.gap, cfg.mode == MODE_SW)) {
                 p16_ids[c16].push_back((int)i);
                 ++n_p16;
                 b->cells += (double)lq * lr;
@@ -921,7 +921,7 @@ struct DevProfile {
     // packed profiles (+open) of the 16-bit scan kernel, one per gap-open value ever used with this
     // profile on this device: built under the profile's mutex, immutable afterwards and freed only in
     // release_profile_resident, so concurrent scans with different penalties never see a buffer replaced
-    std::map<int, Sw16Profile> sw16;
+    std::map<int, std::vector<Sw16Profile>> sw16;   // one entry per strip of the query (queries <= 400 aa: one)
 };
 
 void release_profile_resident(parasail_profile *p) {
@@ -933,7 +933,7 @@ void release_profile_resident(parasail_profile *p) {
         cudaSetDevice(kv.first);
         void *ptrs[] = {d->d_query, d->d_qoff, d->d_matrix};
         for (void *q : ptrs) if (q) cudaFreeAsync(q, d->stream);
-        for (auto &sp : d->sw16) if (sp.second.prof) cudaFreeAsync(sp.second.prof, d->stream);
+        for (auto &sv : d->sw16) for (auto &sp : sv.second) if (sp.prof) cudaFreeAsync(sp.prof, d->stream);
         cudaSetDevice(cur);
         delete d;
     }
@@ -1019,27 +1019,52 @@ static int scan_general(const FnConfig &cfg, const parasail_profile *prof, DevPr
 }
 
 
-// the packed 16-bit profile for this gap-open penalty: built once per (device, open) and then shared
-// read-only by every thread that scans with this profile (Profile: Send + Sync upstream)
-static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open, int gap, Sw16Profile *out) {
+// the packed 16-bit profile(s) for this gap-open penalty: built once per (device, open) and then shared
+// read-only by every thread that scans with this profile (Profile: Send + Sync upstream).  Queries of more
+// than 400 residues are cut into strips of equal height (at most 25 rows per lane each), one profile per
+// strip: the scan then sweeps the database once per strip, handing the bottom row over through HBM.
+static constexpr int kSw16StripRows = 400, kSw16MaxStrips = 16;
+static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open, int gap, std::vector<Sw16Profile> *out) {
     Ctx &c = g_ctx;
     const HostMatrix &m = prof->matrix;
     if (m.type != PARASAIL_MATRIX_TYPE_SQUARE) return false;
     std::lock_guard<std::mutex> lk(prof->mu);
     auto it = dp->sw16.find(open);
-    if (it != dp->sw16.end()) { *out = it->second; return it->second.prof != nullptr && sw16_supported(it->second, open, gap); }
-    Sw16Profile np_;
-    std::vector<int8_t> host;
-    if (!sw16_build_profile(dp->mapped.data(), (int)dp->mapped.size(), m.table.data(), m.size, open, &np_, &host)) {
-        dp->sw16[open] = Sw16Profile();   // remember that this penalty has no packed form
-        return false;
+    if (it != dp->sw16.end()) {
+        *out = it->second;
+        return !it->second.empty() && sw16_supported(it->second[0], open, gap);
     }
-    if (cudaMallocAsync(&np_.prof, host.size(), c.stream) != cudaSuccess) { cudaGetLastError(); return false; }
-    if (cudaMemcpyAsync(np_.prof, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) return false;
-    cudaStreamSynchronize(c.stream);  // `host` goes out of scope; other streams may use the buffer from here on
-    dp->sw16[open] = np_;
-    *out = np_;
-    return sw16_supported(np_, open, gap);
+    const int lq = (int)dp->mapped.size();
+    const int nstrips = (lq + kSw16StripRows - 1) / kSw16StripRows;
+    std::vector<Sw16Profile> built;
+    bool ok = nstrips >= 1 && nstrips <= kSw16MaxStrips;
+    // every strip but the last is exactly 16*K rows high (its bottom row, the one handed over, must be a real
+    // query row): the smallest of the strip classes whose nstrips strips cover the query
+    int rows = lq;
+    if (ok && nstrips > 1) {
+        rows = 0;
+        for (int k : {12, 16, 20, 25}) if (!rows && SW16_G * k * nstrips >= lq) rows = SW16_G * k;
+        ok = rows > 0;
+    }
+    for (int st = 0; ok && st < nstrips; ++st) {
+        const int r0 = st * rows, nr = std::min(rows, lq - r0);
+        Sw16Profile np_;
+        std::vector<int8_t> host;
+        ok = nr > 0 && sw16_build_profile(dp->mapped.data() + r0, nr, m.table.data(), m.size, open, &np_, &host);
+        if (!ok) break;
+        np_.row0 = r0;
+        if (cudaMallocAsync(&np_.prof, host.size(), c.stream) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        built.push_back(np_);
+        if (cudaMemcpyAsync(np_.prof, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) { ok = false; break; }
+        cudaStreamSynchronize(c.stream);  // `host` goes out of scope; other streams may use the buffer from here on
+    }
+    if (!ok) {
+        for (auto &sp : built) if (sp.prof) cudaFreeAsync(sp.prof, c.stream);
+        built.clear();   // remembered: this penalty / query has no packed form
+    }
+    dp->sw16[open] = built;
+    *out = built;
+    return ok && sw16_supported(built[0], open, gap);
 }
 
 #ifdef PSB_SW16X
@@ -1054,7 +1079,19 @@ template <int K> static const void *sw16_fn_k() {
 #else
 template <int K> static const void *sw16_fn_k() { return (const void *)sw16_scan_kernel<K>; }
 #endif
-static const void *sw16_fn(int K) {
+template <int K> static const void *sw16_strip_fn_k() { return (const void *)sw16_scan_kernel<K, true>; }
+static const void *sw16_fn(int K, bool strip = false) {
+    if (strip) {
+        switch (K) {
+            case 4: return sw16_strip_fn_k<4>();
+            case 8: return sw16_strip_fn_k<8>();
+            case 12: return sw16_strip_fn_k<12>();
+            case 16: return sw16_strip_fn_k<16>();
+            case 20: return sw16_strip_fn_k<20>();
+            case 25: return sw16_strip_fn_k<25>();
+        }
+        return nullptr;
+    }
     switch (K) {
         case 4: return sw16_fn_k<4>();
         case 8: return sw16_fn_k<8>();
@@ -1078,11 +1115,13 @@ static constexpr int kSw16WarpsPerBlock = SW16_WARPS_PER_BLOCK;
 // is -- what limits strong scaling at 8 GPUs.  Those few subjects ("head") are therefore swept by
 // a separate small launch of the same kernel, one warp per SM sub-partition on SMs it owns
 // outright, beside the main launch.
-static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, const Sw16Profile &sp, int open, int gap, psb_db *db,
+static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfile *dp, const std::vector<Sw16Profile> &strips, int open, int gap, psb_db *db,
                      int *const d_out[6], int64_t *n_retried, int *retried_host) {
     Ctx &c = g_ctx;
+    const Sw16Profile &sp = strips[0];
+    const bool multi = strips.size() > 1;
     const HostMatrix &m = prof->matrix;
-    const int lq = sp.lq;
+    const int lq = (int)prof->query.size();
     // one group step costs ~0.6 us when the SM is full; keep a subject's sweep under ~40 % of the
     // time the whole shard needs at ~4.9 TCUPS
     const double est_ms = (double)lq * (double)db->residues / 4.9e9;
@@ -1092,6 +1131,7 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
     int64_t nhead = nroute;
     while (nhead < (int64_t)db->top_len.size() && db->top_len[nhead] > long_len) ++nhead;
     nhead = std::min<int64_t>(((nhead - nroute + 3) / 4) * 4, std::max<int64_t>(0, (db->n - nroute) / 8 / 4 * 4));
+    if (multi) nhead = 0;   // strip by strip: every strip sweeps all subjects in one launch
     if (db->nlong > nroute) {
         // more over-long subjects than the routed head covers: not a workload for the packed kernel
         *n_retried = db->n;
@@ -1101,7 +1141,7 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         std::fprintf(stderr, "[psb] sw16: n %lld residues %lld est %.2f ms long_len %.0f nroute %lld nhead %lld top %d\n", (long long)db->n,
                      (long long)db->residues, est_ms, long_len, (long long)nroute, (long long)nhead, db->top_len.empty() ? 0 : db->top_len[0]);
     DevMem d_retry, d_cnt;
-    PSB_TRY(d_retry.alloc(((size_t)db->n + 2) * sizeof(int), c.stream));
+    PSB_TRY(d_retry.alloc(((size_t)db->n * strips.size() + 2) * sizeof(int), c.stream));
     PSB_TRY(d_cnt.alloc(4 * sizeof(int), c.stream));
     PSB_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(int), c.stream));
 
@@ -1164,7 +1204,68 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
         c.launches += 3;
     }
     const int64_t nshort = db->n - nroute;
-    if (nshort > 0) {
+    DevMem d_bndA, d_bndB, d_scan_tmp16;
+    if (nshort > 0 && multi) {
+        // ---- queries of several strips: one sweep of the database per strip; the bottom row of a strip (T and
+        // Fh of both subjects of a word, one uint2 per column) goes through HBM to the strip below: 16 bytes
+        // per column and strip boundary against ~K*16*2.5 instructions of fill per column ------------------
+        if (!db->d_res_off) {
+            std::lock_guard<std::mutex> lk(db->mu);
+            if (!db->d_res_off) {
+                long long *ro = nullptr;
+                PSB_CUDA(cudaMallocAsync(&ro, ((size_t)db->n + 1) * sizeof(long long), db->stream));
+                if (db->stream != c.stream) PSB_CUDA(cudaStreamSynchronize(db->stream));
+                size_t tb = 0;
+                PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, db->d_len, ro, (int)db->n, c.stream));
+                PSB_TRY(d_scan_tmp16.alloc(tb, c.stream));
+                PSB_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp16.p, tb, db->d_len, ro, (int)db->n, c.stream));
+                PSB_CUDA(cudaStreamSynchronize(c.stream));
+                db->d_res_off = ro;
+            }
+        }
+        PSB_TRY(d_bndA.alloc(((size_t)db->residues + 64) * sizeof(uint2), c.stream));
+        PSB_TRY(d_bndB.alloc(((size_t)db->residues + 64) * sizeof(uint2), c.stream));
+        for (size_t st = 0; st < strips.size(); ++st) {
+            const Sw16Profile &ss = strips[st];
+            Sw16Params p;
+            std::memset(&p, 0, sizeof(p));
+            p.prof = ss.prof; p.nletters = ss.nletters; p.lq = ss.lq; p.open = open; p.gap = gap; p.max_score = ss.max_score;
+            p.words = db->d_words; p.bits = db->bits;
+            p.score = d_out[0]; p.end_query = d_out[1]; p.end_ref = d_out[2];
+            p.retry = d_retry.as<int>(); p.retry_count = d_cnt.as<int>();
+            p.mul_one = 1u; p.mul_64k = 65536u;
+            p.word_off = db->d_word_off + nroute; p.len = db->d_len + nroute; p.n = nshort; p.out_map = db->d_perm + nroute;
+            p.sid_base = (int)nroute;
+            p.res_off = db->d_res_off + nroute;
+            p.bnd_in = st == 0 ? nullptr : ((st & 1) ? d_bndA.as<uint2>() : d_bndB.as<uint2>());
+            p.bnd_out = st + 1 == strips.size() ? nullptr : ((st & 1) ? d_bndB.as<uint2>() : d_bndA.as<uint2>());
+            p.row0 = ss.row0; p.merge = st > 0 ? 1 : 0;
+            DevMem d_cnt_st;   // a work counter per launch
+            PSB_TRY(d_cnt_st.alloc(sizeof(int), c.stream));
+            PSB_CUDA(cudaMemsetAsync(d_cnt_st.p, 0, sizeof(int), c.stream));
+            p.counter = d_cnt_st.as<int>();
+            const void *fn = sw16_fn(ss.K, true);
+            if (!fn) { set_error("sw16: no strip kernel for this query length"); return PSB_EUNSUPPORTED; }
+            int wpb = kSw16WarpsPerBlock, per_sm = 0;
+            size_t smem = sw16_smem_bytes(ss.nletters, ss.K, wpb, true);
+            const size_t smem16 = sw16_smem_bytes(ss.nletters, ss.K, 16, true);
+            PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, smem16)));
+            PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpb * 32, smem));
+            if (per_sm * wpb < 16) {
+                int per_sm16 = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm16, fn, 16 * 32, smem16) == cudaSuccess && per_sm16 * 16 > per_sm * wpb) {
+                    wpb = 16; per_sm = per_sm16; smem = smem16;
+                } else cudaGetLastError();
+            }
+            if (per_sm < 1) per_sm = 1;
+            const long long slots = ((nshort + 1) / 2 + 1) / 2;
+            long long blocks = std::min<long long>((slots + wpb - 1) / wpb, (long long)c.sms * per_sm);
+            if (blocks < 1) blocks = 1;
+            void *args[] = {&p};
+            PSB_CUDA(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(wpb * 32), args, smem, c.stream));
+            c.launches++;
+        }
+    } else if (nshort > 0) {
         Sw16Params p;
         std::memset(&p, 0, sizeof(p));
         p.prof = sp.prof; p.nletters = sp.nletters; p.lq = sp.lq; p.open = open; p.gap = gap; p.max_score = sp.max_score;
@@ -1518,7 +1619,7 @@ void psb_db_free(psb_db_t *db) {
     int cur = 0;
     cudaGetDevice(&cur);
     cudaSetDevice(db->device);
-    void *ptrs[] = {db->d_words, db->d_word_off, db->d_perm, db->d_len};
+    void *ptrs[] = {db->d_words, db->d_word_off, db->d_perm, db->d_len, db->d_res_off};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, db->stream);
     cudaSetDevice(cur);
     delete db;
@@ -1559,7 +1660,7 @@ static int scan_enqueue(ScanJob &job, const FnConfig &cfg, const parasail_profil
     PSB_CUDA(cudaEventCreate(&job.ev0));
     PSB_CUDA(cudaEventCreate(&job.ev1));
     PSB_CUDA(cudaEventRecord(job.ev0, c.stream));
-    Sw16Profile sp16;
+    std::vector<Sw16Profile> sp16;
     const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 && sw16_prepare(profile, dp, open, gap, &sp16);
     int rc;
     if (fast) rc = scan_sw16(cfg, profile, dp, sp16, open, gap, db, outp, &job.retried, job.retried_host);

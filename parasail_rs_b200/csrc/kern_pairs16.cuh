@@ -75,10 +75,12 @@ inline long long pairs16_item_trace_words(int G, int K, int lr_max) {
     return (((long long)(lr_max + G - 1) * G * pairs16_trace_words(K)) + 3) / 4 * 4;
 }
 // static 16-bit bound: every intermediate of the fill stays inside int16 for this pair in a G*K-row frame
-inline bool pairs16_fits(int rows, int lq, int lr, int smax, int smin, int open, int gap) {
+// (global / semi-global values are kept biased by +16384: half the range on either side)
+inline bool pairs16_fits(int rows, int lq, int lr, int smax, int smin, int open, int gap, bool sw) {
     const long long pos = (long long)(lq < lr ? lq : lr) * (smax > 0 ? smax : 0) + 2ll * open + 256;
     const long long neg = 3ll * open + (long long)(rows + lr + 4) * gap + 256 + (smin < 0 ? -smin : 0);
-    return pos < 32000 && neg < 32000;
+    const long long lim = sw ? 32000 : 16000;
+    return pos < lim && neg < lim;
 }
 // trace / stats: neighbouring cells must differ by less than 128 so that one byte of H per cell is enough
 inline bool pairs16_trace_ok(int mat_min, int mat_max, int open) {
@@ -132,6 +134,13 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
 
     const int o = p.open, e = p.gap;
     const unsigned NEGE = p16_pack(-e, -e), NEGO = p16_pack(-o, -o);
+    // global / semi-global kernels keep every value biased by +16384 in both halves: max and add are
+    // translation invariant, the trace byte is untouched (the bias is a multiple of 256), and a biased half
+    // never drops below o, so T = H - o is a plain 32-bit subtraction that cannot borrow across the halves
+    // -- it leaves the DPX/ALU pipe, which is what bounds these kernels.  (Local alignment keeps the floor at
+    // 0 for VIADDMNMX.RELU and pays the packed add.)
+    constexpr int BIAS = SW ? 0 : 16384;
+    const unsigned O32 = (unsigned)o * 0x10001u, E32 = (unsigned)e * 0x10001u;
     const int mode = p.mode;
     const bool top_free = SW || (mode == MODE_SG && p.s1_beg);
     const bool left_free = SW || (mode == MODE_SG && p.s2_beg);
@@ -195,7 +204,7 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
             const int ia = il - padA, ib = il - padB;
             const int la = (ia < 0 || left_free) ? 0 : -o - ia * e;
             const int lb = (ib < 0 || left_free) ? 0 : -o - ib * e;
-            T[k] = p16_pack(la - o, lb - o);
+            T[k] = p16_pack(la - o + BIAS, lb - o + BIAS);
             E[k] = T[k];
             T2[k] = T[k];
         }
@@ -205,9 +214,14 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
             const int ia = il - padA, ib = il - padB;
             const int la = (il < 0 || ia < 0 || left_free) ? 0 : -o - ia * e;
             const int lb = (il < 0 || ib < 0 || left_free) ? 0 : -o - ib * e;
-            Tdiag_in = p16_pack(la - o, lb - o);
+            Tdiag_in = p16_pack(la - o + BIAS, lb - o + BIAS);
         }
         unsigned Tout = Tdiag_in, Fout = 0;
+        // the table's top boundary as lane 0 sees it at step s (its column j = s): T = H[-1][j] - o and
+        // Fh = F[0][j] + o = H[-1][j], advanced by one column per step by every lane alike (no divergence)
+        unsigned topT = p16_pack(-(top_free ? 0 : o) - o + BIAS, -(top_free ? 0 : o) - o + BIAS);
+        unsigned topF = p16_pack(-(top_free ? 0 : o) + BIAS, -(top_free ? 0 : o) + BIAS);
+        const unsigned topStep = top_free ? 0u : E32;
         // local: per half, a column maximum must exceed `thr` to matter (see kern_sw16.cuh)
         unsigned thr = 0, best = 0, bestj = 0;
         // global / semi-global candidates, kept in T space (T = H - o)
@@ -234,11 +248,8 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
                 const int j = s - lg;
                 unsigned Tup = shfl_up(Tout, 1);
                 unsigned Fup = shfl_up(Fout, 1);
-                if (lg == 0) {
-                    const int hb = top_free ? 0 : -o - j * e;     // H[-1][j]
-                    Tup = p16_pack(hb - o, hb - o);
-                    Fup = p16_pack(hb, hb);                        // Fh = F + o with F[0][j] = H[-1][j] - o
-                }
+                if (lg == 0) { Tup = topT; Fup = topF; }
+                if (!SW) { topT -= topStep; topF -= topStep; }   // biased halves: a 32-bit subtraction cannot borrow
                 if (j >= 0 && j < Lmax) {
                     const unsigned w = ring[j & 63];
                     const unsigned char *pa = pa_base + (w & 0xffffu);
@@ -258,7 +269,7 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
                         const unsigned h = viaddmax2(Td, So, En);
                         const unsigned Hn = SW ? viaddmax2_relu(Fu, NEGO, h) : viaddmax2(Fu, NEGO, h);
                         const unsigned Fn = viaddmax2(Fu, NEGE, h);
-                        const unsigned Tn = vadd2(Hn, NEGO);
+                        const unsigned Tn = SW ? vadd2(Hn, NEGO) : Hn - O32;
                         if (TRACE) {
                             if (k & 1) hb8[k >> 1] = prmt(heven, Hn, 0x6420u);
                             else heven = Hn;
@@ -423,7 +434,7 @@ PSB_KERNEL void pairs16_kernel(Pairs16Params p) {
                     const int cT = half ? colTb : colTa, cI = half ? colIb : colIa;
                     // the last column beats the last row only when strictly better (rules::SG_COL_WINS_TIE)
                     if (col_ends && (!row_ends || cT > bT)) { bT = cT; bJ = Lr - 1; bI = cI; }
-                    p.score[pid] = bT + o; p.end_query[pid] = bI; p.end_ref[pid] = bJ;
+                    p.score[pid] = bT + o - BIAS; p.end_query[pid] = bI; p.end_ref[pid] = bJ;
                 }
             }
         }

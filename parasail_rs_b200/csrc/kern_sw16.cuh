@@ -73,6 +73,7 @@ struct Sw16Profile {
     int nletters = 0;        // alphabet size + 1 (the pad letter)
     int max_score = 0, min_score = 0;
     int open_baked = -1;
+    int row0 = 0;            // first query row this profile covers (strip profiles of long queries)
 };
 
 static const int kSw16K[] = {4, 8, 12, 16, 20, 25, 28, 32};
@@ -140,15 +141,22 @@ struct Sw16Params {
     int *retry_count;
     int sid_base;                 // added to a subject index before it is pushed to `retry`
     int *counter;                 // dynamic work queue over pairs of items
+    // STRIP kernels (queries longer than one strip of 16*K rows are swept strip by strip, one launch each):
+    const long long *res_off;     // first residue of each sorted subject (n+1): an item's boundary line starts at
+                                  // res_off of its first subject and has one uint2 (T, Fh of both subjects) per column
+    const uint2 *bnd_in;          // bottom row of the strip above (NULL for the first strip)
+    uint2 *bnd_out;               // this strip's bottom row (NULL for the last strip)
+    int row0;                     // first query row of this strip
+    int merge;                    // 1: combine with the result already stored for the subject (strips after the first)
     unsigned mul_one;             // the constant 1, kept opaque so that T = X*1 - o can be an IMAD
     unsigned mul_64k;             // the constant 65536, opaque for the same reason: (b << 16) + a as an IMAD
 };
 
-// per warp: 2 rings of 64 words, 2 published group bests (padded to 16 B), and 2 halves x 32 lanes x
-// sw16_park_words(K) words of parked H columns
-inline size_t sw16_warp_smem(int K) { return 2 * 64 * 4 + 16 + (size_t)2 * 32 * sw16_park_words(K) * 4; }
-inline size_t sw16_smem_bytes(int nletters, int K, int warps) {
-    return (size_t)nletters * sw16_letter_stride(sw16_chunks(K)) + (size_t)warps * sw16_warp_smem(K);
+// per warp: 2 rings of 64 words, 2 published group bests (padded to 16 B), 2 halves x 32 lanes x
+// sw16_park_words(K) words of parked H columns, and (strip kernels) 2 rings of 64 boundary columns
+inline size_t sw16_warp_smem(int K, bool strip = false) { return 2 * 64 * 4 + 16 + (size_t)2 * 32 * sw16_park_words(K) * 4 + (strip ? 2 * 64 * 8 : 0); }
+inline size_t sw16_smem_bytes(int nletters, int K, int warps, bool strip = false) {
+    return (size_t)nletters * sw16_letter_stride(sw16_chunks(K)) + (size_t)warps * sw16_warp_smem(K, strip);
 }
 
 PSB_DEV unsigned sw16_fetch_code(const unsigned *words, long long w0, int len, int c, int bits, int pad_code) {
@@ -180,7 +188,7 @@ PSB_DEV unsigned sw16_fetch_code(const unsigned *words, long long w0, int len, i
 #define SW16_BOUNDS
 #endif
 
-template <int K>
+template <int K, bool STRIP = false>
 PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
     constexpr int G = SW16_G;
     constexpr int CH = (K + SW16_ROWS_PER_LOAD - 1) / SW16_ROWS_PER_LOAD;   // = sw16_chunks(K): 16-byte profile loads per lane and letter
@@ -199,7 +207,8 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
     sync_block();
     const unsigned char *lane_base = smem_raw + lg * 16;
     constexpr int PARKW = SW16_PROF32 ? ((K + 3) / 4) * 4 : ((K + 15) / 16) * 16;   // = sw16_park_words(K)
-    unsigned char *wsm = smem_raw + (size_t)p.nletters * LSTRIDE + (size_t)warp_in_block() * (2 * 64 * 4 + 16 + 2 * 32 * PARKW * 4);
+    unsigned char *wsm = smem_raw + (size_t)p.nletters * LSTRIDE + (size_t)warp_in_block() * (2 * 64 * 4 + 16 + 2 * 32 * PARKW * 4 + (STRIP ? 2 * 64 * 8 : 0));
+    uint2 *bring = (uint2 *)(wsm + 2 * 64 * 4 + 16 + 2 * 32 * PARKW * 4) + grp * 64;   // STRIP: boundary columns of the strip above
     unsigned *ring = (unsigned *)wsm + grp * 64;
     volatile unsigned *gpub = (volatile unsigned *)(wsm + 2 * 64 * 4) + grp;   // group best - 1, per half
     uint4 *park = (uint4 *)(wsm + 2 * 64 * 4 + 16);   // [half][chunk4][lane] 16-byte slots
@@ -230,6 +239,7 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
         const int Lmax = lenA > lenB ? lenA : lenB;    // this group's columns
         const int Lother = shfl_xor(Lmax, 16);
         const int nsteps = (Lmax > Lother ? Lmax : Lother) + G - 1;  // warp-uniform
+        const long long bbase = STRIP ? p.res_off[sa < p.n ? sa : 0] : 0;   // this item's boundary line
 
         // boundary values of a local alignment: H = 0, so T = H - o (decoupled form) or T = H (shifted form)
         const unsigned TB = SW16_DECOUPLE ? NEGO : 0u;
@@ -256,6 +266,11 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                 const unsigned ca = sw16_fetch_code(p.words, wA, lenA, c, p.bits, pad_code);
                 const unsigned cb = sw16_fetch_code(p.words, wB, lenB, c, p.bits, pad_code);
                 ring[c & 63] = (ca * LSTRIDE) | ((cb * LSTRIDE) << 16);
+                if (STRIP) {
+                    uint2 bv; bv.x = TB; bv.y = 0u;   // first strip: the table's top boundary (H = 0, F opened from it)
+                    if (p.bnd_in && c < Lmax) bv = p.bnd_in[bbase + c];
+                    bring[c & 63] = bv;
+                }
             }
             sync_warp();
             const int send = (s0 + 32 < nsteps) ? s0 + 32 : nsteps;
@@ -265,7 +280,10 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                 const int j = s - lg;
                 unsigned Tup = shfl_up(Tout, 1);
                 unsigned Fup = shfl_up(Fout, 1);
-                if (lg == 0) { Tup = TB; Fup = 0; }
+                if (lg == 0) {
+                    if (STRIP) { const uint2 bv = bring[j & 63]; Tup = bv.x; Fup = bv.y; }
+                    else { Tup = TB; Fup = 0; }
+                }
                 if (j >= 0 && j < Lmax) {
                     const unsigned w = ring[j & 63];
                     const unsigned char *pa = lane_base + (w & 0xffffu);
@@ -310,6 +328,9 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                     }
                     if (K & 1) cmax = vimax2(cmax, tprev);
                     Tdiag_in = Tup; Tout = Tu; Fout = Fu;
+                    if (STRIP) {
+                        if (lg == G - 1 && p.bnd_out) { uint2 bv; bv.x = Tu; bv.y = Fu; p.bnd_out[bbase + j] = bv; }
+                    }
                     thr = vimax2(thr, *gpub);
                     const unsigned m = vimax2(thr, cmax);
                     if (m != thr) {
@@ -392,12 +413,16 @@ PSB_KERNEL void SW16_BOUNDS sw16_scan_kernel(Sw16Params p) {
                 if (overflow) {
                     const int slot_r = atomic_add(p.retry_count, 1);
                     p.retry[slot_r] = (int)sid + p.sid_base;
-                } else if (sc == 0) {
-                    p.score[oid] = 0; p.end_query[oid] = 0; p.end_ref[oid] = 0;
                 } else {
-                    p.score[oid] = sc;
-                    p.end_ref[oid] = (int)(0xffffu - (unsigned)((comp >> 10) & 0xffffu));
-                    p.end_query[oid] = 1023 - (int)(comp & 1023u);
+                    int er = sc == 0 ? 0 : (int)(0xffffu - (unsigned)((comp >> 10) & 0xffffu));
+                    int eq = sc == 0 ? 0 : 1023 - (int)(comp & 1023u) + (STRIP ? p.row0 : 0);
+                    int best_sc = sc;
+                    if (STRIP && p.merge) {
+                        // the strips above have stored their best: (score, smaller end_ref, smaller end_query) decides
+                        const int osc = p.score[oid], oer = p.end_ref[oid], oeq = p.end_query[oid];
+                        if (osc > sc || (osc == sc && (sc == 0 || oer < er || (oer == er && oeq < eq)))) { best_sc = osc; er = oer; eq = oeq; }
+                    }
+                    p.score[oid] = best_sc; p.end_query[oid] = eq; p.end_ref[oid] = er;
                 }
             }
         }

@@ -22,6 +22,7 @@ struct psb_db {
     long long *d_word_off = nullptr;  // n+1, sorted order (length descending, stable)
     int *d_perm = nullptr;            // sorted position -> caller's subject id
     int *d_len = nullptr;             // sorted order
+    long long *d_res_off = nullptr;   // n+1 prefix sum of d_len: boundary lines of the strip-wise scan (built on first use)
     std::mutex mu;
 };
 

@@ -130,7 +130,7 @@ extern "C" int emu_pairs16(int G, int K, int mode, int s1_beg, int s1_end, int s
             const int pid = items[2 * w + h];
             if (pid < 0) continue;
             const int lq = (int)(q_off[pid + 1] - q_off[pid]), lr = (int)(r_off[pid + 1] - r_off[pid]);
-            if (lq > G * K || !pairs16_fits(G * K, lq, lr, mat_max, mat_min, open, gap)) return -2;
+            if (lq > G * K || !pairs16_fits(G * K, lq, lr, mat_max, mat_min, open, gap, sw)) return -2;
             lrmax = std::max(lrmax, lr);
             slot_of[pid] = 2 * w + h;
         }
@@ -163,6 +163,42 @@ extern "C" int emu_pairs16(int G, int K, int mode, int s1_beg, int s1_end, int s
         w.matches = matches; w.similar = similar; w.length = length;
         if (what == 2) emu::launch((n + 31) / 32, walk16_smem_bytes(size), [&]() { walk16_kernel<true>(w); });
         else emu::launch((n + 31) / 32, walk16_smem_bytes(size), [&]() { walk16_kernel<false>(w); });
+    }
+    return 0;
+}
+
+// ---- strip-wise scan of a long query (STRIP instantiations of the scan kernel), host loop as in engine.cu ----
+extern "C" int emu_sw16_strips(const uint8_t *mapped_query, int lq, const int *table, int size, int open, int gap, int rows_per_strip,
+                               const unsigned *words, const long long *word_off, const int *len, int bits, long long n,
+                               const int *out_map, int *score, int *end_query, int *end_ref, int *retry, int *retry_count, int nblocks) {
+    std::vector<long long> res_off((size_t)n + 1, 0);
+    for (long long i = 0; i < n; ++i) res_off[(size_t)i + 1] = res_off[(size_t)i] + len[i];
+    std::vector<uint2> bndA((size_t)res_off[(size_t)n] + 64), bndB((size_t)res_off[(size_t)n] + 64);
+    const int nstrips = (lq + rows_per_strip - 1) / rows_per_strip;
+    if (rows_per_strip % SW16_G != 0 || sw16_pick_k(rows_per_strip) * SW16_G != rows_per_strip) return -4;   // full strips only
+    for (int st = 0; st < nstrips; ++st) {
+        const int r0 = st * rows_per_strip, nr = std::min(rows_per_strip, lq - r0);
+        Sw16Profile pr;
+        std::vector<int8_t> host;
+        if (!sw16_build_profile(mapped_query + r0, nr, table, size, open, &pr, &host)) return -1;
+        if (!sw16_supported(pr, open, gap)) return -2;
+        int counter = 0;
+        Sw16Params p;
+        std::memset(&p, 0, sizeof(p));
+        p.prof = host.data(); p.nletters = pr.nletters; p.lq = nr; p.open = open; p.gap = gap; p.max_score = pr.max_score;
+        p.words = words; p.word_off = word_off; p.len = len; p.bits = bits; p.n = n; p.out_map = out_map;
+        p.score = score; p.end_query = end_query; p.end_ref = end_ref; p.retry = retry; p.retry_count = retry_count;
+        p.counter = &counter; p.mul_one = 1u; p.mul_64k = 65536u;
+        p.res_off = res_off.data();
+        p.bnd_in = st == 0 ? nullptr : ((st & 1) ? bndA.data() : bndB.data());
+        p.bnd_out = st + 1 == nstrips ? nullptr : ((st & 1) ? bndB.data() : bndA.data());
+        p.row0 = r0; p.merge = st > 0;
+        const size_t smem = sw16_smem_bytes(p.nletters, pr.K, 1, true);
+        switch (pr.K) {
+#define STCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { sw16_scan_kernel<KK, true>(p); }); break;
+            STCASE(4) STCASE(8) STCASE(12) STCASE(16)
+            default: return -3;
+        }
     }
     return 0;
 }

@@ -106,7 +106,9 @@ class Sw16Params(C.Structure):
                 ("max_score", C.c_int), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
                 ("bits", C.c_int), ("n", C.c_longlong), ("out_map", C.c_void_p), ("score", C.c_void_p),
                 ("end_query", C.c_void_p), ("end_ref", C.c_void_p), ("retry", C.c_void_p),
-                ("retry_count", C.c_void_p), ("sid_base", C.c_int), ("counter", C.c_void_p), ("mul_one", C.c_uint), ("mul_64k", C.c_uint)]
+                ("retry_count", C.c_void_p), ("sid_base", C.c_int), ("counter", C.c_void_p),
+                ("res_off", C.c_void_p), ("bnd_in", C.c_void_p), ("bnd_out", C.c_void_p), ("row0", C.c_int), ("merge", C.c_int),
+                ("mul_one", C.c_uint), ("mul_64k", C.c_uint)]
 
 
 def pack_db(subjects_mapped, bits):
@@ -154,7 +156,7 @@ def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1, split=False):
     counter = np.zeros(1, dtype=np.int32)
     p = Sw16Params(ptr(prof), mat.size + 1, len(qm), open, gap, mx.value, ptr(words), ptr(word_off), ptr(lens), bits, n,
                    ptr(perm), ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(retry),
-                   ptr(retry_count), 0, ptr(counter), 1, 65536)
+                   ptr(retry_count), 0, ptr(counter), None, None, None, 0, 0, 1, 65536)
     rc = (lib().emu_sw16x if split and K.value >= 8 else lib().emu_sw16)(K.value, C.byref(p), nblocks)
     assert rc == 0, (rc, K.value)
     return outs, sorted(int(perm[i]) for i in retry[: retry_count[0]])
@@ -254,3 +256,24 @@ def pairs16(qs, rs, mat, G, K, mode, open, gap, flags=(1, 1, 1, 1), what=0, nblo
     if what == 1:
         outs["cigar_ops"] = [rev[rev_off[i]: rev_off[i] + outs["nops"][i]][::-1].copy() for i in range(n)]
     return outs
+
+
+def sw16_strips(query, subjects, mat, open, gap, rows_per_strip, bits=5, nblocks=1):
+    """The strip-wise scan of a long query (STRIP instantiations of csrc/kern_sw16.cuh, host loop as in
+    engine.cu): one sweep of the database per strip of `rows_per_strip` query rows.  Returns (outs, retry)."""
+    mapper = mat.mapper.astype(np.uint8)
+    qm = np.ascontiguousarray(mapper[np.asarray(query, dtype=np.uint8)])
+    sm = [mapper[np.asarray(s, dtype=np.uint8)] for s in subjects]
+    table = np.ascontiguousarray(mat.table, dtype=np.int32)
+    words, word_off, lens, perm = pack_db(sm, bits)
+    n = len(sm)
+    outs = {k: np.full(n, -777, dtype=np.int32) for k in ("score", "end_query", "end_ref")}
+    nst = (len(qm) + rows_per_strip - 1) // rows_per_strip
+    retry = np.full(n * nst + 2, -1, dtype=np.int32)
+    retry_count = np.zeros(1, dtype=np.int32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emu_sw16_strips(ptr(qm), len(qm), ptr(table), mat.size, open, gap, rows_per_strip, ptr(words), ptr(word_off), ptr(lens),
+                               bits, C.c_longlong(n), ptr(perm), ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]),
+                               ptr(retry), ptr(retry_count), nblocks)
+    assert rc == 0, rc
+    return outs, sorted(set(int(perm[i]) for i in retry[: retry_count[0]]))

@@ -86,3 +86,39 @@ def test_split_column_variant(oracle, blosum62, lq):
             psb_data.random_seq(19, 3, 50, protein=False)]
     _, retry = check(oracle, mat, qd, subs, 5, 2, split=True)
     assert retry == ([0, 1] if lq * 100 > 32000 else [])
+
+
+@pytest.mark.parametrize("lq,rows", [(100, 64), (130, 64), (300, 128), (400, 192)])
+def test_strip_wise_scan_of_long_queries(oracle, blosum62, lq, rows):
+    # queries longer than one strip: one sweep per strip, bottom rows handed over, per-strip bests merged with
+    # (score, smaller end_ref, smaller end_query).  Every strip but the last is exactly 16*K rows high (the
+    # bottom row of lane 15 must be a real query row)
+    q = psb_data.random_seq(17, 0, lq)
+    subs = []
+    for i, L in enumerate([35, 90, 91, 150, 17, 64, 33, 200]):
+        if i % 2 == 0:
+            a = (i * 13) % max(1, lq - 30)
+            seg = psb_data.mutate(q[a: a + L], 17, 100 + i, 0.2, 0.05)[:L]
+            s = np.concatenate([seg, psb_data.random_seq(18, i, max(0, L - len(seg)))])[:L]
+        else:
+            s = psb_data.random_seq(18, i, L)
+        subs.append(s)
+    subs.append(np.concatenate([q[rows - 5: rows + 25], q[rows - 5: rows + 25]]))   # a match that straddles the strip boundary, twice
+    outs, retry = emu_harness.sw16_strips(q, subs, blosum62, 10, 1, rows)
+    assert retry == []
+    for i, s in enumerate(subs):
+        exp = oracle.align(q, s, blosum62, mode=2, open=10, gap=1)
+        assert (outs["score"][i], outs["end_query"][i], outs["end_ref"][i]) == (exp["score"], exp["end_query"], exp["end_ref"]), (i, lq, len(s))
+
+
+def test_strip_wise_scan_ties_across_strips(oracle):
+    # the same maximum in two strips: the smaller end_ref must win whichever strip finds it
+    mat = oracle.Matrix.create(b"ACGT", 2, -3)
+    unit = np.frombuffer(b"ACGTTGCA", dtype=np.uint8)
+    q = np.concatenate([unit, psb_data.random_seq(19, 0, 60, protein=False), unit, psb_data.random_seq(19, 1, 40, protein=False)])
+    subs = [np.concatenate([psb_data.random_seq(19, 2, 11, protein=False), unit, psb_data.random_seq(19, 3, 9, protein=False)]),
+            unit.copy(), np.concatenate([unit, unit]), psb_data.random_seq(19, 4, 50, protein=False)]
+    outs, _ = emu_harness.sw16_strips(q, subs, mat, 5, 2, 64, bits=3)
+    for i, s in enumerate(subs):
+        exp = oracle.align(q, s, mat, mode=2, open=5, gap=2)
+        assert (outs["score"][i], outs["end_query"][i], outs["end_ref"][i]) == (exp["score"], exp["end_query"], exp["end_ref"]), i

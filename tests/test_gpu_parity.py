@@ -508,3 +508,17 @@ def test_scan_box_equals_resident_scan(ps, oracle, blosum62):
     exp = oracle.align_batch(query, np.array([0, len(query)]), cat, off[:301], blosum62, mode=2, open=10, gap=1, shared_query=True)
     for k in KEYS3:
         assert np.array_equal(getattr(ref, k)[:300], exp[k]), k
+
+
+@pytest.mark.parametrize("lq", [401, 512, 700, 1000, 1601])
+def test_scan_long_query_strip_wise(ps, oracle, blosum62, lq):
+    # queries beyond one strip (400 rows) are swept strip by strip in packed 16-bit lanes
+    query = psb_data.random_seq(501, lq, lq)
+    cat, off = psb_data.protein_db(502, 503 + lq, 400, query=query[: min(lq, 400)], planted_frac=0.05)
+    # plant segments from every part of the query, some straddling strip boundaries
+    segs = [query[a: a + 120] for a in range(0, lq - 60, max(60, lq // 7))]
+    extra = [np.concatenate([psb_data.random_seq(504, i, 30), psb_data.mutate(s, 504, 50 + i, 0.1, 0.03), psb_data.random_seq(505, i, 20)])
+             for i, s in enumerate(segs)]
+    ecat, eoff = psb_data.concat(extra)
+    cat = np.concatenate([cat, ecat]); off = np.concatenate([off, eoff[1:] + off[-1]])
+    scan_case(ps, oracle, blosum62, query, cat, off)
