@@ -495,8 +495,10 @@ PSB_KERNEL void walk16_kernel(Walk16Params p) {
     const uint8_t *tr = (const uint8_t *)(p.trace + p.trace_off[item]) + half;
     unsigned *out = STATS ? nullptr : p.rev_ops + p.rev_off[pid];
     // byte of cell (i, j); exact H from a byte and the exact value `ref` of a neighbouring cell
+    // il / K by multiplication: exact for il < 1024 and every K <= 32 (checked by tests/test_emu_pairs16.py)
+    const unsigned rcpK = 65536u / (unsigned)K + 1u;
     auto load = [&](int i, int j) -> unsigned {
-        const int il = i + pad, t = il / K, k = il - t * K;
+        const int il = i + pad, t = (int)(((unsigned)il * rcpK) >> 16), k = il - t * K;
         return tr[((long long)(j + t) * G + t) * TWB + 2 * k];
     };
     auto recon = [](unsigned byte, int ref) -> int { return ref + (int)(signed char)(unsigned char)(byte - (unsigned)ref); };

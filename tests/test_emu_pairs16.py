@@ -91,3 +91,10 @@ def test_ties(oracle):
         for gaps in ((5, 2), (1, 1), (0, 0), (2, 0)):
             check(oracle, mat, qs, rs, 16, 1, mode, *gaps, what=1)
             check(oracle, mat, qs, rs, 16, 1, mode, *gaps, what=2)
+
+
+def test_walk_row_to_lane_division_trick():
+    # walk16_kernel turns a row index into (lane, row in lane) with a multiply: exact over the whole frame
+    for K in range(1, 33):
+        M = 65536 // K + 1
+        assert all((il * M) >> 16 == il // K for il in range(1024)), K
