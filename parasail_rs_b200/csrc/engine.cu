@@ -341,7 +341,7 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
     p.mode = g.mode; p.s1_beg = g.s1_beg; p.s1_end = g.s1_end; p.s2_beg = g.s2_beg; p.s2_end = g.s2_end;
     p.bnd = d_bnd.as<int>(); p.progress = d_ctl.as<int>() + 1; p.next_strip = d_ctl.as<int>(); p.cand = d_cand.as<int>();
     p.multi_n = 0; p.r_off = nullptr;
-    const size_t smem = v3 ? wave32v3_smem_bytes(g.size, wpb) : (v2 ? wave32v2_smem_bytes(g.size, wpb) : wave32_smem_bytes(g.size, wpb));
+    const size_t smem = v3 ? wave32v3_smem_bytes(g.size, wpb, K) : (v2 ? wave32v2_smem_bytes(g.size, wpb) : wave32_smem_bytes(g.size, wpb));
     if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpb * 32, smem));
@@ -870,7 +870,7 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
     // batches that keep per-cell decisions (trace, and `_stats` on the packed path, whose statistics come from
     // the walk) are cut so that a pass's decision bits + scratch stay within a budget of device memory
     int64_t budget = (int64_t)64 << 30;
-    {
+    if (req.n > 4096 && (req.cfg.trace || req.cfg.stats)) {   // (a driver query: kept off the single-pair path)
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min<int64_t>(budget, (int64_t)(free_b / 2));
         else cudaGetLastError();
@@ -1899,9 +1899,13 @@ int psb_scan_box(const char *fn_name, const parasail_profile_t *profile, int ope
     if (ndev <= 0) { set_error("no CUDA device available: libparasail_b200 has no CPU fallback (needs an sm_100a GPU)"); return PSB_ENODEV; }
     if (n_gpus <= 0 || n_gpus > ndev) n_gpus = ndev;
     if ((int64_t)n_gpus > n) n_gpus = (int)n;
+    const bool dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
+    const auto t_in = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count(); };
     PSB_TRY(ensure_ctx());   // the batch's pinned arrays are allocated by the calling thread
     psb_batch_t *b = new_batch(n, cfg);
     if (!b) { set_error("pinned host allocation failed"); return PSB_ENOMEM; }
+    if (dbg) std::fprintf(stderr, "[psb] scan_box: batch ready at %.3f ms\n", since());
     const int64_t total = off[n] - off[0];
     b->cells = (double)profile->query.size() * (double)total;
     std::vector<int64_t> cut(n_gpus + 1, n);
@@ -1931,9 +1935,11 @@ int psb_scan_box(const char *fn_name, const parasail_profile_t *profile, int ope
     int rc = PSB_OK;
     Ctx &c = g_ctx;
     c.last_ms = 0.0; c.launches = 0;
+    if (dbg) std::fprintf(stderr, "[psb] scan_box: %d ranges submitted at %.3f ms\n", n_gpus, since());
     for (int d = 0; d < n_gpus; ++d) {
         if (cut[d + 1] <= cut[d]) continue;
         box_worker(d)->wait();
+        if (dbg) std::fprintf(stderr, "[psb] scan_box: device %d done at %.3f ms\n", d, since());
         if (rcs[d] != PSB_OK && rc == PSB_OK) { rc = rcs[d]; set_error("psb_scan_box (device " + std::to_string(d) + "): " + errs[d]); }
         b->n_retried += retried[d];
         c.last_ms = std::max(c.last_ms, ms[d]);   // the devices run side by side: the slowest one

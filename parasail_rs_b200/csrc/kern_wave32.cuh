@@ -419,21 +419,21 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
 //   * residues: a 64-column shared ring refilled every 8 steps from registers loaded one refill early;
 //   * columns past the end of the subject carry a pad letter scoring -128.  Local: their H is a decayed
 //     E of a real cell, which can never beat that cell (strict >), so the step has no column mask, and the
-//     end cell is key = (H << BITS) + (K*C-1 - (c*K + k)) -- the maximum prefers the smaller column, then
-//     the smaller row -- with a branch-free update of (best key, best block).  Global / semi-global
+//     end cell is the column maximum (one VIMNMX3 per two rows) tested against the lane's best per column --
+//     strict >, so the smaller column wins ties, and the cold branch takes the first row.  Global / semi-global
 //     (IS_SW = false): nothing reads a pad column's cells, the last row and last column are looked at
 //     per column as in generation 2.
 // `bnd` must be zero-filled before the launch; `progress` is not used by this generation.
-inline size_t wave32v3_smem_bytes(int size, int warps) {
-    return (((size_t)size * size * sizeof(int) + 15) & ~(size_t)15) + (size_t)warps * (64 + (size_t)(size + 1) * 512);
+// per warp: a 64-residue ring and a profile of 32-bit (S + open) words, [letter][4-row chunk][lane][16 B]
+inline size_t wave32v3_smem_bytes(int size, int warps, int K) {
+    return (((size_t)size * size * sizeof(int) + 15) & ~(size_t)15) + (size_t)warps * (64 + (size_t)(size + 1) * ((K + 3) / 4) * 512);
 }
 // local: scores must leave room for the tile index below them in the 32-bit key; every mode: |H - open|
 // stays below 2^30 (the hand-over words keep their validity mark in the top two bits of T)
 inline bool wave32v3_range_ok(int K, int C, bool is_sw, long long lq, long long lr, int max_score, int min_score, int open, int gap) {
-    int bits = 0;
-    while ((1 << bits) < K * C) ++bits;
+    (void)K; (void)C;
     const long long up = (lq < lr ? lq : lr) * (long long)(max_score > 1 ? max_score : 1);
-    if (is_sw) return up < (1ll << (30 - bits));
+    if (is_sw) return up < (1ll << 29);
     long long step = -(long long)min_score;
     if (gap > step) step = gap;
     if (step < 1) step = 1;
@@ -446,15 +446,14 @@ PSB_DEV long long wave32v3_pack(int T, int F) { return (long long)(((unsigned lo
 template <int K, int C, bool IS_SW>
 PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     static_assert(C == 4, "four residues travel in one word");
-    static_assert(K <= 16, "one 16-byte profile slot per lane and letter");
-    constexpr int KC = K * C;
-    constexpr int BITS = KC <= 16 ? 4 : (KC <= 32 ? 5 : 6);
+    static_assert(K <= 16 && K % 4 == 0, "rows per lane come in 16-byte profile chunks of four");
+    constexpr int CH = K / 4;
     PSB_SHARED_DECL(smem_raw);
     const int lane = lane_id();
     const int size = p.size, o = p.open, e = p.gap;
     int *smat = (int *)smem_raw;
     const size_t mat_bytes = (((size_t)size * size * sizeof(int)) + 15) & ~(size_t)15;
-    const size_t per_warp = 64 + (size_t)(size + 1) * 512;
+    const size_t per_warp = 64 + (size_t)(size + 1) * CH * 512;
     unsigned char *wsm = smem_raw + mat_bytes + (size_t)warp_in_block() * per_warp;
     uint8_t *ringL = (uint8_t *)wsm;                     // 64 residues
     unsigned char *wprof = wsm + 64;
@@ -470,7 +469,10 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     const int rows_per_strip = 32 * K;
     const int nstrips = (Lq + rows_per_strip - 1) / rows_per_strip;
     const int nitems = nstrips * (p.multi_n > 0 ? p.multi_n : 1);
-    const long long top_edge = wave32v3_pack(-o, NEG_INF32);   // H = 0, no F (local / free top edge)
+    // hand-over words carry T = H - o and Fh = F + o of the row below (the vertical gap of the next row,
+    // ready to use: the one-instruction chain of kern_pairs16.cuh).  Free / local top edge: H = 0, so
+    // T = -o and Fh = H = 0 (F opened from the edge).
+    const long long top_edge = wave32v3_pack(-o, 0);
 
     for (;;) {
         int item = 0;
@@ -489,22 +491,23 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
         const long long *bnd_in = bnd0 + (long long)(strip - 1) * Lr;
         long long *bnd_out = bnd0 + (long long)strip * Lr;
 
-        // per-warp int8 profile of this strip: [letter][lane][16 rows] of (S + open); pad rows and the
-        // pad letter (index `size`) are -128
+        // per-warp profile of this strip: 32-bit (S + open) words, [letter][chunk][lane][4 rows]; pad rows and
+        // the pad letter (index `size`) score -128.  One LDS.128 per four rows, no sign extension per cell.
         sync_warp();
         for (int a = 0; a <= size; ++a) {
-            unsigned wv[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
-            if (a < size) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    if (i0 + k < Lq) {
-                        const unsigned b = (unsigned)smat[(int)p.q[i0 + k] * size + a] & 0xffu;
-                        wv[k >> 2] = (wv[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (b << (8 * (k & 3)));
+            for (int ch = 0; ch < CH; ++ch) {
+                int wv[4] = {-128, -128, -128, -128};
+                if (a < size) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const int k = 4 * ch + k4;
+                        if (i0 + k < Lq) wv[k4] = smat[(int)p.q[i0 + k] * size + a];
                     }
                 }
+                uint4 v; v.x = (unsigned)wv[0]; v.y = (unsigned)wv[1]; v.z = (unsigned)wv[2]; v.w = (unsigned)wv[3];
+                *(uint4 *)(wprof + (((size_t)a * CH + ch) * 32 + lane) * 16) = v;
             }
-            uint4 v; v.x = wv[0]; v.y = wv[1]; v.z = wv[2]; v.w = wv[3];
-            *(uint4 *)(wprof + ((size_t)a * 32 + lane) * 16) = v;
         }
         int T[K], E[K];
 #pragma unroll
@@ -515,9 +518,9 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
         int Tdiag_in = (i0 == 0) ? -o : ((left_free ? 0 : -o - (i0 - 1) * e) - o);
         int Tout[C], Fout[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) { Tout[c] = -o; Fout[c] = NEG_INF32; }
+        for (int c = 0; c < C; ++c) { Tout[c] = -o; Fout[c] = 0; }
         unsigned Lw_out = 0;
-        int bestH = IS_SW ? 0 : NEG_INF32, bestKey = 0, bestB = 0;    // local: a score must exceed 0 to count
+        int bestH = IS_SW ? 0 : NEG_INF32;    // local: a score must exceed 0 to count
         int bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
         const int klast = (Lq - 1) - i0;
         const int t_claim = wave_time_us();   // debugging aid (PSB_DEBUG_TIMING): when the strip was claimed
@@ -556,9 +559,9 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) { Tup[c] = (int)((unsigned)W[c] ^ 0x40000000u); Fup[c] = (int)((unsigned long long)W[c] >> 32); }
                 if (!IS_SW && strip == 0 && !top_free) {
-                    // top edge of a global alignment: H(-1, j) = -o - j*e
+                    // top edge of a global alignment: H(-1, j) = -o - j*e, F(0, j) opened from it
 #pragma unroll
-                    for (int c = 0; c < C; ++c) Tup[c] = -o - (C * s + c) * e - o;
+                    for (int c = 0; c < C; ++c) { Fup[c] = -o - (C * s + c) * e; Tup[c] = Fup[c] - o; }
                 }
                 Lw = *(const unsigned *)(ringL + ((C * s) & 63));
                 if (strip > 0) {
@@ -571,52 +574,57 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
             Lw_out = Lw;
             if (b >= 0 && b < nblk) {
-                int cmax = -0x7fffffff - 1;
                 int Tdg = Tdiag_in;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const unsigned letter = (Lw >> (8 * c)) & 0xffu;
-                    const uint4 pv = *(const uint4 *)(wprof + ((size_t)letter * 32 + lane) * 16);
-                    const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w};
+                    int So[K];
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) {
+                        const uint4 pv = *(const uint4 *)(wprof + (((size_t)letter * CH + ch) * 32 + lane) * 16);
+                        So[4 * ch] = (int)pv.x; So[4 * ch + 1] = (int)pv.y; So[4 * ch + 2] = (int)pv.z; So[4 * ch + 3] = (int)pv.w;
+                    }
                     int Td = Tdg;
-                    int Fk = viaddmax(Fup[c], -e, Tup[c]);
-                    int Tlast = 0, Flast = 0;
+                    int Fk = Fup[c];            // Fh = F + o of this lane's first row
+                    int cm = NEG_INF32, hp = NEG_INF32;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const unsigned SEL = (unsigned)(k & 3) * 0x1111u + 0x8880u;
-                        const int So = (int)prmt(pw[k >> 2], 0u, SEL);
                         const int Tl = T[k];
                         const int En = viaddmax(E[k], -e, Tl);
-                        const int h0 = IS_SW ? viaddmax_relu(Td, So, En) : viaddmax(Td, So, En);
-                        const int H = h0 > Fk ? h0 : Fk;
-                        const int Fnext = viaddmax(Fk, -e, h0 - o);   // the only dependent op per row
+                        const int h = viaddmax(Td, So[k], En);
+                        const int H = IS_SW ? viaddmax_relu(Fk, -o, h) : viaddmax(Fk, -o, h);
+                        Fk = viaddmax(Fk, -e, h);        // the only loop-carried op per row
                         Td = Tl;
                         if (IS_SW) {
-                            const int key = (H << BITS) + (KC - 1 - (c * K + k));
-                            cmax = cmax > key ? cmax : key;
+                            if (k & 1) cm = vimax3(cm, hp, H);
+                            else hp = H;
                         }
-                        if (k == K - 1) { Tlast = H - o; Flast = Fk; }
                         T[k] = H - o; E[k] = En;
-                        Fk = Fnext;
                     }
-                    Tout[c] = Tlast; Fout[c] = Flast;
+                    Tout[c] = T[K - 1]; Fout[c] = Fk;
                     Tdg = Tup[c];
-                    if (!IS_SW) {
-                        const int j = C * b + c;
-                        if (j < Lr) {
-                            if (last_strip && klast >= 0 && klast < K && (row_ends || (j == Lr - 1 && !col_ends))) {
-                                // last row: sg scans it left to right (strict >); nw reads the corner only
-                                int hv = 0;
+                    const int j = C * b + c;
+                    if (IS_SW) {
+                        // the column maximum must strictly exceed the lane's best: smaller columns win ties; the cold
+                        // branch finds the first row that holds it (pad columns only carry decayed values: never taken)
+                        if (cm > bestH) {
+                            bestH = cm; bestJ = j;
 #pragma unroll
-                                for (int k = 0; k < K; ++k) if (k == klast) hv = T[k] + o;
-                                if (hv > bestH) { bestH = hv; bestJ = j; bestI = Lq - 1; }
-                            }
-                            if (col_ends && j == Lr - 1) {
+                            for (int k = K - 1; k >= 0; --k) if (T[k] + o == cm) bestI = i0 + k;
+                        }
+                    } else if (j < Lr) {
+                        if (last_strip && klast >= 0 && klast < K && (row_ends || (j == Lr - 1 && !col_ends))) {
+                            // last row: sg scans it left to right (strict >); nw reads the corner only
+                            int hv = 0;
 #pragma unroll
-                                for (int k = 0; k < K; ++k) {
-                                    const int hv = T[k] + o;
-                                    if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
-                                }
+                            for (int k = 0; k < K; ++k) if (k == klast) hv = T[k] + o;
+                            if (hv > bestH) { bestH = hv; bestJ = j; bestI = Lq - 1; }
+                        }
+                        if (col_ends && j == Lr - 1) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const int hv = T[k] + o;
+                                if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
                             }
                         }
                     }
@@ -626,12 +634,6 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         if (C * b + c < Lr) st_relaxed64(bnd_out + C * b + c, wave32v3_pack(Tout[c], Fout[c]));
-                }
-                if (IS_SW) {
-                    const bool upd = (cmax >> BITS) > bestH;
-                    bestH = upd ? (cmax >> BITS) : bestH;
-                    bestKey = upd ? cmax : bestKey;
-                    bestB = upd ? b : bestB;
                 }
             }
         };
@@ -651,15 +653,7 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
         }
         sync_warp();
-        if (IS_SW) {
-            if (bestH > 0) {
-                const int idx = KC - 1 - (bestKey & ((1 << BITS) - 1));
-                bestJ = C * bestB + idx / K;
-                bestI = i0 + idx % K;
-            } else {
-                bestH = NEG_INF32;
-            }
-        }
+        if (IS_SW && bestH <= 0) bestH = NEG_INF32;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
             const int oH = shfl_xor(bestH, m), oJ = shfl_xor(bestJ, m), oI = shfl_xor(bestI, m);

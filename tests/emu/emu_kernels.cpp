@@ -79,7 +79,7 @@ extern "C" void emu_wave32_use_v2(int on) { g_wave_v2 = on == 1; g_wave_gen = on
 extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams *rp, int nblocks) {
     Wave32Params p = *pp;
     if (g_wave_gen == 3) {
-        size_t smem3 = wave32v3_smem_bytes(p.size, 1);
+        size_t smem3 = wave32v3_smem_bytes(p.size, 1, K);
         switch (K) {
 #define W3CASE(KK) case KK: if (p.mode == MODE_SW) emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<KK, 4, true>(p); }); else emu::launch(nblocks, smem3, [&]() { wave32v3_kernel<KK, 4, false>(p); }); break;
             W3CASE(4) W3CASE(8) W3CASE(16)
