@@ -1746,7 +1746,10 @@ static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile
     if (const char *ev = std::getenv("PSB_SCAN_HOST_PIECE_MB")) piece_mb = std::max(8ll, std::atoll(ev));
     if (const char *ev = std::getenv("PSB_SCAN_HOST_FIRST_MB")) first_mb = std::max(1ll, std::atoll(ev));
     const int64_t piece = piece_mb << 20;
-    const int64_t first = total > (first_mb << 20) + piece / 4 ? (first_mb << 20) : total;
+    // the first piece only has to be large enough to keep the GPU busy until the second has landed: a sixth
+    // of the range, between 4 MB and first_mb (a 1/8 shard of C2, 45 MB, is scanned as 7.5 MB + 37.5 MB)
+    const int64_t first_cap = std::min<int64_t>(first_mb << 20, std::max<int64_t>((int64_t)4 << 20, total / 6));
+    const int64_t first = total > first_cap + ((int64_t)4 << 20) ? first_cap : total;
     const int nrest = first == total ? 0 : (int)std::max<int64_t>(1, std::min<int64_t>(30, (total - first + piece * 3 / 4) / piece));
     const int npieces = (int)std::min<int64_t>(n, 1 + nrest);
     std::vector<int64_t> cut(npieces + 1, n);

@@ -80,7 +80,7 @@ inline bool pairs16_fits(int rows, int lq, int lr, int smax, int smin, int open,
     const long long pos = (long long)(lq < lr ? lq : lr) * (smax > 0 ? smax : 0) + 2ll * open + 256;
     const long long neg = 3ll * open + (long long)(rows + lr + 4) * gap + 256 + (smin < 0 ? -smin : 0);
     const long long lim = sw ? 32000 : 16000;
-    return pos < lim && neg < lim;
+    return pos < lim && neg < lim && lr <= 65000;   // end columns travel as 16-bit halves
 }
 // trace / stats: neighbouring cells must differ by less than 128 so that one byte of H per cell is enough
 inline bool pairs16_trace_ok(int mat_min, int mat_max, int open) {

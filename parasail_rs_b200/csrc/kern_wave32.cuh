@@ -419,8 +419,10 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
 //   * residues: a 64-column shared ring refilled every 8 steps from registers loaded one refill early;
 //   * columns past the end of the subject carry a pad letter scoring -128.  Local: their H is a decayed
 //     E of a real cell, which can never beat that cell (strict >), so the step has no column mask, and the
-//     end cell is the column maximum (one VIMNMX3 per two rows) tested against the lane's best per column --
-//     strict >, so the smaller column wins ties, and the cold branch takes the first row.  Global / semi-global
+//     end cell is key = (H << BITS) + (K*C-1 - (c*K + k)) -- the maximum prefers the smaller column, then
+//     the smaller row -- with a branch-free update of (best key, best block) (a per-column test of the column
+//     maximum was measured: its four branches per step cost a lone warp more than the two instructions per
+//     cell of the key).  Global / semi-global
 //     (IS_SW = false): nothing reads a pad column's cells, the last row and last column are looked at
 //     per column as in generation 2.
 // `bnd` must be zero-filled before the launch; `progress` is not used by this generation.
@@ -431,9 +433,10 @@ inline size_t wave32v3_smem_bytes(int size, int warps, int K) {
 // local: scores must leave room for the tile index below them in the 32-bit key; every mode: |H - open|
 // stays below 2^30 (the hand-over words keep their validity mark in the top two bits of T)
 inline bool wave32v3_range_ok(int K, int C, bool is_sw, long long lq, long long lr, int max_score, int min_score, int open, int gap) {
-    (void)K; (void)C;
+    int bits = 0;
+    while ((1 << bits) < K * C) ++bits;
     const long long up = (lq < lr ? lq : lr) * (long long)(max_score > 1 ? max_score : 1);
-    if (is_sw) return up < (1ll << 29);
+    if (is_sw) return up < (1ll << (30 - bits));
     long long step = -(long long)min_score;
     if (gap > step) step = gap;
     if (step < 1) step = 1;
@@ -448,6 +451,8 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     static_assert(C == 4, "four residues travel in one word");
     static_assert(K <= 16 && K % 4 == 0, "rows per lane come in 16-byte profile chunks of four");
     constexpr int CH = K / 4;
+    constexpr int KC = K * C;
+    constexpr int BITS = KC <= 16 ? 4 : (KC <= 32 ? 5 : 6);
     PSB_SHARED_DECL(smem_raw);
     const int lane = lane_id();
     const int size = p.size, o = p.open, e = p.gap;
@@ -520,7 +525,7 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
 #pragma unroll
         for (int c = 0; c < C; ++c) { Tout[c] = -o; Fout[c] = 0; }
         unsigned Lw_out = 0;
-        int bestH = IS_SW ? 0 : NEG_INF32;    // local: a score must exceed 0 to count
+        int bestH = IS_SW ? 0 : NEG_INF32, bestKey = 0, bestB = 0;    // local: a score must exceed 0 to count
         int bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
         const int klast = (Lq - 1) - i0;
         const int t_claim = wave_time_us();   // debugging aid (PSB_DEBUG_TIMING): when the strip was claimed
@@ -574,6 +579,7 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
             Lw_out = Lw;
             if (b >= 0 && b < nblk) {
+                int cmax = -0x7fffffff - 1;
                 int Tdg = Tdiag_in;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -586,7 +592,6 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     }
                     int Td = Tdg;
                     int Fk = Fup[c];            // Fh = F + o of this lane's first row
-                    int cm = NEG_INF32, hp = NEG_INF32;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int Tl = T[k];
@@ -596,23 +601,16 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                         Fk = viaddmax(Fk, -e, h);        // the only loop-carried op per row
                         Td = Tl;
                         if (IS_SW) {
-                            if (k & 1) cm = vimax3(cm, hp, H);
-                            else hp = H;
+                            // branch-free end cell: the maximum of (H, inverted tile index) prefers the smaller column, then the smaller row
+                            const int key = (H << BITS) + (KC - 1 - (c * K + k));
+                            cmax = cmax > key ? cmax : key;
                         }
                         T[k] = H - o; E[k] = En;
                     }
                     Tout[c] = T[K - 1]; Fout[c] = Fk;
                     Tdg = Tup[c];
                     const int j = C * b + c;
-                    if (IS_SW) {
-                        // the column maximum must strictly exceed the lane's best: smaller columns win ties; the cold
-                        // branch finds the first row that holds it (pad columns only carry decayed values: never taken)
-                        if (cm > bestH) {
-                            bestH = cm; bestJ = j;
-#pragma unroll
-                            for (int k = K - 1; k >= 0; --k) if (T[k] + o == cm) bestI = i0 + k;
-                        }
-                    } else if (j < Lr) {
+                    if (!IS_SW && j < Lr) {
                         if (last_strip && klast >= 0 && klast < K && (row_ends || (j == Lr - 1 && !col_ends))) {
                             // last row: sg scans it left to right (strict >); nw reads the corner only
                             int hv = 0;
@@ -635,6 +633,12 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     for (int c = 0; c < C; ++c)
                         if (C * b + c < Lr) st_relaxed64(bnd_out + C * b + c, wave32v3_pack(Tout[c], Fout[c]));
                 }
+                if (IS_SW) {
+                    const bool upd = (cmax >> BITS) > bestH;
+                    bestH = upd ? (cmax >> BITS) : bestH;
+                    bestKey = upd ? cmax : bestKey;
+                    bestB = upd ? b : bestB;
+                }
             }
         };
         for (int s0 = 0; s0 < nsteps; s0 += 8) {
@@ -653,7 +657,15 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
         }
         sync_warp();
-        if (IS_SW && bestH <= 0) bestH = NEG_INF32;
+        if (IS_SW) {
+            if (bestH > 0) {
+                const int idx = KC - 1 - (bestKey & ((1 << BITS) - 1));
+                bestJ = C * bestB + idx / K;
+                bestI = i0 + idx % K;
+            } else {
+                bestH = NEG_INF32;
+            }
+        }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
             const int oH = shfl_xor(bestH, m), oJ = shfl_xor(bestJ, m), oI = shfl_xor(bestI, m);

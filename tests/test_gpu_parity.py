@@ -522,3 +522,20 @@ def test_scan_long_query_strip_wise(ps, oracle, blosum62, lq):
     ecat, eoff = psb_data.concat(extra)
     cat = np.concatenate([cat, ecat]); off = np.concatenate([off, eoff[1:] + off[-1]])
     scan_case(ps, oracle, blosum62, query, cat, off)
+
+
+def test_pairs16_edge_shapes(ps, oracle):
+    # 1 x 1, 1 x n, n x 1, zero gap penalties with a reference beyond 65 000 columns (takes the 32-bit path), lower case, N
+    dna, odna = ps.Matrix.create(b"ACGT", 2, -3), oracle.Matrix.create(b"ACGT", 2, -3)
+    s = lambda b: np.frombuffer(b, dtype=np.uint8)
+    qs = [s(b"A"), s(b"A"), s(b"ACGTACGTAC"), s(b"acgtnACGT"), psb_data.random_seq(601, 0, 40, protein=False)]
+    rs = [s(b"A"), s(b"TTTTACGT"), s(b"G"), s(b"ACGTNNACGT"), psb_data.random_seq(601, 1, 70000, protein=False)]
+    for mode in (0, 1, 2):
+        for gaps in ((5, 2), (0, 0)):
+            for kind in ("score", "stats", "trace"):
+                bl = builder(ps, mode, dna, *gaps)
+                bl = bl.use_stats() if kind == "stats" else (bl.use_trace() if kind == "trace" else bl)
+                got = bl.build().align_batch(qs, rs)
+                exp = oracle_batch(oracle, qs, rs, odna, mode, *gaps, stats=(kind == "stats"), cigar=(kind == "trace"))
+                keys = KEYS6 if kind == "stats" else (KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops") if kind == "trace" else KEYS3)
+                assert_same(got, exp, keys, f"mode {mode} gaps {gaps} {kind}")
