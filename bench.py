@@ -160,11 +160,11 @@ def main():
     guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--db", type=int, default=1000000, help="number of database proteins (C2: 1M)")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-sample", type=int, default=200000, help="subjects of the CPU-baseline sample (rank 0, N=1)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -325,10 +325,10 @@ def main():
     roofline = {
         "bound": "int_alu_dpx", "achieved": achieved, "peak": peak_s16, "unit": "GCUPS", "frac": achieved / peak_s16,
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch on a 200k-subject
-        # scan (profiles/r1e_ncu_full_sw16_keymetrics.csv: 51.76 MB + 0.16 MB for 47.6 MB of packed
-        # residues + 2.4 MB of results), scaled to this launch's algorithmic bytes
-        "traffic": packed_bytes * (51.761152e6 + 0.164352e6) / (47.589941e6 + 2.4e6),
-        "traffic_source": "ncu --set full capture of round 1 (200k subjects), scaled by algorithmic bytes; not measured in this run",
+        # scan (profiles/r2j_ncu_sw16_C2_keymetrics.csv: 51.76 MB + 0.06 MB for 47.6 MB of packed
+        # residues + 2.4 MB of results, which leave L2 later), scaled to this launch's algorithmic bytes
+        "traffic": packed_bytes * (51.763968e6 + 0.058112e6) / (47.589941e6 + 2.4e6),
+        "traffic_source": "ncu --set full capture profiles/r2j_ncu_sw16_C2 (200k subjects, this build), scaled by algorithmic bytes; not measured in this run",
         "kernel": "sw16_scan_kernel<25> (packed s16x2 DPX, 16-lane groups)", "kernel_ms_per_launch": float(kms.item()),
         "peak_basis": f"148 SM x {LANE_OPS_PER_CLK_SM} lane-ops/clk x {sm_mhz:.0f} MHz (sampled) / {OPS_PER_CELL} ops per cell x 2 cells per s16x2 op",
         "peak_at_max_clock": 148 * LANE_OPS_PER_CLK_SM * 1.965 / OPS_PER_CELL * 2,

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
 #include <cstdio>
@@ -1107,6 +1108,19 @@ static const void *sw16_fn(int K, bool strip = false) {
 
 static constexpr int kSw16WarpsPerBlock = SW16_WARPS_PER_BLOCK;
 
+// measured scan rate (cell updates per second) per rows-per-lane class, exponentially averaged over the
+// single-strip scan jobs of this process that were large enough to be meaningful
+static std::atomic<double> g_sw16_rate[33];
+static double sw16_rate_get(int K) {
+    const double r = g_sw16_rate[K & 31].load(std::memory_order_relaxed);
+    return r > 1e11 ? r : 4.9e12;
+}
+static void sw16_rate_update(int K, double cells, double ms) {
+    if (cells < 2e9 || ms <= 0.05) return;
+    const double now = cells / (ms * 1e-3), old = g_sw16_rate[K & 31].load(std::memory_order_relaxed);
+    g_sw16_rate[K & 31].store(old > 1e11 ? 0.7 * old + 0.3 * now : now, std::memory_order_relaxed);
+}
+
 // packed 16-bit local scan of the whole database.  Subjects that leave the 16-bit range are
 // re-run by the 32-bit per-pair kernel; subjects too long for 16-bit column indices go to the
 // multi-pair wavefront kernel.  The sweep of one subject is serial in its length, and on an SM
@@ -1122,10 +1136,14 @@ static int scan_sw16(const FnConfig &cfg, const parasail_profile *prof, DevProfi
     const bool multi = strips.size() > 1;
     const HostMatrix &m = prof->matrix;
     const int lq = (int)prof->query.size();
-    // one group step costs ~0.6 us when the SM is full; keep a subject's sweep under ~40 % of the
-    // time the whole shard needs at ~4.9 TCUPS
-    const double est_ms = (double)lq * (double)db->residues / 4.9e9;
-    const double long_len = std::max(1024.0, 0.4 * est_ms / 0.62e-3);
+    // Keep a subject's serial sweep under ~40 % of the time the whole shard needs.  Both figures follow from
+    // ONE quantity, the scan rate of this kernel class on this device, which is measured, not assumed: every
+    // finished scan job updates it (scan_finish); 4.9 TCUPS is only the value before the first measurement.
+    // A group step advances 64*K cells of one of the SM's 16 resident warps: step = 64*K*16*SMs / rate.
+    const double rate = sw16_rate_get(sp.K);
+    const double est_ms = (double)lq * (double)db->residues / rate * 1e3;
+    const double step_ms = 64.0 * sp.K * 16.0 * c.sms / rate * 1e3;
+    const double long_len = std::max(1024.0, 0.4 * est_ms / step_ms);
     int64_t nroute = 0;
     while (nroute < (int64_t)db->top_len.size() && db->top_len[nroute] > 65535) ++nroute;
     int64_t nhead = nroute;
@@ -1636,6 +1654,8 @@ struct ScanJob {
     int64_t retried = 0;
     int *retried_host = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;   // kernels begin / end, results on the host
+    int rate_k = 0;          // > 0: a single-strip packed scan of `rate_cells` cells (feeds the measured rate)
+    double rate_cells = 0;
     ScanJob() = default;
     ScanJob(const ScanJob &) = delete;
     ScanJob &operator=(const ScanJob &) = delete;
@@ -1663,6 +1683,7 @@ static int scan_enqueue(ScanJob &job, const FnConfig &cfg, const parasail_profil
     std::vector<Sw16Profile> sp16;
     const bool fast = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64 && sw16_prepare(profile, dp, open, gap, &sp16);
     int rc;
+    if (fast && sp16.size() == 1 && db->nlong == 0) { job.rate_k = sp16[0].K; job.rate_cells = (double)profile->query.size() * (double)db->residues; }
     if (fast) rc = scan_sw16(cfg, profile, dp, sp16, open, gap, db, outp, &job.retried, job.retried_host);
     else rc = scan_general(cfg, profile, dp, open, gap, db, nullptr, 0, nullptr, outp);
     if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); return rc; }
@@ -1681,6 +1702,7 @@ static int scan_finish(ScanJob &job) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, job.ev0, job.ev1) == cudaSuccess) c.last_ms += ms;
     if (std::getenv("PSB_DEBUG_TIMING")) std::fprintf(stderr, "[psb] scan job: %.3f ms, %d re-run at 32 bit\n", ms, *job.retried_host);
+    if (job.rate_k > 0) sw16_rate_update(job.rate_k, job.rate_cells, ms);
     job.retried += *job.retried_host;
     return PSB_OK;
 }

@@ -22,7 +22,16 @@ def main():
     rep, out = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    # several launches in one report: the longest one is the kernel of interest (the others are its small companions)
+    it = hdr.index("gpu__time_duration.sum")
+    def dur(r):
+        try:
+            return float(r[it].replace(",", "")) * (1000.0 if False else 1.0)
+        except (ValueError, IndexError):
+            return -1.0
+    iu = units[it]
+    vals = max(rows[2:], key=lambda r: float(r[hdr.index("sm__cycles_elapsed.max")].replace(",", "")) if len(r) > it and r[it] else -1)
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     with open(out + "_keymetrics.csv", "w") as f:
         w = csv.writer(f)
