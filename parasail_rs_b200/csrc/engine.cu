@@ -1068,18 +1068,7 @@ static bool sw16_prepare(const parasail_profile *prof, DevProfile *dp, int open,
     return ok && sw16_supported(built[0], open, gap);
 }
 
-#ifdef PSB_SW16X
-// experiment build (-DPSB_SW16X): the split-column variant of the scan kernel for K >= 8
-}  // namespace psb
-#include "kern_sw16x.cuh"
-namespace psb {
-template <int K> static const void *sw16_fn_k() {
-    if constexpr (K >= 8) return (const void *)sw16x_scan_kernel<K>;
-    else return (const void *)sw16_scan_kernel<K>;
-}
-#else
 template <int K> static const void *sw16_fn_k() { return (const void *)sw16_scan_kernel<K>; }
-#endif
 template <int K> static const void *sw16_strip_fn_k() { return (const void *)sw16_scan_kernel<K, true>; }
 static const void *sw16_fn(int K, bool strip = false) {
     if (strip) {
@@ -1768,9 +1757,12 @@ static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile
     if (const char *ev = std::getenv("PSB_SCAN_HOST_PIECE_MB")) piece_mb = std::max(8ll, std::atoll(ev));
     if (const char *ev = std::getenv("PSB_SCAN_HOST_FIRST_MB")) first_mb = std::max(1ll, std::atoll(ev));
     const int64_t piece = piece_mb << 20;
-    // the first piece only has to be large enough to keep the GPU busy until the second has landed: a sixth
-    // of the range, between 4 MB and first_mb (a 1/8 shard of C2, 45 MB, is scanned as 7.5 MB + 37.5 MB)
-    const int64_t first_cap = std::min<int64_t>(first_mb << 20, std::max<int64_t>((int64_t)4 << 20, total / 6));
+    // the first piece only has to be large enough to keep the GPU busy until the second has landed: a quarter
+    // of the range, between 4 MB and first_mb (a 1/8 shard of C2, 45 MB, is scanned as 11 MB + 34 MB: measured
+    // 4.64 ms against 5.05 ms in one piece and 4.83 ms with a sixth, tools/shard_e2e_probe.py)
+    long long first_div = 4;
+    if (const char *ev = std::getenv("PSB_SCAN_HOST_FIRST_DIV")) first_div = std::max(1ll, std::atoll(ev));
+    const int64_t first_cap = std::min<int64_t>(first_mb << 20, std::max<int64_t>((int64_t)4 << 20, total / first_div));
     const int64_t first = total > first_cap + ((int64_t)4 << 20) ? first_cap : total;
     const int nrest = first == total ? 0 : (int)std::max<int64_t>(1, std::min<int64_t>(30, (total - first + piece * 3 / 4) / piece));
     const int npieces = (int)std::min<int64_t>(n, 1 + nrest);

@@ -60,16 +60,6 @@ extern "C" int emu_sw16(int K, const Sw16Params *pp, int nblocks) {
 }
 extern "C" int emu_sizeof_sw16() { return (int)sizeof(Sw16Params); }
 
-// experimental split-column variant (csrc/kern_sw16x.cuh)
-#include "../../parasail_rs_b200/csrc/kern_sw16x.cuh"
-extern "C" int emu_sw16x(int K, const Sw16Params *pp, int nblocks) {
-    Sw16Params p = *pp;
-    size_t smem = sw16_smem_bytes(p.nletters, K, 1);
-#define SXCASE(KK) case KK: emu::launch(nblocks, smem, [&]() { sw16x_scan_kernel<KK>(p); }); return 0;
-    switch (K) { SXCASE(8) SXCASE(12) SXCASE(16) SXCASE(20) SXCASE(25) SXCASE(28) SXCASE(32) }
-    return -1;
-}
-
 // ---- long-pair wavefront kernel -------------------------------------------------------------------
 #include "../../parasail_rs_b200/csrc/kern_wave32.cuh"
 

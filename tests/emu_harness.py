@@ -134,9 +134,8 @@ def pack_db(subjects_mapped, bits):
     return np.array(words + [0], dtype=np.uint32), word_off, lens, np.array(perm, dtype=np.int32)
 
 
-def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1, split=False):
-    """Run the emulated packed scan kernel: one query vs subjects.  Returns (outs, retry list).
-    split=True runs the experimental split-column variant (csrc/kern_sw16x.cuh; K >= 8 only)."""
+def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1):
+    """Run the emulated packed scan kernel: one query vs subjects.  Returns (outs, retry list)."""
     assert lib().emu_sizeof_sw16() == C.sizeof(Sw16Params)
     mapper = mat.mapper.astype(np.uint8)
     qm = np.ascontiguousarray(mapper[np.asarray(query, dtype=np.uint8)])
@@ -157,7 +156,7 @@ def sw16(query, subjects, mat, open, gap, bits=5, nblocks=1, split=False):
     p = Sw16Params(ptr(prof), mat.size + 1, len(qm), open, gap, mx.value, ptr(words), ptr(word_off), ptr(lens), bits, n,
                    ptr(perm), ptr(outs["score"]), ptr(outs["end_query"]), ptr(outs["end_ref"]), ptr(retry),
                    ptr(retry_count), 0, ptr(counter), None, None, None, 0, 0, 1, 65536)
-    rc = (lib().emu_sw16x if split and K.value >= 8 else lib().emu_sw16)(K.value, C.byref(p), nblocks)
+    rc = lib().emu_sw16(K.value, C.byref(p), nblocks)
     assert rc == 0, (rc, K.value)
     return outs, sorted(int(perm[i]) for i in retry[: retry_count[0]])
 

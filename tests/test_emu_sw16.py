@@ -7,8 +7,8 @@ import emu_harness
 import psb_data
 
 
-def check(oracle, mat, query, subjects, o, e, bits=5, split=False):
-    outs, retry = emu_harness.sw16(query, subjects, mat, o, e, bits, split=split)
+def check(oracle, mat, query, subjects, o, e, bits=5):
+    outs, retry = emu_harness.sw16(query, subjects, mat, o, e, bits)
     for i, s in enumerate(subjects):
         if i in retry:
             continue
@@ -60,32 +60,6 @@ def test_high_scores_stay_in_16_bit(oracle, blosum62):
     subs = [q.copy(), psb_data.random_seq(9, 1, 380), np.concatenate([psb_data.random_seq(9, 2, 60), q[50:300]])]
     outs, retry = check(oracle, blosum62, q, subs, 10, 1)
     assert retry == [] and outs["score"][0] > 2000
-
-
-@pytest.mark.parametrize("lq", [120, 200, 300, 400, 440, 512])
-def test_split_column_variant(oracle, blosum62, lq):
-    # the experimental kernel of csrc/kern_sw16x.cuh (two half-columns per lane, one column apart) must
-    # give the shipped kernel's results: K classes 8..32, related and unrelated subjects, ties, overflow
-    q = psb_data.random_seq(17, 0, lq)
-    subs = []
-    for i in range(9):
-        L = [35, 90, 91, 150, 17, 64, 33, 1, 260][i]
-        if i % 2 == 0:
-            seg = psb_data.mutate(q[: min(lq, L)], 17, 100 + i, 0.2, 0.05)[:L]
-            s = np.concatenate([seg, psb_data.random_seq(18, i, max(0, L - len(seg)))])[:L]
-        else:
-            s = psb_data.random_seq(18, i, L)
-        subs.append(s)
-    subs.append(np.concatenate([q[5:60]] * 4))      # many equal maxima
-    for o, e in ((10, 1), (3, 3), (0, 0)):
-        _, retry = check(oracle, blosum62, q, subs, o, e, split=True)
-        assert retry == []
-    mat = oracle.Matrix.create(b"ACGT", 100, -90)
-    qd = psb_data.random_seq(19, 0, lq, protein=False)
-    subs = [qd.copy(), psb_data.random_seq(19, 1, 380, protein=False), psb_data.random_seq(19, 2, 60, protein=False),
-            psb_data.random_seq(19, 3, 50, protein=False)]
-    _, retry = check(oracle, mat, qd, subs, 5, 2, split=True)
-    assert retry == ([0, 1] if lq * 100 > 32000 else [])
 
 
 @pytest.mark.parametrize("lq,rows", [(100, 64), (130, 64), (300, 128), (400, 192)])

@@ -309,6 +309,22 @@ def test_long_pair_wavefront(ps, oracle, mode):
     assert_same(gb, oracle_batch(oracle, qs, rs, m, mode, 5, 2), KEYS3, f"wave batch mode {mode}")
 
 
+@pytest.mark.parametrize("name", ["sw", "nw", "sg"])
+def test_long_pair_50kb_against_cached_oracle(ps, name):
+    # 50 kb x 50 kb (2.5e9 cells, the scalar oracle needs about a minute per mode): compared with
+    # tests/golden/long_pair_50k.json, the oracle's results for exactly these seeded inputs
+    # (tests/bench_configs.py C5 recipe).  Scores above 32767 -> true 32-bit lanes all the way.
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "long_pair_50k.json")))
+    case = {c["name"]: c for c in g["cases"]}[name]
+    L = g["L"]
+    r = psb_data.random_seq(5001, 0, L, protein=False)
+    q = psb_data.mutate(r, 5001, 1, 0.10, 0.01, protein=False)
+    q = q[:L] if len(q) >= L else np.concatenate([q, psb_data.random_seq(5002, 0, L - len(q), protein=False)])
+    got = builder(ps, case["mode"], ps.Matrix.create(b"ACGT", 2, -3), 5, 2).solution_width(32).build().align(q, r)
+    assert (got.get_score(), got.get_end_query(), got.get_end_ref()) == (case["score"], case["end_query"], case["end_ref"])
+
+
 def test_long_local_pair_column_blocked(ps, oracle, blosum62, monkeypatch):
     # local long pairs take the column-blocked generation of the wavefront kernel (4 columns per step,
     # strips hand over through self-validating 64-bit words): reference lengths around the block size,

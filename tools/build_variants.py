@@ -2,11 +2,10 @@
 """Build tuning / experiment variants of libparasail_b200.so into variants/ (git-ignored, but it travels
 to the GPU box).  Time them against the default build with tools/variant_bench.sh, e.g.
 
-    python tools/build_variants.py sw16x
-    gpurun -- 'tools/variant_bench.sh parasail_rs_b200/libparasail_b200.so variants/lib_sw16x.so'
+    python tools/build_variants.py shifted
+    gpurun -- 'tools/variant_bench.sh parasail_rs_b200/libparasail_b200.so variants/lib_shifted.so'
 
 variants:
-  sw16x     split-column scan kernel (csrc/kern_sw16x.cuh): two half-columns per lane, one column apart
   prof8     scan kernel with the int8 profile joined by PRMT (SW16_PROF32=0)
   nopp      scan kernel without the ping-pong column copies (SW16_PINGPONG=0)
   shifted   scan kernel with round 1's shifted recurrence (three dependent instructions per row)
@@ -20,7 +19,6 @@ sys.path.insert(0, ROOT)
 from parasail_rs_b200 import build  # noqa: E402
 
 VARIANTS = {
-    "sw16x": ["PSB_SW16X"],
     "prof8": ["SW16_PROF32=0"],
     "nopp": ["SW16_PINGPONG=0"],
     "shifted": ["SW16_DECOUPLE=0"],
