@@ -289,7 +289,7 @@ def main():
             dist.barrier(group=cpu_group)
     host_barrier()
     if rank == 0:
-        for _ in range(4):   # warm-up: contexts of the worker threads, pool growth, staging and pinned result blocks
+        for _ in range(6):   # warm-up: contexts of the worker threads, pool growth, staging and pinned result blocks, measured rates of the piece plan
             e2e_res = e2e_step()
     host_barrier()
     e2e_wall = 0.0

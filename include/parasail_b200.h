@@ -320,6 +320,10 @@ int psb_batch_topk(const psb_batch_t *batch, int k, int64_t *idx_out, int *score
 /* residue-count balanced sharding of a database across n_shards GPUs: writes
  * shard_of[i] in [0, n_shards) for each of the n sequences. */
 int psb_shard_plan(const int64_t *off, int64_t n, int n_shards, int *shard_of);
+/* how psb_scan_host / psb_scan_box cut a host database of `total` residues into pipelined pieces, given the
+ * upload time and the scan time per residue (ms per byte; the library measures both while it runs): writes up
+ * to `cap` piece sizes (bytes) and returns their number.  Host-only; exported so the plan can be inspected. */
+int psb_host_scan_plan(int64_t total, double upload_ms_per_byte, double scan_ms_per_byte, int64_t *sizes_out, int cap);
 
 /* device-time of the kernels of the last batch call on this thread, in milliseconds, and how
  * many kernel launches it issued (bench.py's gpu_launches) */

@@ -722,6 +722,15 @@ def shard_plan(offsets, n_shards):
     return out
 
 
+def host_scan_plan(total, upload_ms_per_byte, scan_ms_per_byte):
+    """piece sizes (bytes) psb_scan_host / psb_scan_box would use for `total` residues at the given rates"""
+    out = np.zeros(256, dtype=np.int64)
+    k = lib().psb_host_scan_plan(int(total), float(upload_ms_per_byte), float(scan_ms_per_byte), out.ctypes.data_as(C.c_void_p), len(out))
+    if k < 0:
+        raise Error(last_error())
+    return out[:min(k, len(out))].tolist()
+
+
 def kernel_ms():
     return float(lib().psb_last_kernel_ms())
 

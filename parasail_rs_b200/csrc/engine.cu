@@ -1470,7 +1470,11 @@ struct DbBuild {
     void *st_raw = nullptr, *st_off = nullptr;
     size_t st_raw_bytes = 0, st_off_bytes = 0;
     int st_device = 0;
-    cudaEvent_t uploaded = nullptr;
+    cudaEvent_t offs_up = nullptr;   // copy stream: the offsets have landed (enough for lengths / sort / word offsets)
+    cudaEvent_t res_begin = nullptr; // copy stream: the residue copy begins (timing, feeds the measured upload rate)
+    cudaEvent_t uploaded = nullptr;  // copy stream: the residues have landed too
+    cudaEvent_t packed = nullptr;    // compute stream: this piece's sort/pack chain has run (gates the next piece's residue upload)
+    cudaStream_t up = nullptr;     // the stream the uploads were queued on
     long long raw_base = 0;
     unsigned lut[64];
     uint8_t *raw() const { return st_raw ? (uint8_t *)st_raw : d_raw.as<uint8_t>(); }
@@ -1481,50 +1485,37 @@ struct DbBuild {
     // the owner synchronises the streams that used the staging blocks before destroying this
     ~DbBuild() {
         if (uploaded) cudaEventDestroy(uploaded);
+        if (offs_up) cudaEventDestroy(offs_up);
+        if (res_begin) cudaEventDestroy(res_begin);
+        if (packed) cudaEventDestroy(packed);
         stage_release(st_device, st_raw, st_raw_bytes);
         stage_release(st_device, st_off, st_off_bytes);
     }
 };
 
-static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int64_t n, const HostMatrix &hm, bool use_copy_stream, int force_bits = 0) {
+// Phase A1: the device-side object and the host->device copies (nothing here looks at the individual offsets,
+// so psb_scan_host can queue the upload of piece k+1 before it spends host time on piece k)
+static psb_db *db_upload(DbBuild &B, const uint8_t *cat, const int64_t *off, int64_t n, const HostMatrix &hm, bool use_copy_stream, int force_bits = 0,
+                         cudaEvent_t residues_after = nullptr) {
     Ctx &c = g_ctx;
     if (hm.size > 32) { set_error("psb_db_create: alphabets above 32 letters cannot be 5-bit packed"); return nullptr; }
+    if (off[n] <= off[0]) { set_error("psb_db_create: offsets are not increasing"); return nullptr; }
     psb_db *db = new psb_db();
     db->device = c.device; db->stream = c.stream; db->n = n; db->msize = hm.size;
     std::memcpy(db->mapper, hm.mapper, 256);
     // 2 bit for alphabets of up to 4 letters, 3 bit up to 8 (ACGT + wildcard: DNA ships at 3 bit), else 5
     db->bits = force_bits ? force_bits : db_bits_for(hm.size);
-    const int rpw = db_residues_per_word(db->bits);
     db->residues = off[n] - off[0];
-    auto fail = [&](const std::string &what) {
-        set_error(what);
-        cudaStreamSynchronize(c.stream);
-        psb_db_free(db);
-        return (psb_db *)nullptr;
-    };
-    // host pass: validation, histogram of lengths (for the longest few), exact packed size
-    std::vector<int> hist(65537, 0);
-    std::vector<int> huge;   // lengths above 65535
-    long long words = 0;
-    int maxlen = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        const int64_t l = off[i + 1] - off[i];
-        if (l <= 0 || l > 0x7fffffff) return fail("psb_db_create: empty or oversized subject " + std::to_string(i));
-        words += (l + rpw - 1) / rpw;
-        if (l > 65535) huge.push_back((int)l); else hist[(size_t)l]++;
-        if (l > maxlen) maxlen = (int)l;
-    }
-    std::sort(huge.begin(), huge.end(), [](int a, int b2) { return a > b2; });
-    db->maxlen = maxlen; db->nlong = (int)huge.size(); db->words = words;
-    db->top_len = huge;
-    if (db->top_len.size() > 4096) db->top_len.resize(4096);
-    for (int l = 65535; l >= 1 && db->top_len.size() < 4096; --l)
-        for (int t = 0; t < hist[l] && db->top_len.size() < 4096; ++t) db->top_len.push_back(l);
-
     const size_t n1 = (size_t)n + 1;
     // with the copy stream, the upload must not queue behind whatever scan is already running on the
     // compute stream: its staging blocks are recycled plain allocations (see StageBlock)
     cudaStream_t up = use_copy_stream ? c.copy : c.stream;
+    auto fail = [&](const std::string &what) {
+        set_error(what);
+        cudaStreamSynchronize(up);
+        psb_db_free(db);
+        return (psb_db *)nullptr;
+    };
     if (use_copy_stream) {
         B.st_device = c.device;
         B.st_raw = stage_acquire(c.device, (size_t)db->residues, &B.st_raw_bytes);
@@ -1533,6 +1524,77 @@ static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int6
     } else if (B.d_raw.alloc((size_t)db->residues, up) != PSB_OK || B.d_off.alloc(n1 * 8, up) != PSB_OK) {
         return fail(psb_last_error());
     }
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    // offsets first: lengths, sort and word offsets need nothing else, so that whole chain of small launches runs
+    // while the residues (the long copy) are still on the link -- under a saturated link each of those launches
+    // costs 30-50 us instead of 5 (measured: 0.6 ms for the chain of the first piece, tools/shard_e2e_probe.py)
+    ck(cudaMemcpyAsync(B.offs(), off, n1 * 8, cudaMemcpyHostToDevice, up));
+    if (use_copy_stream) {
+        ck(cudaEventCreateWithFlags(&B.offs_up, cudaEventDisableTiming));
+        ck(cudaEventRecord(B.offs_up, up));
+        // a saturated link makes every small launch on the device wait its turn for the command fetch (30-50 us
+        // each, measured), so the residues of this piece stay off the link until the previous piece's sort/pack
+        // chain has run; they still have that piece's whole scan to land in
+        if (residues_after) ck(cudaStreamWaitEvent(up, residues_after, 0));
+        ck(cudaEventCreate(&B.res_begin));
+        ck(cudaEventRecord(B.res_begin, up));
+    }
+    ck(cudaMemcpyAsync(B.raw(), cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, up));
+    if (use_copy_stream) {
+        ck(cudaEventCreate(&B.uploaded));
+        ck(cudaEventRecord(B.uploaded, up));
+    }
+    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
+    B.db = db; B.raw_base = off[0]; B.up = up;
+    fill_lut(B.lut, hm.mapper);
+    return db;
+}
+
+// words of `rpw` residues that `l` residues occupy; rpw is one of 16 / 10 / 6 (2, 3, 5 bit): constant
+// divisors, because a 64-bit division per subject was most of this pass
+template <int RPW> static inline long long words_of(long long l) { return (l + RPW - 1) / RPW; }
+
+// Phase A2: one host pass over the offsets (validation, histogram of lengths for the longest few, exact
+// packed size) and the remaining device allocations
+static int db_host_pass(DbBuild &B, const int64_t *off) {
+    Ctx &c = g_ctx;
+    psb_db *db = B.db;
+    const int64_t n = db->n;
+    const int rpw = db_residues_per_word(db->bits);
+    auto fail = [&](const std::string &what) {
+        set_error(what);
+        cudaStreamSynchronize(B.up);
+        cudaStreamSynchronize(c.stream);
+        psb_db_free(db);
+        B.db = nullptr;
+        return PSB_EINVAL;
+    };
+    thread_local std::vector<int> hist;
+    hist.assign(65537, 0);
+    std::vector<int> huge;   // lengths above 65535
+    long long words = 0;
+    int64_t maxlen = 0, bad = -1;
+    auto pass = [&](auto wof) {
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t l = off[i + 1] - off[i];
+            if (l <= 0 || l > 0x7fffffff) { bad = i; return; }
+            words += wof(l);
+            if (l > 65535) huge.push_back((int)l); else hist[(size_t)l]++;
+            maxlen = l > maxlen ? l : maxlen;
+        }
+    };
+    if (rpw == 6) pass(words_of<6>); else if (rpw == 10) pass(words_of<10>); else if (rpw == 16) pass(words_of<16>);
+    else pass([rpw](long long l) { return (l + rpw - 1) / rpw; });
+    if (bad >= 0) return fail("psb_db_create: empty or oversized subject " + std::to_string(bad));
+    std::sort(huge.begin(), huge.end(), [](int a, int b2) { return a > b2; });
+    db->maxlen = (int)maxlen; db->nlong = (int)huge.size(); db->words = words;
+    db->top_len = huge;
+    if (db->top_len.size() > 4096) db->top_len.resize(4096);
+    for (int l = (int)std::min<int64_t>(maxlen, 65535); l >= 1 && db->top_len.size() < 4096; --l)
+        for (int t = 0; t < hist[l] && db->top_len.size() < 4096; ++t) db->top_len.push_back(l);
+
+    const size_t n1 = (size_t)n + 1;
     if (B.d_len0.alloc((size_t)n * 4, c.stream) != PSB_OK || B.d_idx0.alloc((size_t)n * 4, c.stream) != PSB_OK ||
         B.d_wcount.alloc(n1 * 8, c.stream) != PSB_OK)
         return fail(psb_last_error());
@@ -1543,16 +1605,21 @@ static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int6
     ck(cudaMallocAsync(&db->d_len, (size_t)n * 4, c.stream));
     ck(cudaMallocAsync(&db->d_words, (size_t)db->words * 4 + 64, c.stream));
     if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
-    ck(cudaMemcpyAsync(B.offs(), off, n1 * 8, cudaMemcpyHostToDevice, up));
-    ck(cudaMemcpyAsync(B.raw(), cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, up));
-    if (use_copy_stream) {
-        ck(cudaEventCreateWithFlags(&B.uploaded, cudaEventDisableTiming));
-        ck(cudaEventRecord(B.uploaded, up));
-    }
-    if (e != cudaSuccess) return fail(std::string("psb_db_create: ") + cudaGetErrorString(e));
-    B.db = db; B.raw_base = off[0];
-    fill_lut(B.lut, hm.mapper);
-    return db;
+    return PSB_OK;
+}
+
+static psb_db *db_begin(DbBuild &B, const uint8_t *cat, const int64_t *off, int64_t n, const HostMatrix &hm, bool use_copy_stream, int force_bits = 0) {
+    if (!db_upload(B, cat, off, n, hm, use_copy_stream, force_bits)) return nullptr;
+    if (db_host_pass(B, off) != PSB_OK) return nullptr;
+    return B.db;
+}
+
+// PSB_DEBUG_TIMING: extra marks on the compute stream (psb_scan_host's device timeline)
+static thread_local std::vector<cudaEvent_t> *g_dbg_marks = nullptr;
+static void dbg_mark_stream(cudaStream_t st) {
+    if (!g_dbg_marks) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_dbg_marks->push_back(e); }
 }
 
 static int db_finish(DbBuild &B) {
@@ -1561,20 +1628,30 @@ static int db_finish(DbBuild &B) {
     const int64_t n = db->n;
     const size_t n1 = (size_t)n + 1;
     const int rpw = db_residues_per_word(db->bits);
-    if (B.uploaded) PSB_CUDA(cudaStreamWaitEvent(c.stream, B.uploaded, 0));
+    if (B.offs_up) PSB_CUDA(cudaStreamWaitEvent(c.stream, B.offs_up, 0));
+    dbg_mark_stream(c.stream);
     db_lengths_kernel<<<c.sms * 4, 256, 0, c.stream>>>(B.offs(), n, B.d_len0.as<int>(), B.d_idx0.as<int>());
+    dbg_mark_stream(c.stream);
     size_t tb = 0, tb2 = 0;
     PSB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, B.d_len0.as<int>(), db->d_len, B.d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
     PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, B.d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
     PSB_TRY(B.d_tmp.alloc(std::max(tb, tb2), c.stream));
     PSB_CUDA(cub::DeviceRadixSort::SortPairsDescending(B.d_tmp.p, tb, B.d_len0.as<int>(), db->d_len, B.d_idx0.as<int>(), db->d_perm, (int)n, 0, 32, c.stream));
+    dbg_mark_stream(c.stream);
     db_wcount_sorted_kernel<<<c.sms * 4, 256, 0, c.stream>>>(db->d_len, n, rpw, B.d_wcount.as<long long>());
     PSB_CUDA(cub::DeviceScan::ExclusiveSum(B.d_tmp.p, tb2, B.d_wcount.as<long long>(), db->d_word_off, (int)n1, c.stream));
     PackParams pp;
     pp.raw = B.raw(); pp.raw_off = B.offs(); pp.raw_base = B.raw_base; pp.perm = db->d_perm;
     pp.word_off = db->d_word_off; pp.words = db->d_words; pp.n = n; pp.bits = db->bits;
     std::memcpy(pp.lut, B.lut, sizeof(pp.lut));
-    pack_db_kernel<<<c.sms * 8, 256, 0, c.stream>>>(pp);
+    if (B.uploaded) PSB_CUDA(cudaStreamWaitEvent(c.stream, B.uploaded, 0));
+    dbg_mark_stream(c.stream);
+    pack_db_kernel<<<c.sms * 8, 256, 256, c.stream>>>(pp);
+    if (B.uploaded) {
+        PSB_CUDA(cudaEventCreateWithFlags(&B.packed, cudaEventDisableTiming));
+        PSB_CUDA(cudaEventRecord(B.packed, c.stream));
+    }
+    dbg_mark_stream(c.stream);
     c.launches += 5;
     PSB_CUDA(cudaGetLastError());
     // no synchronisation: later work on this stream is ordered after the packing kernel, and the
@@ -1645,6 +1722,7 @@ struct ScanJob {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;   // kernels begin / end, results on the host
     int rate_k = 0;          // > 0: a single-strip packed scan of `rate_cells` cells (feeds the measured rate)
     double rate_cells = 0;
+    bool finished = false;   // scan_finish has run
     ScanJob() = default;
     ScanJob(const ScanJob &) = delete;
     ScanJob &operator=(const ScanJob &) = delete;
@@ -1686,6 +1764,8 @@ static int scan_enqueue(ScanJob &job, const FnConfig &cfg, const parasail_profil
 // waits until the job's results are on the host
 static int scan_finish(ScanJob &job) {
     Ctx &c = g_ctx;
+    if (job.finished) return PSB_OK;
+    job.finished = true;
     cudaError_t e = job.done ? cudaEventSynchronize(job.done) : cudaStreamSynchronize(c.stream);
     if (e != cudaSuccess) { set_error(std::string("psb_scan: ") + cudaGetErrorString(e)); return PSB_ECUDA; }
     float ms = 0.f;
@@ -1744,42 +1824,141 @@ namespace psb {
 // into pieces whose upload (copy stream), device-side sort + packing and scan are pipelined, and the
 // per-subject results land in hosts[k][base ...] (pinned).  Used by psb_scan_host (one device, base 0) and by
 // the per-device workers of psb_scan_box (each with its own range of the caller's arrays).
+// measured rates of the host scan on this thread's device: what the piece plan is computed from
+struct HostScanRates {
+    double h2d_ms_per_byte = 0;     // residue uploads of >= 4 MB, exponentially averaged
+    uint64_t key = 0;               // the scan (function, query length, penalties) the next figure belongs to
+    double scan_ms_per_byte = 0;    // kernel time per database residue of that scan
+};
+static thread_local HostScanRates g_hs;
+// a finished piece's residue upload feeds the measured upload rate (both events have completed by now)
+static void note_upload(DbBuild &B) {
+    if (!B.res_begin || !B.uploaded || !B.db || B.db->residues < ((int64_t)4 << 20)) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, B.res_begin, B.uploaded) != cudaSuccess || ms <= 0.f) { cudaGetLastError(); return; }
+    const double now = (double)ms / (double)B.db->residues;
+    g_hs.h2d_ms_per_byte = g_hs.h2d_ms_per_byte > 0 ? 0.5 * g_hs.h2d_ms_per_byte + 0.5 * now : now;
+    cudaEventDestroy(B.res_begin); B.res_begin = nullptr;   // counted once
+}
+static uint64_t host_scan_key(const FnConfig &cfg, int lq, int open, int gap, int msize) {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : {(uint64_t)encode_fn(cfg), (uint64_t)lq, (uint64_t)open, (uint64_t)gap, (uint64_t)msize}) { h ^= x + 1; h *= 1099511628211ull; }
+    return h | 1;
+}
+// piece sizes (bytes) for a host scan of `total` residues: geometric with ratio r = 0.85 v/u (every piece lands
+// before its predecessor has been scanned), first piece and count chosen to minimise the exposed time
+//   (first piece's upload) + (pieces - 1) x boundary,   boundary = sort/pack chain + the scan kernel's ramp and tail
+// e.g. C2 on one GPU (362 MB, 52 GB/s, 27 ms of scan): 22 + 76 + 264 MB; a 1/8 shard (45 MB): 10 + 35 MB.
+std::vector<int64_t> plan_pieces(int64_t total, double u, double v) {
+    const double boundary_ms = 0.35;
+    const int64_t cap = (int64_t)1 << 30;   // bounds the device memory of a piece
+    // no piece below ~1 ms of scan: the sweep of a piece's longest subjects is serial, so smaller pieces take that
+    // long anyway (measured: 8 MB and 11 MB pieces of C2 both scan in 1.2 ms)
+    const int64_t min_piece = std::max<int64_t>((int64_t)4 << 20, (int64_t)(1.0 / v));
+    // ratio in steps of 1/4 and sizes in steps of 2 MB: the measured rates move a little from call to call, the
+    // plan (and with it every allocation size of the pipeline) should not
+    const double r = std::min(16.0, std::max(1.25, std::floor(0.85 * v / u * 4.0) / 4.0));
+    const double quantum = (double)((int64_t)2 << 20);
+    auto cut_up = [&](double s0) {
+        std::vector<int64_t> sizes;
+        double s = std::max(quantum, std::floor(s0 / quantum) * quantum);
+        for (int64_t left = total; left > 0; s *= r) {
+            int64_t sz = std::min<int64_t>((int64_t)(std::floor(std::min(s, (double)cap) / quantum) * quantum), left);
+            if (left - sz < min_piece) sz = left;
+            sizes.push_back(sz);
+            left -= sz;
+        }
+        return sizes;
+    };
+    std::vector<int64_t> sizes(1, total);
+    double best_cost = (double)total * u;
+    for (int m = 2; m <= 8; ++m) {
+        double s0 = (double)total * (r - 1.0) / (std::pow(r, m) - 1.0);
+        const bool floor_hit = s0 < (double)min_piece;
+        if (floor_hit) s0 = (double)min_piece;
+        if (s0 + (double)min_piece > (double)total) break;
+        std::vector<int64_t> cand = cut_up(s0);
+        const double cost = (double)cand[0] * u + (double)(cand.size() - 1) * boundary_ms;
+        if (cost < best_cost) { best_cost = cost; sizes.swap(cand); }
+        if (floor_hit) break;
+    }
+    return sizes;
+}
+
+struct ScanLeftovers {
+    std::vector<std::unique_ptr<DbBuild>> builds;
+    std::vector<std::unique_ptr<ScanJob>> jobs;
+    void clear() {
+        for (auto &b : builds) if (b && b->db) { psb_db_free(b->db); b->db = nullptr; }
+        jobs.clear(); builds.clear();
+    }
+};
 static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile, int open, int gap, const uint8_t *cat,
-                          const int64_t *off, int64_t n, int *const hosts[6], int64_t base, int64_t *n_retried) {
+                          const int64_t *off, int64_t n, int *const hosts[6], int64_t base, int64_t *n_retried,
+                          ScanLeftovers *leftovers = nullptr) {
     Ctx &c = g_ctx;
     const HostMatrix &hm = profile->matrix;
-    // pieces: the upload of piece k+1 (copy stream) runs under the scan of piece k, and nothing on the
-    // host waits for the GPU until the last piece is queued.  The first piece is small so the scan
-    // starts early; the others are big because every piece pays the scan kernel's ramp-up and tail
-    // once.  PSB_SCAN_HOST_FIRST_MB / PSB_SCAN_HOST_PIECE_MB override the sizes for experiments.
+    // pieces: the upload of piece k+1 (copy stream) runs under the scan of piece k, and nothing on the host waits
+    // for the GPU until the last piece is queued.  The sizes follow from two measured rates (HostScanRates): with
+    // u = upload time and v = scan time per residue, piece k+1 may be r = 0.85 v/u times piece k and still land
+    // before piece k has been scanned; the first piece and the number of pieces minimise
+    // (upload of the first piece) + (pieces - 1) x (cost of a piece boundary).  plan_pieces() below.
     const int64_t total = off[n] - off[0];
-    long long piece_mb = 96, first_mb = 24;
-    if (const char *ev = std::getenv("PSB_SCAN_HOST_PIECE_MB")) piece_mb = std::max(8ll, std::atoll(ev));
-    if (const char *ev = std::getenv("PSB_SCAN_HOST_FIRST_MB")) first_mb = std::max(1ll, std::atoll(ev));
-    const int64_t piece = piece_mb << 20;
-    // the first piece only has to be large enough to keep the GPU busy until the second has landed: a quarter
-    // of the range, between 4 MB and first_mb (a 1/8 shard of C2, 45 MB, is scanned as 11 MB + 34 MB: measured
-    // 4.64 ms against 5.05 ms in one piece and 4.83 ms with a sixth, tools/shard_e2e_probe.py)
-    long long first_div = 4;
-    if (const char *ev = std::getenv("PSB_SCAN_HOST_FIRST_DIV")) first_div = std::max(1ll, std::atoll(ev));
-    const int64_t first_cap = std::min<int64_t>(first_mb << 20, std::max<int64_t>((int64_t)4 << 20, total / first_div));
-    const int64_t first = total > first_cap + ((int64_t)4 << 20) ? first_cap : total;
-    const int nrest = first == total ? 0 : (int)std::max<int64_t>(1, std::min<int64_t>(30, (total - first + piece * 3 / 4) / piece));
-    const int npieces = (int)std::min<int64_t>(n, 1 + nrest);
-    std::vector<int64_t> cut(npieces + 1, n);
-    cut[0] = 0;
-    for (int k = 1; k < npieces; ++k) {
-        const int64_t target = off[0] + first + (total - first) * (k - 1) / std::max(1, npieces - 1);
-        cut[k] = std::lower_bound(off, off + n + 1, target) - off;
-        if (cut[k] <= cut[k - 1]) cut[k] = std::min<int64_t>(n, cut[k - 1] + 1);
+    const uint64_t rate_key = host_scan_key(cfg, (int)profile->query.size(), open, gap, hm.size);
+    const double u_rate = g_hs.h2d_ms_per_byte > 0 ? g_hs.h2d_ms_per_byte : 1e3 / 50e9;
+    const bool packed_path = cfg.mode == MODE_SW && !cfg.stats && cfg.width != 32 && cfg.width != 64;
+    const double v_rate = (g_hs.key == rate_key && g_hs.scan_ms_per_byte > 0) ? g_hs.scan_ms_per_byte
+                                                                                : (double)profile->query.size() * 1e3 / (packed_path ? 4.9e12 : 1.5e12);
+    std::vector<int64_t> sizes;
+    const char *e_piece = std::getenv("PSB_SCAN_HOST_PIECE_MB"), *e_first = std::getenv("PSB_SCAN_HOST_FIRST_MB"), *e_div = std::getenv("PSB_SCAN_HOST_FIRST_DIV");
+    if (e_piece || e_first || e_div) {
+        // experiments (tools/shard_e2e_probe.py): a first piece of total/div capped at first_mb, the rest in equal pieces
+        const long long piece_mb = e_piece ? std::max(8ll, std::atoll(e_piece)) : 96, first_mb = e_first ? std::max(1ll, std::atoll(e_first)) : 24;
+        const long long first_div = e_div ? std::max(1ll, std::atoll(e_div)) : 4;
+        const int64_t piece = piece_mb << 20;
+        const int64_t first_cap = std::min<int64_t>(first_mb << 20, std::max<int64_t>((int64_t)4 << 20, total / first_div));
+        const int64_t first = total > first_cap + ((int64_t)4 << 20) ? first_cap : total;
+        const int nrest = first == total ? 0 : (int)std::max<int64_t>(1, std::min<int64_t>(30, (total - first + piece * 3 / 4) / piece));
+        sizes.push_back(first);
+        for (int k = 0; k < nrest; ++k) sizes.push_back((total - first) * (k + 1) / nrest - (total - first) * k / nrest);
+    } else {
+        sizes = plan_pieces(total, u_rate, v_rate);
+        // hysteresis: the rates are measured and move a little from call to call; a plan that is still within 5 % of
+        // the best one is kept, so that a service repeating a scan keeps its allocation sizes (a new size can mean a
+        // host-blocking growth of the memory pool)
+        static thread_local struct { int64_t total = 0; uint64_t key = 0; std::vector<int64_t> sizes; } last;
+        auto exposed = [&](const std::vector<int64_t> &sz) {
+            double t = (double)sz[0] * u_rate + 0.35 * (double)(sz.size() - 1);
+            for (size_t k = 0; k + 1 < sz.size(); ++k) t += std::max(0.0, (double)sz[k + 1] * u_rate - (double)sz[k] * v_rate);
+            return t;
+        };
+        if (last.total == total && last.key == rate_key && !last.sizes.empty() && exposed(last.sizes) <= 1.05 * exposed(sizes) + 0.05) sizes = last.sizes;
+        last.total = total; last.key = rate_key; last.sizes = sizes;
     }
+    std::vector<int64_t> cut(1, 0);
+    {
+        int64_t acc = 0;
+        for (size_t k = 0; k + 1 < sizes.size() && cut.back() < n; ++k) {
+            acc += sizes[k];
+            int64_t at = std::lower_bound(off, off + n + 1, off[0] + acc) - off;
+            if (at <= cut.back()) at = cut.back() + 1;
+            if (at >= n) break;
+            cut.push_back(at);
+        }
+        cut.push_back(n);
+    }
+    const int npieces = (int)cut.size() - 1;
+    const double ms_at_entry = c.last_ms;
     int rc = PSB_OK;
     std::vector<std::unique_ptr<DbBuild>> builds(npieces);
     std::vector<std::unique_ptr<ScanJob>> jobs(npieces);
     for (int k = 0; k < npieces; ++k) { builds[k].reset(new DbBuild()); jobs[k].reset(new ScanJob()); }
-    auto begin = [&](int k) -> int {
+    bool eager = false;   // experiment knob: 1 = every upload queued right behind the previous one, no gating
+    if (const char *ev = std::getenv("PSB_SCAN_HOST_EAGER_UPLOAD")) eager = std::atoi(ev) != 0;
+    auto upload = [&](int k) -> int {
         if (cut[k + 1] <= cut[k]) return PSB_OK;
-        return db_begin(*builds[k], cat, off + cut[k], cut[k + 1] - cut[k], hm, true) ? PSB_OK : PSB_ECUDA;
+        cudaEvent_t gate = (!eager && k > 0 && builds[k - 1]) ? builds[k - 1]->packed : nullptr;
+        return db_upload(*builds[k], cat, off + cut[k], cut[k + 1] - cut[k], hm, true, 0, gate) ? PSB_OK : PSB_ECUDA;
     };
     // a finished piece gives its device memory back (staging blocks, packed shard, result arrays), so
     // at most kDepth pieces are resident however large the host database is
@@ -1787,7 +1966,8 @@ static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile
     auto retire = [&](int k) -> int {
         if (k < 0 || !jobs[k]) return PSB_OK;
         int r = PSB_OK;
-        if (jobs[k]->ev0) { r = scan_finish(*jobs[k]); *n_retried += jobs[k]->retried; }
+        if (jobs[k]->ev0 && !jobs[k]->finished) { r = scan_finish(*jobs[k]); *n_retried += jobs[k]->retried; }
+        if (builds[k]) note_upload(*builds[k]);
         if (builds[k] && builds[k]->db) { psb_db_free(builds[k]->db); builds[k]->db = nullptr; }
         jobs[k].reset(); builds[k].reset();
         return r;
@@ -1795,23 +1975,92 @@ static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile
     const bool dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
     const auto t_in = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count(); };
-    rc = begin(0);
+    if (dbg) {
+        std::string line;
+        for (int k = 0; k < npieces; ++k) line += " " + std::to_string((off[cut[k + 1]] - off[cut[k]]) >> 20);
+        std::fprintf(stderr, "[psb] scan_host(dev %d): pieces (MB):%s; upload %.1f GB/s, scan %.1f GB/s of residues\n", c.device, line.c_str(),
+                     1e-6 / u_rate, 1e-6 / v_rate);
+    }
+    // order of the host's work: the copy engine comes first.  Upload k+1 is queued before any host time goes into
+    // piece k (its offsets pass, the sort/pack launches, the scan launches), so the link never waits for the host.
+    // PSB_DEBUG_TIMING: a device-side timeline (upload landed / packing begins / scan begins / scan ends / results
+    // on the host), relative to an event recorded on the idle compute stream at entry
+    std::vector<cudaEvent_t> tl;
+    if (dbg) g_dbg_marks = &tl;
+    auto mark = [&](cudaStream_t st) { dbg_mark_stream(st); };
+    mark(c.stream);
+    rc = upload(0);
+    mark(c.copy);
+    // the query side now, while the compute stream is idle: a profile's first use on a device uploads it and waits
+    // for that upload, which would otherwise happen inside scan_enqueue(0) behind the first piece's whole chain
+    if (rc == PSB_OK) {
+        DevProfile *dp0 = nullptr;
+        rc = get_dev_profile(profile, &dp0);
+        std::vector<Sw16Profile> sp0;
+        if (rc == PSB_OK && packed_path) sw16_prepare(profile, dp0, open, gap, &sp0);
+    }
     if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): %d pieces, first upload queued at %.3f ms\n", c.device, npieces, since());
+    auto next_upload = [&](int k) {
+        if (k + 1 >= npieces || rc != PSB_OK) return;
+        if (k + 1 >= kDepth) rc = retire(k + 1 - kDepth);
+        if (rc == PSB_OK) rc = upload(k + 1);
+        if (rc == PSB_OK) mark(c.copy);
+    };
     for (int k = 0; k < npieces && rc == PSB_OK; ++k) {
-        if (!builds[k]->db) continue;
-        rc = db_finish(*builds[k]);
+        if (eager) next_upload(k);
+        if (rc != PSB_OK) break;
+        if (!builds[k]->db) { if (!eager) next_upload(k); continue; }
+        const double h0 = dbg ? since() : 0.0;
+        rc = db_host_pass(*builds[k], off + cut[k]);
+        const double h1 = dbg ? since() : 0.0;
+        if (dbg) { cudaStreamWaitEvent(c.stream, builds[k]->offs_up, 0); mark(c.stream); }
+        if (rc == PSB_OK) rc = db_finish(*builds[k]);
+        if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): piece %d host: offsets pass + allocations %.3f ms, chain launches %.3f ms\n", c.device, k, h1 - h0, since() - h1);
+        mark(c.stream);
+        // the next piece's upload is queued as soon as its gate (this piece's chain) exists, before host time
+        // goes into this piece's scan launches
+        if (!eager) next_upload(k);
         if (rc == PSB_OK) rc = scan_enqueue(*jobs[k], cfg, profile, open, gap, builds[k]->db, hosts, base + cut[k]);
+        mark(c.stream);
         if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): piece %d queued at %.3f ms\n", c.device, k, since());
-        // while this piece is being scanned: host pass over the next piece's offsets and its upload
-        if (rc == PSB_OK && k + 1 < npieces) {
-            if (k + 1 >= kDepth) rc = retire(k + 1 - kDepth);
-            if (rc == PSB_OK) rc = begin(k + 1);
-        }
+    }
+    // everything is queued: the host retires the earlier pieces while the last ones are still being scanned
+    for (int k = 0; k + 1 < npieces; ++k) {
+        const int r = retire(k);
+        if (rc == PSB_OK) rc = r;
     }
     cudaStreamSynchronize(c.copy);
     if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): uploads done at %.3f ms\n", c.device, since());
+    if (rc == PSB_OK && jobs[npieces - 1] && jobs[npieces - 1]->ev0) {
+        rc = scan_finish(*jobs[npieces - 1]);
+        *n_retried += jobs[npieces - 1]->retried;
+    }
     cudaStreamSynchronize(c.stream);
     if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): all done at %.3f ms\n", c.device, since());
+    if (dbg && !tl.empty()) {
+        // order of the marks: entry | upload 0 | per piece k: [upload k+1] upload-k-landed (lengths< >lengths sort> <pack pack>) pack-end results-on-host
+        std::string line;
+        for (size_t i = 1; i < tl.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tl[0], tl[i]);
+            char buf[32]; std::snprintf(buf, sizeof buf, " %.3f", ms); line += buf;
+        }
+        std::fprintf(stderr, "[psb] scan_host(dev %d): device timeline (ms after entry):%s\n", c.device, line.c_str());
+        for (cudaEvent_t e : tl) cudaEventDestroy(e);
+    }
+    g_dbg_marks = nullptr;
+    // the results are on the host.  What is left is giving the last piece's device memory back: a caller with
+    // somewhere better to do that (psb_scan_box's workers, after they have reported completion) takes it over
+    if (rc == PSB_OK && total >= ((int64_t)8 << 20) && c.last_ms > ms_at_entry) {
+        const double now = (c.last_ms - ms_at_entry) / (double)total;
+        g_hs.scan_ms_per_byte = g_hs.key == rate_key && g_hs.scan_ms_per_byte > 0 ? 0.5 * g_hs.scan_ms_per_byte + 0.5 * now : now;
+        g_hs.key = rate_key;
+    }
+    if (leftovers && rc == PSB_OK) {
+        if (builds[npieces - 1]) note_upload(*builds[npieces - 1]);
+        leftovers->builds.push_back(std::move(builds[npieces - 1]));
+        leftovers->jobs.push_back(std::move(jobs[npieces - 1]));
+    }
     for (int k = 0; k < npieces; ++k) {
         const int r = retire(k);
         if (rc == PSB_OK) rc = r;
@@ -1836,6 +2085,7 @@ struct BoxWorker {
     std::condition_variable cv;
     std::function<void()> job;
     bool has_job = false, quit = false;
+    ScanLeftovers left;   // device memory of the last piece of the call just reported: given back after the report
     void loop() {
         psb_set_device(device);
         std::unique_lock<std::mutex> lk(mu);
@@ -1848,6 +2098,9 @@ struct BoxWorker {
             lk.lock();
             has_job = false;
             cv.notify_all();
+            lk.unlock();
+            left.clear();   // off the caller's critical path (about 0.1 ms of frees and event destruction)
+            lk.lock();
         }
     }
     void submit(std::function<void()> j) {
@@ -1938,11 +2191,12 @@ int psb_scan_box(const char *fn_name, const parasail_profile_t *profile, int ope
     std::vector<std::string> errs(n_gpus);
     for (int d = 0; d < n_gpus; ++d) {
         if (cut[d + 1] <= cut[d]) continue;
-        box_worker(d)->submit([&, d] {
+        BoxWorker *w = box_worker(d);
+        w->submit([&, d, w] {
             int rc = ensure_ctx();
             if (rc == PSB_OK) {
                 g_ctx.last_ms = 0.0; g_ctx.launches = 0;
-                rc = scan_host_into(cfg, profile, open, gap, cat, off + cut[d], cut[d + 1] - cut[d], hosts, cut[d], &retried[d]);
+                rc = scan_host_into(cfg, profile, open, gap, cat, off + cut[d], cut[d + 1] - cut[d], hosts, cut[d], &retried[d], &w->left);
                 ms[d] = g_ctx.last_ms; launches[d] = g_ctx.launches;
             }
             rcs[d] = rc;
@@ -1978,6 +2232,13 @@ int psb_batch_topk(const psb_batch_t *batch, int k, int64_t *idx_out, int *score
     std::partial_sort(idx.begin(), idx.begin() + kk, idx.end(), better);
     for (int64_t i = 0; i < kk; ++i) { idx_out[i] = idx[i]; if (score_out) score_out[i] = batch->score[idx[i]]; }
     return (int)kk;
+}
+
+int psb_host_scan_plan(int64_t total, double upload_ms_per_byte, double scan_ms_per_byte, int64_t *sizes_out, int cap) {
+    if (total <= 0 || upload_ms_per_byte <= 0 || scan_ms_per_byte <= 0 || !sizes_out || cap <= 0) { set_error("psb_host_scan_plan: bad argument"); return PSB_EINVAL; }
+    const std::vector<int64_t> sizes = plan_pieces(total, upload_ms_per_byte, scan_ms_per_byte);
+    for (size_t k = 0; k < sizes.size() && (int)k < cap; ++k) sizes_out[k] = sizes[k];
+    return (int)sizes.size();
 }
 
 int psb_shard_plan(const int64_t *off, int64_t n, int n_shards, int *shard_of) {

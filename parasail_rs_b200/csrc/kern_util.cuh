@@ -46,26 +46,32 @@ struct PackParams {
     int bits;
     unsigned lut[64];
 };
-// one warp per subject, lanes stride over its words
+// one warp per subject, lanes stride over its words.  256 bytes of dynamic shared memory hold the byte -> code
+// table (indexing the kernel parameter itself with a per-lane byte would serialise on the constant cache:
+// 0.68 ms for 253 MB before, profiles/README.md r2r).
 PSB_KERNEL void pack_db_kernel(PackParams p) {
+    PSB_SHARED_DECL(smem);
+    uint8_t *slut = smem;
+    for (int b = thread_in_block(); b < 256; b += threads_per_block()) slut[b] = (uint8_t)((p.lut[b >> 2] >> (8 * (b & 3))) & 0xff);
+    sync_block();
     const int rpw = residues_per_word(p.bits);
     const long long warp = ((long long)block_id() * threads_per_block() + thread_in_block()) >> 5;
     const long long nwarps = ((long long)grid_blocks() * threads_per_block()) >> 5;
     const int lane = lane_id();
     for (long long s = warp; s < p.n; s += nwarps) {
-        const long long src = p.raw_off[p.perm[s]] - p.raw_base;
-        const int len = (int)(p.raw_off[p.perm[s] + 1] - p.raw_off[p.perm[s]]);
+        const long long o0 = p.raw_off[p.perm[s]];
+        const uint8_t *src = p.raw + (o0 - p.raw_base);
+        const int len = (int)(p.raw_off[p.perm[s] + 1] - o0);
         const long long w0 = p.word_off[s];
         const int nw = (int)(p.word_off[s + 1] - w0);
         for (int w = lane; w < nw; w += 32) {
             unsigned word = 0;
-            for (int t = 0; t < rpw; ++t) {
-                const int idx = w * rpw + t;
-                if (idx < len) {
-                    const unsigned b = p.raw[src + idx];
-                    const unsigned code = (p.lut[b >> 2] >> (8 * (b & 3))) & 0xff;
-                    word |= code << (p.bits * t);
-                }
+            const int i0 = w * rpw;
+            if (i0 + rpw <= len) {
+#pragma unroll 2
+                for (int t = 0; t < rpw; ++t) word |= (unsigned)slut[src[i0 + t]] << (p.bits * t);
+            } else {
+                for (int t = 0; i0 + t < len; ++t) word |= (unsigned)slut[src[i0 + t]] << (p.bits * t);
             }
             p.words[w0 + w] = word;
         }
