@@ -18,11 +18,13 @@
 #include <cub/device/device_scan.cuh>
 #include <map>
 #include <mutex>
+#include <limits>
 #include <numeric>
 #include <condition_variable>
 #include <functional>
 #include <string>
 #include <thread>
+#include <future>
 #include <vector>
 
 #include "kern_gotoh32.cuh"
@@ -49,6 +51,10 @@ struct Ctx {
     int sms = 0;
     double last_ms = 0.0;
     int launches = 0;
+    // the big per-pass buffers of psb_align_pairs (decision bytes, CIGAR scratch): kept by the thread from pass to
+    // pass of one batch and only grown, so that a lane working through sixteen passes does not put sixteen
+    // multi-gigabyte allocations through the stream-ordered pool (KeptMem below)
+    struct Kept { void *p = nullptr; size_t cap = 0; } kept[3];
 };
 static thread_local Ctx g_ctx;
 
@@ -139,6 +145,40 @@ struct DevMem {
     template <typename T> T *as() const { return (T *)p; }
 };
 #define PSB_TRY(expr) do { int rc_ = (expr); if (rc_ != PSB_OK) return rc_; } while (0)
+
+// DevMem's interface over one of the thread's kept slots: alloc() reuses the slot's block when it is large enough
+// and replaces it otherwise; nothing is freed when the object goes out of scope (release_kept does that, at the end
+// of the batch)
+struct KeptMem {
+    int slot;
+    void *p = nullptr;
+    explicit KeptMem(int s) : slot(s) {}
+    int alloc(size_t n, cudaStream_t stream) {
+        Ctx::Kept &k = g_ctx.kept[slot];
+        if (k.cap < n || !k.p) {
+            if (k.p) cudaFreeAsync(k.p, stream);
+            k.p = nullptr; k.cap = 0;
+            const size_t want = n + n / 8 + 256;
+            cudaError_t e = cudaMallocAsync(&k.p, want, stream);
+            if (e != cudaSuccess) {
+                k.p = nullptr;
+                set_error(std::string("cudaMallocAsync(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+                return e == cudaErrorMemoryAllocation ? PSB_ENOMEM : PSB_ECUDA;
+            }
+            k.cap = want;
+        }
+        p = k.p;
+        return PSB_OK;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+static void release_kept() {
+    Ctx &c = g_ctx;
+    for (Ctx::Kept &k : c.kept) {
+        if (k.p) cudaFreeAsync(k.p, c.stream);
+        k.p = nullptr; k.cap = 0;
+    }
+}
 
 // pinned host blocks are slow to create; recycle them process-wide by size class
 static std::mutex g_pin_mu;
@@ -375,9 +415,41 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
 struct PairChunk {
     int64_t lo, hi;  // pair range of the caller's batch handled by this pass
 };
+struct PassOut;
+// host threads that work through the passes of a large batch side by side.  Measured on 10^6 pairs (tools/
+// pairs_host_probe.py; one lane / two / three): sw_trace 250 x 250: 106 / 50 / 47 ms, nw 250 x 250: 45 / 23.7 / 21.8 ms,
+// sg_stats 150 x 500: 68 / 34 / 36 ms -- but with three or four lanes the multi-gigabyte decision buffers of the
+// trace and stats passes no longer fit what the stream-ordered pool holds mapped and single calls stall for
+// 100-500 ms while it grows; two lanes never did
+static constexpr int kPairLanes = 2;
+static int run_pairs_lanes(const PairsRequest &req, const std::vector<PairChunk> &chunks, psb_batch_t *b, std::vector<PassOut> &pouts, int lanes);
 
-static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_batch_t *b, int64_t *csr_used) {
+// what a pass hands back besides the slices of the batch's arrays it fills: the passes of a batch may run on two
+// host threads at once (run_pairs_lanes), so nothing that depends on the other passes is written by a pass itself
+struct PassOut {
+    double cells = 0;
+    DevMem d_csr;                     // device: this pass's CIGAR words (forward order, pairs lo..hi-1 back to back);
+                                      // run_pairs copies every pass's words straight into the batch's one array
+    std::vector<long long> csr_off;   // n+1 word offsets into d_csr
+    float ms = 0.f;                   // timed region of the pass
+    int launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // (multi-lane only) begin / end of the pass on the device
+};
+
+static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_batch_t *b, PassOut *po) {
     Ctx &c = g_ctx;
+    const int launches_at_entry = c.launches;
+    // PSB_DEBUG_TIMING: where the HOST time of a pass goes
+    const bool host_dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
+    auto h_last = std::chrono::steady_clock::now();
+    std::string h_line;
+    auto hphase = [&](const char *what) {
+        if (!host_dbg) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[64];
+        std::snprintf(buf, sizeof buf, " %s %.3f", what, std::chrono::duration<double, std::milli>(now - h_last).count());
+        h_line += buf; h_last = now;
+    };
     const FnConfig &cfg = req.cfg;
     const HostMatrix &m = *req.matrix;
     const int64_t n = hi - lo;
@@ -432,7 +504,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             if (c16 >= 0 && pairs16_fits(p16_class(c16).G * p16_class(c16).K, lq, lr, m.max, m.min, req.open, req.gap, cfg.mode == MODE_SW)) {
                 p16_ids[c16].push_back((int)i);
                 ++n_p16;
-                b->cells += (double)lq * lr;
+                po->cells += (double)lq * lr;
                 continue;
             }
         }
@@ -446,10 +518,11 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         const long long cells = (long long)lq * lr;
         if (first_cls < 0) { first_cls = cl; first_cells = cells; }
         else if (cl != first_cls || cells != first_cells) uniform = false;
-        b->cells += (double)cells;
+        po->cells += (double)cells;
     }
     // the coarse family carries only the wide statistics word: the strip-boundary scratch is sized for it
     const bool wide_stats = !(max_min < 1024 && max_sum < 4096) || !fine;
+    hphase("classify");
 
     // upload residues + offsets (relative to this range) and map them to matrix columns
     DevMem d_q, d_r, d_qoff, d_roff, d_matrix;
@@ -473,6 +546,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     PSB_CUDA(cudaMemcpyAsync(d_qoff.p, qoff_rel.data(), qoff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
     PSB_CUDA(cudaMemcpyAsync(d_roff.p, roff_rel.data(), roff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
     PSB_CUDA(cudaMemcpyAsync(d_matrix.p, m.table.data(), m.table.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    hphase("uploads");
     // outputs
     DevMem d_out[6], d_counter, d_bnd;
     const int nout = cfg.stats || want_table ? 6 : 3;
@@ -485,7 +559,8 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     if (bnd_stride > 0) PSB_TRY(d_bnd.alloc((size_t)(bnd_stride * max_grid_warps(n)) * sizeof(int), c.stream));
 
     // trace / table blocks: [strip][step][lane][K] per pair
-    DevMem d_trace, d_traceoff, d_tab[4], d_rev, d_revoff, d_nops, d_beg[2];
+    DevMem d_traceoff, d_tab[4], d_revoff, d_nops, d_beg[2];
+    KeptMem d_trace(0), d_rev(1);
     std::vector<long long> trace_off, rev_off;
     long long trace_total = 0, rev_total = 0;
     if (want_trace || want_table) {
@@ -515,6 +590,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         if (want_table) for (int k = 0; k < 4; ++k) PSB_TRY(d_tab[k].alloc((size_t)trace_total * sizeof(int), c.stream));
     }
 
+    hphase("trace-offsets");
     Gotoh32Params p;
     std::memset(&p, 0, sizeof(p));
     p.q = d_q.as<uint8_t>(); p.q_off = d_qoff.as<long long>();
@@ -549,7 +625,8 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
 
     // ---- packed 16-bit classes: two pairs per register, sorted by reference length so that the pairs of
     // a word (and the words of a warp) are of similar size -----------------------------------------------
-    DevMem d_items, d_toff16, d_slot16, d_ids16, d_mat8, d_trace16, d_cnt16;
+    DevMem d_items, d_toff16, d_slot16, d_ids16, d_mat8, d_cnt16;
+    KeptMem d_trace16(2);
     std::vector<int> h_items, h_slot16, h_ids16;   // kept alive until the stream has consumed them
     std::vector<long long> h_toff16;
     std::vector<int8_t> h_mat8(33 * 32);
@@ -604,6 +681,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             PSB_CUDA(cudaMemcpyAsync(d_ids16.p, h_ids16.data(), h_ids16.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
         }
     }
+    hphase("items");
     // every host->device copy of this pass is queued: the timed region (psb_last_kernel_ms) starts here
     PSB_CUDA(cudaEventRecord(c.ev0, c.stream));
     {
@@ -701,7 +779,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     }
 
     // device-side trace walk -> CIGAR CSR
-    DevMem d_csroff, d_csr, d_scan_tmp;
+    DevMem d_csroff, d_scan_tmp;
     if (want_trace) {
         for (int cl = 0; cl < kNumClass; ++cl) {
             if (cls[cl].empty()) continue;
@@ -728,6 +806,7 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         c.launches++;
     }
     PSB_CUDA(cudaEventRecord(c.ev1, c.stream));
+    hphase("launches");
 
     // results back to the batch's pinned arrays
     int *outs[6] = {b->score, b->end_query, b->end_ref, b->matches, b->similar, b->length};
@@ -738,24 +817,17 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         std::vector<long long> csr_off(n + 1);
         PSB_CUDA(cudaMemcpyAsync(csr_off.data(), d_csroff.p, ((size_t)n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
         PSB_CUDA(cudaStreamSynchronize(c.stream));
+        hphase("wait-kernels");
         const long long total = csr_off[n];
-        PSB_TRY(d_csr.alloc((size_t)total * sizeof(unsigned), c.stream));
+        PSB_TRY(po->d_csr.alloc((size_t)total * sizeof(unsigned), c.stream));
         CompactParams cp;
         cp.rev_ops = d_rev.as<unsigned>(); cp.rev_off = d_revoff.as<long long>();
-        cp.csr_off = d_csroff.as<long long>(); cp.csr_ops = d_csr.as<unsigned>(); cp.n = (int)n;
+        cp.csr_off = d_csroff.as<long long>(); cp.csr_ops = po->d_csr.as<unsigned>(); cp.n = (int)n;
         compact_cigar_kernel<<<c.sms * 8, 256, 0, c.stream>>>(cp);
         c.launches++;
-        BatchImpl *impl = (BatchImpl *)b->impl;
-        // grow the CSR op array (pinned) to hold this range
-        uint32_t *ops = (uint32_t *)impl->take((size_t)(*csr_used + total + 1) * sizeof(uint32_t));
-        if (!ops) { set_error("pinned allocation failed"); return PSB_ENOMEM; }
-        if (*csr_used) std::memcpy(ops, b->cigar_ops, (size_t)*csr_used * sizeof(uint32_t));
-        b->cigar_ops = ops;
-        PSB_CUDA(cudaMemcpyAsync(ops + *csr_used, d_csr.p, (size_t)total * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream));
         PSB_CUDA(cudaMemcpyAsync(b->beg_query + lo, d_beg[0].p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         PSB_CUDA(cudaMemcpyAsync(b->beg_ref + lo, d_beg[1].p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-        for (int64_t i = 0; i <= n; ++i) b->cigar_off[lo + i] = *csr_used + csr_off[i];
-        *csr_used += total;
+        po->csr_off.swap(csr_off);
     }
 
     // single-pair extras: row-major trace bytes, tables, last row / column
@@ -799,9 +871,13 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             }
         }
     }
+    hphase("results-queued");
     PSB_CUDA(cudaStreamSynchronize(c.stream));
+    hphase("wait");
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) c.last_ms += ms;
+    if (cudaEventElapsedTime(&ms, c.ev0, c.ev1) == cudaSuccess) { c.last_ms += ms; po->ms = ms; }
+    if (host_dbg) std::fprintf(stderr, "[psb] pass %lld..%lld host ms:%s\n", (long long)lo, (long long)hi, h_line.c_str());
+    po->launches = c.launches - launches_at_entry;
     for (auto &d : dbg_ev) {
         float t = 0.f;
         if (d.second.second && cudaEventElapsedTime(&t, d.second.first, d.second.second) == cudaSuccess)
@@ -880,11 +956,24 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
     const HostMatrix &hm0 = *req.matrix;
     const bool p16_scheme = !std::getenv("PSB_NO_P16") && pairs16_scheme_ok(hm0.size, hm0.min, hm0.max, req.open, req.gap, hm0.type == PARASAIL_MATRIX_TYPE_PSSM) &&
                             pairs16_trace_ok(hm0.min, hm0.max, req.open) && req.cfg.width != 32 && req.cfg.width != 64 && !req.extra;
-    int64_t csr_used = 0;
-    int64_t lo = 0;
-    while (lo < req.n) {
-        int64_t hi = req.n;
-        if (req.cfg.trace || (req.cfg.stats && p16_scheme)) {
+    // ---- passes.  A large batch is cut into passes twice over: by device memory (above) and by residues, so that
+    // two host threads ("lanes", each with its own streams) can work on alternate passes: the uploads and the host
+    // preparation of one pass run under the kernels of the other.  Small batches stay one pass on the calling thread.
+    auto res_upto = [&](int64_t i) { return (req.shared_query ? 0 : req.q_off[i] - req.q_off[0]) + (req.r_off[i] - req.r_off[0]); };
+    const int64_t total_res = res_upto(req.n);
+    int lanes = kPairLanes;
+    if (const char *ev = std::getenv("PSB_PAIRS_LANES")) lanes = std::max(1, std::min(kPairLanes, std::atoi(ev)));
+    int64_t pass_res = std::numeric_limits<int64_t>::max();
+    if (lanes > 1 && !req.extra && req.n >= 4096 && total_res >= ((int64_t)64 << 20))
+        pass_res = std::min<int64_t>((int64_t)256 << 20, std::max<int64_t>((int64_t)16 << 20, total_res / (4 * lanes)));
+    if (const char *ev = std::getenv("PSB_PAIRS_PASS_MB")) pass_res = std::max<int64_t>(1, std::atoll(ev)) << 20;
+    const bool mem_cut = req.cfg.trace || (req.cfg.stats && p16_scheme);
+    if (mem_cut && pass_res != std::numeric_limits<int64_t>::max()) budget /= lanes;   // one pass per lane is in flight
+    std::vector<PairChunk> chunks;
+    bool has_long = false;   // pairs for the whole-GPU wavefront kernel: those passes are not run side by side
+    for (int64_t lo = 0; lo < req.n;) {
+        int64_t hi;
+        if (mem_cut) {
             int64_t bytes = 0;
             hi = lo;
             while (hi < req.n) {
@@ -896,14 +985,67 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
                     const int K = 16;  // upper bound on rows per lane of any class
                     need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);
                 } else need = 0;
-                if (hi > lo && bytes + need > budget) break;
+                if (hi > lo && (bytes + need > budget || res_upto(hi + 1) - res_upto(lo) > pass_res)) break;
                 bytes += need; ++hi;
             }
+        } else if (pass_res == std::numeric_limits<int64_t>::max()) {
+            hi = req.n;
+        } else {
+            // the last pair index whose residues still fit the pass (res_upto is monotone)
+            int64_t a = lo + 1, z = req.n;
+            while (a < z) { const int64_t mid = (a + z + 1) / 2; if (res_upto(mid) - res_upto(lo) <= pass_res) a = mid; else z = mid - 1; }
+            hi = a;
+            if (req.n - hi < (hi - lo) / 4) hi = req.n;   // no runt at the end
         }
-        const int rc = run_pairs_range(req, lo, hi, b, &csr_used);
-        if (rc != PSB_OK) { cudaStreamSynchronize(c.stream); free_batch(b); return rc; }
+        chunks.push_back({lo, hi});
         lo = hi;
     }
+    if (chunks.size() > 1 && hm0.type != PARASAIL_MATRIX_TYPE_PSSM && !req.cfg.stats && !req.cfg.trace) {
+        if (req.shared_query) has_long = req.q_off[1] - req.q_off[0] >= kWaveMinLq;
+        else for (int64_t i = 0; i < req.n && !has_long; ++i) has_long = req.q_off[i + 1] - req.q_off[i] >= kWaveMinLq;
+    }
+    std::vector<PassOut> pouts(chunks.size());
+    int rc = PSB_OK;
+    const bool host_dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
+    const auto t_run = std::chrono::steady_clock::now();
+    if (chunks.size() == 1 || lanes == 1 || has_long) {
+        for (size_t k = 0; k < chunks.size() && rc == PSB_OK; ++k) rc = run_pairs_range(req, chunks[k].lo, chunks[k].hi, b, &pouts[k]);
+        if (rc != PSB_OK) cudaStreamSynchronize(c.stream);
+    } else {
+        rc = run_pairs_lanes(req, chunks, b, pouts, lanes);
+    }
+    const auto t_join = std::chrono::steady_clock::now();
+    if (rc == PSB_OK && req.cfg.trace) {
+        // the passes' CIGAR words are still on the device: one pinned array for the batch, one copy per pass into it
+        long long total = 0;
+        for (const PassOut &po : pouts) total += po.csr_off.empty() ? 0 : po.csr_off.back();
+        BatchImpl *impl = (BatchImpl *)b->impl;
+        b->cigar_ops = (uint32_t *)impl->take((size_t)(total + 1) * sizeof(uint32_t));
+        if (!b->cigar_ops) { set_error("pinned allocation failed"); rc = PSB_ENOMEM; }
+        long long used = 0;
+        for (size_t k = 0; k < pouts.size() && rc == PSB_OK; ++k) {
+            const PassOut &po = pouts[k];
+            const int64_t n = chunks[k].hi - chunks[k].lo;
+            if ((int64_t)po.csr_off.size() != n + 1) { set_error("psb: a pass returned no CIGAR offsets"); rc = PSB_ECUDA; break; }
+            if (po.csr_off[n] > 0 &&
+                cudaMemcpyAsync(b->cigar_ops + used, po.d_csr.p, (size_t)po.csr_off[n] * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) {
+                set_error(std::string("psb: CIGAR copy: ") + cudaGetErrorString(cudaGetLastError())); rc = PSB_ECUDA; break;
+            }
+            for (int64_t i = 0; i <= n; ++i) b->cigar_off[chunks[k].lo + i] = used + po.csr_off[i];
+            used += po.csr_off[n];
+        }
+        if (cudaStreamSynchronize(c.stream) != cudaSuccess && rc == PSB_OK) { set_error("psb: CIGAR copy failed"); rc = PSB_ECUDA; }
+    }
+    for (PassOut &po : pouts) {
+        b->cells += po.cells;
+        po.d_csr.release();
+    }
+    release_kept();
+    if (host_dbg)
+        std::fprintf(stderr, "[psb] run_pairs: %zu passes, passes %.3f ms, join %.3f ms\n", chunks.size(),
+                     std::chrono::duration<double, std::milli>(t_join - t_run).count(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_join).count());
+    if (rc != PSB_OK) { free_batch(b); return rc; }
     *out = b;
     return PSB_OK;
 }
@@ -2114,6 +2256,60 @@ struct BoxWorker {
         cv.wait(lk, [&] { return !has_job; });
     }
 };
+// ---- lanes for the passes of a large psb_align_pairs batch ------------------------------------------------
+// Each lane is a resident host thread bound to the caller's device, with its own context (streams, events): the
+// passes are handed out in order, so that while one lane's pass is in its kernels the other lane uploads and
+// prepares the next one.  The passes write disjoint slices of the batch; what is not a slice comes back in PassOut.
+static std::mutex g_lane_mu;
+static std::map<std::pair<int, int>, BoxWorker *> g_lanes;   // (device, lane) -> worker; never destroyed
+static BoxWorker *pair_lane(int device, int lane) {
+    std::lock_guard<std::mutex> lk(g_lane_mu);
+    BoxWorker *&w = g_lanes[{device, lane}];
+    if (!w) {
+        w = new BoxWorker();
+        w->device = device;
+        BoxWorker *ww = w;
+        w->th = std::thread([ww] { ww->loop(); });
+        w->th.detach();
+    }
+    return w;
+}
+static int run_pairs_lanes(const PairsRequest &req, const std::vector<PairChunk> &chunks, psb_batch_t *b, std::vector<PassOut> &pouts, int lanes) {
+    Ctx &c = g_ctx;
+    const int kLanes = std::max(1, std::min(kPairLanes, lanes));
+    std::atomic<size_t> next{0};
+    std::atomic<int> first_rc{PSB_OK};
+    std::string errs[kPairLanes];
+    std::promise<void> done[kPairLanes];
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < kLanes; ++t) {
+        pair_lane(c.device, t)->submit([&, t] {
+            int rc = ensure_ctx();
+            while (rc == PSB_OK && first_rc.load() == PSB_OK) {
+                const size_t k = next.fetch_add(1);
+                if (k >= chunks.size()) break;
+                rc = run_pairs_range(req, chunks[k].lo, chunks[k].hi, b, &pouts[k]);
+            }
+            if (rc != PSB_OK) {
+                errs[t] = psb_last_error();
+                int expected = PSB_OK;
+                first_rc.compare_exchange_strong(expected, rc);
+                cudaStreamSynchronize(g_ctx.stream);
+            }
+            release_kept();
+            done[t].set_value();
+        });
+    }
+    for (int t = 0; t < kLanes; ++t) done[t].get_future().wait();
+    // the passes' timed regions overlap, so their sum says nothing: the figure reported for a pipelined batch is
+    // the wall time of the pipelined section (PSB_PAIRS_LANES=1 gives the serial per-pass kernel times instead)
+    c.last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (const PassOut &po : pouts) c.launches += po.launches;
+    const int rc = first_rc.load();
+    if (rc != PSB_OK) for (int t = 0; t < kLanes; ++t) if (!errs[t].empty()) { set_error(errs[t]); break; }
+    return rc;
+}
+
 static std::mutex g_box_mu;
 static std::vector<BoxWorker *> g_box;   // index = device; never destroyed (the threads live as long as the process)
 static BoxWorker *box_worker(int device) {

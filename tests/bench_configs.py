@@ -81,21 +81,43 @@ def main():
     sm_peak32 = 148 * 64 * 1.965 / 5
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
 
+    import torch
+    def pinned(a):
+        """a page-locked copy of a numpy array (what a caller who cares about upload speed hands the library)"""
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
     def run(aligner, qc, qo, rc, ro, reps=2):
-        aligner.align_batch((qc, qo), (rc, ro))  # warm-up (also grows the memory pool)
-        best, kms = 1e30, 0.0
+        # end to end: pinned host buffers in, pinned result arrays out, the library's own pass pipeline (two lanes)
+        keep = [pinned(x) for x in (qc, qo, rc, ro)]
+        pq, pqo, pr, pro = [t.numpy() for t in keep]
+        aligner.align_batch((pq, pqo), (pr, pro))  # warm-up (also grows the memory pool)
+        best = 1e30
         res = None
         for _ in range(reps):
             t0 = time.perf_counter()
-            res = aligner.align_batch((qc, qo), (rc, ro))
-            dt = time.perf_counter() - t0
-            if dt < best:
-                best, kms = dt, ps.kernel_ms()
+            res = aligner.align_batch((pq, pqo), (pr, pro))
+            best = min(best, time.perf_counter() - t0)
+        # the same call from pageable memory (plain numpy arrays), once
+        t0 = time.perf_counter()
+        aligner.align_batch((qc, qo), (rc, ro))
+        pageable = time.perf_counter() - t0
+        # kernel time: the passes one after the other on one stream, summed timed regions (uploads excluded)
+        os.environ["PSB_PAIRS_LANES"] = "1"
+        aligner.align_batch((pq, pqo), (pr, pro))
+        kms = 1e30
+        for _ in range(reps):
+            aligner.align_batch((pq, pqo), (pr, pro))
+            kms = min(kms, ps.kernel_ms())
+        launches = ps.launches()
+        del os.environ["PSB_PAIRS_LANES"]
         cells = res.cells
         gc = cells / (kms * 1e-3) / 1e9
         return res, {"function": aligner.fn_name, "pairs": len(ro) - 1, "cells": cells, "e2e_s": best, "e2e_gcups": cells / best / 1e9,
+                     "e2e_pageable_s": pageable, "e2e_pageable_gcups": cells / pageable / 1e9,
                      "kernel_ms": kms, "kernel_gcups": gc, "frac_of_s32_roofline": gc / sm_peak32, "frac_of_s16x2_roofline": gc / (2 * sm_peak32),
-                     "launches": ps.launches()}
+                     "launches": launches}
 
     def save():
         with open(args.out, "w") as f:

@@ -555,3 +555,33 @@ def test_pairs16_edge_shapes(ps, oracle):
                 exp = oracle_batch(oracle, qs, rs, odna, mode, *gaps, stats=(kind == "stats"), cigar=(kind == "trace"))
                 keys = KEYS6 if kind == "stats" else (KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops") if kind == "trace" else KEYS3)
                 assert_same(got, exp, keys, f"mode {mode} gaps {gaps} {kind}")
+
+
+@pytest.mark.parametrize("kind", ["score", "stats", "trace"])
+@pytest.mark.parametrize("mode", [0, 2])
+def test_pairs_passes_on_two_lanes_equal_single_pass(ps, oracle, blosum62, mode, kind, monkeypatch):
+    # a large batch is cut into passes that two host threads work through side by side (run_pairs_lanes); forced
+    # here with 1 MB passes on a modest batch: every array, CIGAR CSR included, must equal the single-pass result
+    # and the oracle's
+    qs, rs = mixed_pairs(141, 3000, (1, 420), (1, 500), True)
+    if kind != "score":   # (score-only batches holding a pair for the whole-GPU wavefront kernel run their passes serially)
+        qs += [psb_data.random_seq(142, 0, 2500), psb_data.random_seq(142, 1, 40)]     # a long pair next to a tiny one
+        rs += [psb_data.random_seq(142, 2, 2400), psb_data.random_seq(142, 3, 3000)]
+    bld = builder(ps, mode, ps.Matrix.from_name("blosum62"), 10, 1)
+    keys = KEYS3
+    if kind == "stats":
+        bld, keys = bld.use_stats(), KEYS6
+    if kind == "trace":
+        bld, keys = bld.use_trace(), KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops")
+    a = bld.build()
+    one = a.align_batch(qs, rs)
+    monkeypatch.setenv("PSB_PAIRS_PASS_MB", "1")
+    two = a.align_batch(qs, rs)
+    monkeypatch.setenv("PSB_PAIRS_LANES", "1")
+    serial = a.align_batch(qs, rs)
+    for other, tag in ((two, "two lanes"), (serial, "serial passes")):
+        for k in keys:
+            assert np.array_equal(getattr(one, k), getattr(other, k)), (tag, k)
+        assert other.cells == one.cells
+    exp = oracle_batch(oracle, qs, rs, blosum62, mode, 10, 1, stats=(kind == "stats"), cigar=(kind == "trace"))
+    assert_same(two, exp, keys, f"{kind} mode {mode}")
