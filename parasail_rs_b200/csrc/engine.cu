@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <map>
@@ -55,6 +56,10 @@ struct Ctx {
     // pass of one batch and only grown, so that a lane working through sixteen passes does not put sixteen
     // multi-gigabyte allocations through the stream-ordered pool (KeptMem below)
     struct Kept { void *p = nullptr; size_t cap = 0; } kept[3];
+    // two page-locked bounce buffers for uploads out of pageable caller memory (upload_h2d below)
+    void *bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_free[2] = {nullptr, nullptr};
+    int bounce_next = 0;
 };
 static thread_local Ctx g_ctx;
 
@@ -145,6 +150,45 @@ struct DevMem {
     template <typename T> T *as() const { return (T *)p; }
 };
 #define PSB_TRY(expr) do { int rc_ = (expr); if (rc_ != PSB_OK) return rc_; } while (0)
+
+// Host->device copy that does not depend on the caller's memory being page-locked.  cudaMemcpyAsync out of
+// pageable memory goes through the driver's own staging at a few GB/s with the calling thread blocked; large
+// copies out of such memory are staged here instead, 8 MB at a time through two page-locked bounce buffers of the
+// calling thread (memcpy of one chunk while the previous one is on the link).  Page-locked sources (and small
+// copies) go straight to cudaMemcpyAsync.
+static constexpr size_t kBounceBytes = (size_t)8 << 20;
+static cudaError_t upload_h2d(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    if (bytes < ((size_t)1 << 20)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+    if (at.type != cudaMemoryTypeUnregistered) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    static const bool no_bounce = std::getenv("PSB_NO_BOUNCE") != nullptr;   // A/B knob: leave pageable memory to the driver
+    if (no_bounce) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    Ctx &c = g_ctx;
+    for (int k = 0; k < 2; ++k)
+        if (!c.bounce[k]) {
+            if (cudaMallocHost(&c.bounce[k], kBounceBytes) != cudaSuccess || cudaEventCreateWithFlags(&c.bounce_free[k], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                if (c.bounce[k]) { cudaFreeHost(c.bounce[k]); c.bounce[k] = nullptr; }
+                return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);   // no bounce buffers: the driver's path
+            }
+            cudaEventRecord(c.bounce_free[k], stream);
+        }
+    for (size_t done = 0; done < bytes;) {
+        const int k = c.bounce_next;
+        c.bounce_next ^= 1;
+        const size_t len = std::min(kBounceBytes, bytes - done);
+        cudaError_t e = cudaEventSynchronize(c.bounce_free[k]);   // the copy that last used this buffer has left it
+        if (e != cudaSuccess) return e;
+        std::memcpy(c.bounce[k], (const uint8_t *)src + done, len);
+        e = cudaMemcpyAsync((uint8_t *)dst + done, c.bounce[k], len, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(c.bounce_free[k], stream);
+        if (e != cudaSuccess) return e;
+        done += len;
+    }
+    return cudaSuccess;
+}
 
 // DevMem's interface over one of the thread's kept slots: alloc() reuses the slot's block when it is large enough
 // and replaces it otherwise; nothing is freed when the object goes out of scope (release_kept does that, at the end
@@ -422,7 +466,8 @@ struct PassOut;
 // trace and stats passes no longer fit what the stream-ordered pool holds mapped and single calls stall for
 // 100-500 ms while it grows; two lanes never did
 static constexpr int kPairLanes = 2;
-static int run_pairs_lanes(const PairsRequest &req, const std::vector<PairChunk> &chunks, psb_batch_t *b, std::vector<PassOut> &pouts, int lanes);
+struct PassCutter;
+static int run_pairs_lanes(const PairsRequest &req, PassCutter &cutter, const PairChunk &first, PassOut *first_out, psb_batch_t *b, int lanes);
 
 // what a pass hands back besides the slices of the batch's arrays it fills: the passes of a batch may run on two
 // host threads at once (run_pairs_lanes), so nothing that depends on the other passes is written by a pass itself
@@ -434,6 +479,55 @@ struct PassOut {
     float ms = 0.f;                   // timed region of the pass
     int launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // (multi-lane only) begin / end of the pass on the device
+};
+
+// hands out the passes of a batch in order, cutting each one when it is asked for (thread-safe: the lanes ask)
+struct PassCutter {
+    const PairsRequest &req;
+    const bool mem_cut, p16_scheme;
+    const int64_t budget, pass_res;
+    std::mutex mu;
+    int64_t lo = 0;
+    std::deque<PairChunk> chunks;   // deques: the lanes hold pointers into them while later passes are appended
+    std::deque<PassOut> pouts;
+    PassCutter(const PairsRequest &r, bool mc, bool p16, int64_t bud, int64_t pr) : req(r), mem_cut(mc), p16_scheme(p16), budget(bud), pass_res(pr) {}
+    int64_t res_upto(int64_t i) const { return (req.shared_query ? 0 : req.q_off[i] - req.q_off[0]) + (req.r_off[i] - req.r_off[0]); }
+    bool next(PairChunk *ch, PassOut **po) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (lo >= req.n) return false;
+        int64_t hi;
+        if (mem_cut) {
+            int64_t bytes = 0;
+            const int64_t res_lo = res_upto(lo);
+            hi = lo;
+            while (hi < req.n) {
+                const int64_t lq = req.shared_query ? req.q_off[1] - req.q_off[0] : req.q_off[hi + 1] - req.q_off[hi];
+                const int64_t lr = req.r_off[hi + 1] - req.r_off[hi];
+                int64_t need;
+                if (p16_scheme && lq <= 512) need = (lr + 32) * (lq + 96) * 5 / 4 + 8 * (lq + lr);   // one byte of H per cell of the padded frame
+                else if (req.cfg.trace) {
+                    const int K = 16;  // upper bound on rows per lane of any class
+                    need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);
+                } else need = 0;
+                if (hi > lo && (bytes + need > budget || res_upto(hi + 1) - res_lo > pass_res)) break;
+                bytes += need; ++hi;
+            }
+        } else if (pass_res == std::numeric_limits<int64_t>::max()) {
+            hi = req.n;
+        } else {
+            // the last pair index whose residues still fit the pass (res_upto is monotone)
+            int64_t a = lo + 1, z = req.n;
+            while (a < z) { const int64_t mid = (a + z + 1) / 2; if (res_upto(mid) - res_upto(lo) <= pass_res) a = mid; else z = mid - 1; }
+            hi = a;
+            if (req.n - hi < (hi - lo) / 4) hi = req.n;   // no runt at the end
+        }
+        chunks.push_back({lo, hi});
+        pouts.emplace_back();
+        *ch = chunks.back();
+        *po = &pouts.back();
+        lo = hi;
+        return true;
+    }
 };
 
 static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_batch_t *b, PassOut *po) {
@@ -529,22 +623,24 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     const size_t qbytes = pssm ? (size_t)m.length : (size_t)(q_hi - q_lo);
     PSB_TRY(d_q.alloc(qbytes, c.stream));
     PSB_TRY(d_r.alloc((size_t)(r_hi - r_lo), c.stream));
-    std::vector<long long> qoff_rel(req.shared_query || pssm ? 2 : n + 1), roff_rel(n + 1);
-    if (req.shared_query || pssm) { qoff_rel[0] = 0; qoff_rel[1] = (long long)qbytes; }
-    else for (int64_t i = 0; i <= n; ++i) qoff_rel[i] = req.q_off[lo + i] - q_lo;
-    for (int64_t i = 0; i <= n; ++i) roff_rel[i] = req.r_off[lo + i] - r_lo;
-    PSB_TRY(d_qoff.alloc(qoff_rel.size() * sizeof(long long), c.stream));
-    PSB_TRY(d_roff.alloc(roff_rel.size() * sizeof(long long), c.stream));
+    // the offsets go up as the caller gave them (absolute): the device pointers are biased by the range's first
+    // byte instead, so that base + off[pair] lands inside this pass's upload (no per-pair pass to make them relative)
+    static_assert(sizeof(int64_t) == sizeof(long long), "offset arrays are uploaded as they are");
+    const bool q_two = req.shared_query || pssm;
+    const long long qoff2[2] = {0, (long long)qbytes};
+    PSB_TRY(d_qoff.alloc((q_two ? 2 : (size_t)n + 1) * sizeof(long long), c.stream));
+    PSB_TRY(d_roff.alloc(((size_t)n + 1) * sizeof(long long), c.stream));
     PSB_TRY(d_matrix.alloc(m.table.size() * sizeof(int), c.stream));
     if (pssm && m.query.size() == (size_t)m.length)
         PSB_CUDA(cudaMemcpyAsync(d_q.p, m.query.data(), qbytes, cudaMemcpyHostToDevice, c.stream));
     else if (pssm)
         PSB_CUDA(cudaMemsetAsync(d_q.p, 0xff, qbytes, c.stream));  // no query residues: nothing "matches"
     else
-        PSB_CUDA(cudaMemcpyAsync(d_q.p, req.q_cat + q_lo, qbytes, cudaMemcpyHostToDevice, c.stream));
-    PSB_CUDA(cudaMemcpyAsync(d_r.p, req.r_cat + r_lo, (size_t)(r_hi - r_lo), cudaMemcpyHostToDevice, c.stream));
-    PSB_CUDA(cudaMemcpyAsync(d_qoff.p, qoff_rel.data(), qoff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
-    PSB_CUDA(cudaMemcpyAsync(d_roff.p, roff_rel.data(), roff_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+        PSB_CUDA(upload_h2d(d_q.p, req.q_cat + q_lo, qbytes, c.stream));
+    PSB_CUDA(upload_h2d(d_r.p, req.r_cat + r_lo, (size_t)(r_hi - r_lo), c.stream));
+    if (q_two) PSB_CUDA(cudaMemcpyAsync(d_qoff.p, qoff2, sizeof(qoff2), cudaMemcpyHostToDevice, c.stream));
+    else PSB_CUDA(upload_h2d(d_qoff.p, req.q_off + lo, ((size_t)n + 1) * sizeof(long long), c.stream));
+    PSB_CUDA(upload_h2d(d_roff.p, req.r_off + lo, ((size_t)n + 1) * sizeof(long long), c.stream));
     PSB_CUDA(cudaMemcpyAsync(d_matrix.p, m.table.data(), m.table.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     hphase("uploads");
     // outputs
@@ -593,8 +689,8 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     hphase("trace-offsets");
     Gotoh32Params p;
     std::memset(&p, 0, sizeof(p));
-    p.q = d_q.as<uint8_t>(); p.q_off = d_qoff.as<long long>();
-    p.r = d_r.as<uint8_t>(); p.r_off = d_roff.as<long long>();
+    p.q = d_q.as<uint8_t>() - (q_two ? 0 : q_lo); p.q_off = d_qoff.as<long long>();
+    p.r = d_r.as<uint8_t>() - r_lo; p.r_off = d_roff.as<long long>();
     p.shared_query = (req.shared_query || pssm) ? 1 : 0;
     p.matrix = d_matrix.as<int>(); p.size = m.size; p.is_pssm = pssm ? 1 : 0;
     p.open = req.open; p.gap = req.gap;
@@ -772,9 +868,10 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     }
 
     for (int id : wave_ids) {
-        const long long qb = (req.shared_query ? 0 : qoff_rel[id]), rb = roff_rel[id];
-        const int lq = (int)(req.shared_query ? qoff_rel[1] : qoff_rel[id + 1] - qoff_rel[id]);
-        const int lr = (int)(roff_rel[id + 1] - roff_rel[id]);
+        // (byte offsets relative to the biased p.q / p.r)
+        const long long qb = req.shared_query ? 0 : req.q_off[lo + id], rb = req.r_off[lo + id];
+        const int lq = (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + id + 1] - req.q_off[lo + id]);
+        const int lr = (int)(req.r_off[lo + id + 1] - req.r_off[lo + id]);
         PSB_TRY(launch_wave32(p, m, qb, lq, rb, lr, id));
     }
 
@@ -969,51 +1066,31 @@ int run_pairs(const PairsRequest &req, psb_batch_t **out) {
     if (const char *ev = std::getenv("PSB_PAIRS_PASS_MB")) pass_res = std::max<int64_t>(1, std::atoll(ev)) << 20;
     const bool mem_cut = req.cfg.trace || (req.cfg.stats && p16_scheme);
     if (mem_cut && pass_res != std::numeric_limits<int64_t>::max()) budget /= lanes;   // one pass per lane is in flight
-    std::vector<PairChunk> chunks;
+    // the passes are cut on demand (a pass's cut reads every pair's lengths when device memory bounds it: 10^7
+    // pairs are 0.1 s of that, which the lanes do for themselves, pass by pass, instead of the caller up front)
+    PassCutter cutter(req, mem_cut, p16_scheme, budget, pass_res);
     bool has_long = false;   // pairs for the whole-GPU wavefront kernel: those passes are not run side by side
-    for (int64_t lo = 0; lo < req.n;) {
-        int64_t hi;
-        if (mem_cut) {
-            int64_t bytes = 0;
-            hi = lo;
-            while (hi < req.n) {
-                const int64_t lq = req.shared_query ? req.q_off[1] - req.q_off[0] : req.q_off[hi + 1] - req.q_off[hi];
-                const int64_t lr = req.r_off[hi + 1] - req.r_off[hi];
-                int64_t need;
-                if (p16_scheme && lq <= 512) need = (lr + 32) * (lq + 96) * 5 / 4 + 8 * (lq + lr);   // one byte of H per cell of the padded frame
-                else if (req.cfg.trace) {
-                    const int K = 16;  // upper bound on rows per lane of any class
-                    need = ((lq + 32 * K - 1) / (32 * K)) * (lr + 31) * 32 * K + 8 * (lq + lr);
-                } else need = 0;
-                if (hi > lo && (bytes + need > budget || res_upto(hi + 1) - res_upto(lo) > pass_res)) break;
-                bytes += need; ++hi;
-            }
-        } else if (pass_res == std::numeric_limits<int64_t>::max()) {
-            hi = req.n;
-        } else {
-            // the last pair index whose residues still fit the pass (res_upto is monotone)
-            int64_t a = lo + 1, z = req.n;
-            while (a < z) { const int64_t mid = (a + z + 1) / 2; if (res_upto(mid) - res_upto(lo) <= pass_res) a = mid; else z = mid - 1; }
-            hi = a;
-            if (req.n - hi < (hi - lo) / 4) hi = req.n;   // no runt at the end
-        }
-        chunks.push_back({lo, hi});
-        lo = hi;
-    }
-    if (chunks.size() > 1 && hm0.type != PARASAIL_MATRIX_TYPE_PSSM && !req.cfg.stats && !req.cfg.trace) {
+    PairChunk first;
+    PassOut *first_out = nullptr;
+    cutter.next(&first, &first_out);
+    const bool single = first.hi >= req.n;
+    if (!single && lanes > 1 && hm0.type != PARASAIL_MATRIX_TYPE_PSSM && !req.cfg.stats && !req.cfg.trace) {
         if (req.shared_query) has_long = req.q_off[1] - req.q_off[0] >= kWaveMinLq;
         else for (int64_t i = 0; i < req.n && !has_long; ++i) has_long = req.q_off[i + 1] - req.q_off[i] >= kWaveMinLq;
     }
-    std::vector<PassOut> pouts(chunks.size());
     int rc = PSB_OK;
     const bool host_dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
     const auto t_run = std::chrono::steady_clock::now();
-    if (chunks.size() == 1 || lanes == 1 || has_long) {
-        for (size_t k = 0; k < chunks.size() && rc == PSB_OK; ++k) rc = run_pairs_range(req, chunks[k].lo, chunks[k].hi, b, &pouts[k]);
+    if (single || lanes == 1 || has_long) {
+        PairChunk ch = first;
+        PassOut *po = first_out;
+        do rc = run_pairs_range(req, ch.lo, ch.hi, b, po); while (rc == PSB_OK && cutter.next(&ch, &po));
         if (rc != PSB_OK) cudaStreamSynchronize(c.stream);
     } else {
-        rc = run_pairs_lanes(req, chunks, b, pouts, lanes);
+        rc = run_pairs_lanes(req, cutter, first, first_out, b, lanes);
     }
+    std::deque<PairChunk> &chunks = cutter.chunks;
+    std::deque<PassOut> &pouts = cutter.pouts;
     const auto t_join = std::chrono::steady_clock::now();
     if (rc == PSB_OK && req.cfg.trace) {
         // the passes' CIGAR words are still on the device: one pinned array for the batch, one copy per pass into it
@@ -1671,7 +1748,7 @@ static psb_db *db_upload(DbBuild &B, const uint8_t *cat, const int64_t *off, int
     // offsets first: lengths, sort and word offsets need nothing else, so that whole chain of small launches runs
     // while the residues (the long copy) are still on the link -- under a saturated link each of those launches
     // costs 30-50 us instead of 5 (measured: 0.6 ms for the chain of the first piece, tools/shard_e2e_probe.py)
-    ck(cudaMemcpyAsync(B.offs(), off, n1 * 8, cudaMemcpyHostToDevice, up));
+    ck(upload_h2d(B.offs(), off, n1 * 8, up));
     if (use_copy_stream) {
         ck(cudaEventCreateWithFlags(&B.offs_up, cudaEventDisableTiming));
         ck(cudaEventRecord(B.offs_up, up));
@@ -1682,7 +1759,7 @@ static psb_db *db_upload(DbBuild &B, const uint8_t *cat, const int64_t *off, int
         ck(cudaEventCreate(&B.res_begin));
         ck(cudaEventRecord(B.res_begin, up));
     }
-    ck(cudaMemcpyAsync(B.raw(), cat + off[0], (size_t)db->residues, cudaMemcpyHostToDevice, up));
+    ck(upload_h2d(B.raw(), cat + off[0], (size_t)db->residues, up));
     if (use_copy_stream) {
         ck(cudaEventCreate(&B.uploaded));
         ck(cudaEventRecord(B.uploaded, up));
@@ -2095,6 +2172,12 @@ static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile
     std::vector<std::unique_ptr<DbBuild>> builds(npieces);
     std::vector<std::unique_ptr<ScanJob>> jobs(npieces);
     for (int k = 0; k < npieces; ++k) { builds[k].reset(new DbBuild()); jobs[k].reset(new ScanJob()); }
+    bool pageable_src = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, cat + off[0]) != cudaSuccess) { cudaGetLastError(); pageable_src = true; }
+        else pageable_src = at.type == cudaMemoryTypeUnregistered;
+    }
     bool eager = false;   // experiment knob: 1 = every upload queued right behind the previous one, no gating
     if (const char *ev = std::getenv("PSB_SCAN_HOST_EAGER_UPLOAD")) eager = std::atoi(ev) != 0;
     auto upload = [&](int k) -> int {
@@ -2160,10 +2243,12 @@ static int scan_host_into(const FnConfig &cfg, const parasail_profile_t *profile
         if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): piece %d host: offsets pass + allocations %.3f ms, chain launches %.3f ms\n", c.device, k, h1 - h0, since() - h1);
         mark(c.stream);
         // the next piece's upload is queued as soon as its gate (this piece's chain) exists, before host time
-        // goes into this piece's scan launches
-        if (!eager) next_upload(k);
+        // goes into this piece's scan launches -- unless the caller's memory is pageable: then the upload is a
+        // memcpy loop on this thread (upload_h2d) and this piece's scan has to be on the device first
+        if (!eager && !pageable_src) next_upload(k);
         if (rc == PSB_OK) rc = scan_enqueue(*jobs[k], cfg, profile, open, gap, builds[k]->db, hosts, base + cut[k]);
         mark(c.stream);
+        if (!eager && pageable_src) next_upload(k);
         if (dbg) std::fprintf(stderr, "[psb] scan_host(dev %d): piece %d queued at %.3f ms\n", c.device, k, since());
     }
     // everything is queued: the host retires the earlier pieces while the last ones are still being scanned
@@ -2274,10 +2359,9 @@ static BoxWorker *pair_lane(int device, int lane) {
     }
     return w;
 }
-static int run_pairs_lanes(const PairsRequest &req, const std::vector<PairChunk> &chunks, psb_batch_t *b, std::vector<PassOut> &pouts, int lanes) {
+static int run_pairs_lanes(const PairsRequest &req, PassCutter &cutter, const PairChunk &first, PassOut *first_out, psb_batch_t *b, int lanes) {
     Ctx &c = g_ctx;
     const int kLanes = std::max(1, std::min(kPairLanes, lanes));
-    std::atomic<size_t> next{0};
     std::atomic<int> first_rc{PSB_OK};
     std::string errs[kPairLanes];
     std::promise<void> done[kPairLanes];
@@ -2285,10 +2369,13 @@ static int run_pairs_lanes(const PairsRequest &req, const std::vector<PairChunk>
     for (int t = 0; t < kLanes; ++t) {
         pair_lane(c.device, t)->submit([&, t] {
             int rc = ensure_ctx();
+            PairChunk ch = first;
+            PassOut *po = first_out;
+            bool have = t == 0;   // lane 0 starts with the pass the caller has already cut
             while (rc == PSB_OK && first_rc.load() == PSB_OK) {
-                const size_t k = next.fetch_add(1);
-                if (k >= chunks.size()) break;
-                rc = run_pairs_range(req, chunks[k].lo, chunks[k].hi, b, &pouts[k]);
+                if (!have && !cutter.next(&ch, &po)) break;
+                have = false;
+                rc = run_pairs_range(req, ch.lo, ch.hi, b, po);
             }
             if (rc != PSB_OK) {
                 errs[t] = psb_last_error();
@@ -2304,7 +2391,7 @@ static int run_pairs_lanes(const PairsRequest &req, const std::vector<PairChunk>
     // the passes' timed regions overlap, so their sum says nothing: the figure reported for a pipelined batch is
     // the wall time of the pipelined section (PSB_PAIRS_LANES=1 gives the serial per-pass kernel times instead)
     c.last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    for (const PassOut &po : pouts) c.launches += po.launches;
+    for (const PassOut &po : cutter.pouts) c.launches += po.launches;
     const int rc = first_rc.load();
     if (rc != PSB_OK) for (int t = 0; t < kLanes; ++t) if (!errs[t].empty()) { set_error(errs[t]); break; }
     return rc;

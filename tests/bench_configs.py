@@ -92,17 +92,21 @@ def main():
         # end to end: pinned host buffers in, pinned result arrays out, the library's own pass pipeline (two lanes)
         keep = [pinned(x) for x in (qc, qo, rc, ro)]
         pq, pqo, pr, pro = [t.numpy() for t in keep]
-        aligner.align_batch((pq, pqo), (pr, pro))  # warm-up (also grows the memory pool)
+        for _ in range(2):
+            aligner.align_batch((pq, pqo), (pr, pro))  # warm-up (also grows the memory pool)
         best = 1e30
         res = None
         for _ in range(reps):
             t0 = time.perf_counter()
             res = aligner.align_batch((pq, pqo), (pr, pro))
             best = min(best, time.perf_counter() - t0)
-        # the same call from pageable memory (plain numpy arrays), once
-        t0 = time.perf_counter()
+        # the same call from pageable memory (plain numpy arrays; the library stages them through its bounce buffers)
         aligner.align_batch((qc, qo), (rc, ro))
-        pageable = time.perf_counter() - t0
+        pageable = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            aligner.align_batch((qc, qo), (rc, ro))
+            pageable = min(pageable, time.perf_counter() - t0)
         # kernel time: the passes one after the other on one stream, summed timed regions (uploads excluded)
         os.environ["PSB_PAIRS_LANES"] = "1"
         aligner.align_batch((pq, pqo), (pr, pro))

@@ -217,6 +217,16 @@ def test_scan_host_equals_resident_scan(ps, oracle, blosum62):
     for k in KEYS3:
         assert np.array_equal(getattr(host, k), getattr(base, k)), k
     assert host.cells == base.cells
+    # the arrays above are pageable (uploads staged through the library's bounce buffers); the same from
+    # page-locked memory (plain asynchronous copies, uploads queued ahead of the scan launches), twice so that
+    # the second call runs with the piece plan from measured rates
+    import torch
+    pc = torch.empty(len(cat), dtype=torch.uint8, pin_memory=True); pc.numpy()[:] = cat
+    po = torch.empty(len(off), dtype=torch.int64, pin_memory=True); po.numpy()[:] = off
+    for _ in range(2):
+        pinned = a.scan_host((pc.numpy(), po.numpy()))
+        for k in KEYS3:
+            assert np.array_equal(getattr(pinned, k), getattr(base, k)), ("pinned", k)
     # small database, other mode, stats: single piece through the 32-bit path, against the oracle
     cat2, off2 = psb_data.protein_db(2504, 2505, 300, query=query[:120], planted_frac=0.1)
     a2 = ps.Aligner.new().semi_global().gap_open(10).gap_extend(1).profile(ps.Profile.new(query[:120], True, b62)).build()
@@ -585,3 +595,25 @@ def test_pairs_passes_on_two_lanes_equal_single_pass(ps, oracle, blosum62, mode,
         assert other.cells == one.cells
     exp = oracle_batch(oracle, qs, rs, blosum62, mode, 10, 1, stats=(kind == "stats"), cigar=(kind == "trace"))
     assert_same(two, exp, keys, f"{kind} mode {mode}")
+
+
+def test_pairs_from_pinned_and_pageable_memory(ps):
+    # psb_align_pairs takes any host memory: pageable arrays are staged through bounce buffers, page-locked ones
+    # are copied asynchronously; batches above 64 MB of residues run as passes on two lanes.  Same results.
+    import torch
+    n, lq, lr = 150000, 200, 260          # 69 MB of residues
+    rng = np.random.default_rng(77)
+    qc = rng.integers(0, 20, n * lq, dtype=np.uint8); rc = rng.integers(0, 20, n * lr, dtype=np.uint8)
+    alpha = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV", dtype=np.uint8)
+    qc, rc = alpha[qc], alpha[rc]
+    rc.reshape(n, lr)[::3, :lq] = qc.reshape(n, lq)[::3]      # a third of the pairs related
+    qo = np.arange(n + 1, dtype=np.int64) * lq; ro = np.arange(n + 1, dtype=np.int64) * lr
+    a = ps.Aligner.new().local().matrix(ps.Matrix.from_name("blosum62")).gap_open(10).gap_extend(1).use_stats().build()
+    pageable = a.align_batch((qc, qo), (rc, ro))
+    keep = []
+    for x in (qc, qo, rc, ro):
+        t = torch.empty(x.shape, dtype=torch.from_numpy(x[:0].copy()).dtype, pin_memory=True); t.numpy()[...] = x; keep.append(t)
+    pinned = a.align_batch((keep[0].numpy(), keep[1].numpy()), (keep[2].numpy(), keep[3].numpy()))
+    for k in KEYS6:
+        assert np.array_equal(getattr(pageable, k), getattr(pinned, k)), k
+    assert pageable.score[0] > 900 and pageable.matches[0] == lq      # a related pair: the query is found whole
