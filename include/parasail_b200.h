@@ -320,6 +320,11 @@ int psb_batch_topk(const psb_batch_t *batch, int k, int64_t *idx_out, int *score
 /* residue-count balanced sharding of a database across n_shards GPUs: writes
  * shard_of[i] in [0, n_shards) for each of the n sequences. */
 int psb_shard_plan(const int64_t *off, int64_t n, int n_shards, int *shard_of);
+/* Gives back what the library keeps between calls on the calling thread's device: the decision buffers its
+ * pair lanes hold from batch to batch, recycled staging and page-locked blocks, and the unused part of the
+ * device's stream-ordered memory pool.  Never needed for correctness; for a process that is done with large
+ * batches and wants the memory for something else. */
+int psb_trim(void);
 /* how psb_scan_host / psb_scan_box cut a host database of `total` residues into pipelined pieces, given the
  * upload time and the scan time per residue (ms per byte; the library measures both while it runs): writes up
  * to `cap` piece sizes (bytes) and returns their number.  Host-only; exported so the plan can be inspected. */

@@ -722,6 +722,12 @@ def shard_plan(offsets, n_shards):
     return out
 
 
+def trim():
+    """give back the memory the library keeps between calls on this thread's device (psb_trim)"""
+    if lib().psb_trim() != 0:
+        raise Error(last_error())
+
+
 def host_scan_plan(total, upload_ms_per_byte, scan_ms_per_byte):
     """piece sizes (bytes) psb_scan_host / psb_scan_box would use for `total` residues at the given rates"""
     out = np.zeros(256, dtype=np.int64)

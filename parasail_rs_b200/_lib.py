@@ -200,6 +200,8 @@ def lib():
     L.psb_batch_topk.argtypes = [C.POINTER(CBatch), C.c_int, C.c_void_p, C.c_void_p]
     L.psb_shard_plan.restype = C.c_int
     L.psb_shard_plan.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    L.psb_trim.restype = C.c_int
+    L.psb_trim.argtypes = []
     L.psb_host_scan_plan.restype = C.c_int
     L.psb_host_scan_plan.argtypes = [C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_int]
     L.psb_last_kernel_ms.restype = C.c_double

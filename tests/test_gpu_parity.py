@@ -617,3 +617,9 @@ def test_pairs_from_pinned_and_pageable_memory(ps):
     for k in KEYS6:
         assert np.array_equal(getattr(pageable, k), getattr(pinned, k)), k
     assert pageable.score[0] > 900 and pageable.matches[0] == lq      # a related pair: the query is found whole
+    # psb_trim gives the lanes' kept buffers, the recycled blocks and the idle part of the pool back; the next call
+    # simply takes them again
+    ps.trim()
+    again = a.align_batch((keep[0].numpy(), keep[1].numpy()), (keep[2].numpy(), keep[3].numpy()))
+    for k in KEYS6:
+        assert np.array_equal(getattr(again, k), getattr(pinned, k)), k
