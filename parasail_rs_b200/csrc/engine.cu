@@ -462,9 +462,8 @@ struct PairChunk {
 struct PassOut;
 // host threads that work through the passes of a large batch side by side.  Measured on 10^6 pairs (tools/
 // pairs_host_probe.py; one lane / two / three): sw_trace 250 x 250: 106 / 50 / 47 ms, nw 250 x 250: 45 / 23.7 / 21.8 ms,
-// sg_stats 150 x 500: 68 / 34 / 36 ms -- but with three or four lanes the multi-gigabyte decision buffers of the
-// trace and stats passes no longer fit what the stream-ordered pool holds mapped and single calls stall for
-// 100-500 ms while it grows; two lanes never did
+// sg_stats 150 x 500: 68 / 34 / 36 ms.  A third lane buys at most 8 % and another set of multi-gigabyte decision
+// buffers; two it is.
 static constexpr int kPairLanes = 2;
 struct PassCutter;
 static int run_pairs_lanes(const PairsRequest &req, PassCutter &cutter, const PairChunk &first, PassOut *first_out, psb_batch_t *b, int lanes);
