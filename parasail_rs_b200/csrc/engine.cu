@@ -529,6 +529,14 @@ struct PassCutter {
     }
 };
 
+// offset of pair i's CIGAR scratch (lq + lr + 2 words per pair, pair order) from the offset arrays on the device
+__global__ void rev_off_kernel(const long long *q_off, const long long *r_off, int q_shared, long long qlen, long long q_base, long long r_base,
+                               long long n, long long *out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (q_shared ? i * qlen : q_off[i] - q_base) + (r_off[i] - r_base) + 2 * i;
+}
+
 static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_batch_t *b, PassOut *po) {
     Ctx &c = g_ctx;
     const int launches_at_entry = c.launches;
@@ -656,18 +664,16 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     // trace / table blocks: [strip][step][lane][K] per pair
     DevMem d_traceoff, d_tab[4], d_revoff, d_nops, d_beg[2];
     KeptMem d_trace(0), d_rev(1);
-    std::vector<long long> trace_off, rev_off;
-    long long trace_total = 0, rev_total = 0;
-    if (want_trace || want_table) {
+    std::vector<long long> trace_off;
+    long long trace_total = 0;
+    // CIGAR scratch: pair i owns lq + lr + 2 words, in pair order, so its offset has a closed form that the device
+    // computes from the offset arrays it already holds (rev_off_kernel); only the decision blocks of pairs on the
+    // 32-bit kernels (none in a typical batch) need a host pass
+    const long long rev_total = (q_two ? (long long)n * (long long)qbytes : (long long)(q_hi - q_lo)) + (long long)(r_hi - r_lo) + 2 * (long long)n;
+    bool any32 = false;
+    for (int cl = 0; cl < kNumClass; ++cl) any32 = any32 || !cls[cl].empty();
+    if ((want_trace || want_table) && any32) {
         trace_off.assign(n, 0);
-        rev_off.resize(n);
-        for (int c16 = 0; c16 < (int)p16_ids.size(); ++c16)
-            for (int id : p16_ids[c16]) {
-                const int lq = (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + id + 1] - req.q_off[lo + id]);
-                const int lr = (int)(req.r_off[lo + id + 1] - req.r_off[lo + id]);
-                rev_off[id] = rev_total;
-                rev_total += lq + lr + 2;
-            }
         for (int cl = 0; cl < kNumClass; ++cl)
             for (int id : cls[cl]) {
                 const int K = ct.k[cl];
@@ -676,8 +682,6 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
                 const long long strips = (lq + 32 * K - 1) / (32 * K);
                 trace_off[id] = trace_total;
                 trace_total += ((strips * (lr + 31) * 32 * K + 15) / 16) * 16;
-                rev_off[id] = rev_total;
-                rev_total += lq + lr + 2;
             }
         PSB_TRY(d_traceoff.alloc((size_t)n * sizeof(long long), c.stream));
         PSB_CUDA(cudaMemcpyAsync(d_traceoff.p, trace_off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
@@ -711,7 +715,10 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     if (want_trace) {
         PSB_TRY(d_rev.alloc((size_t)rev_total * sizeof(unsigned), c.stream));
         PSB_TRY(d_revoff.alloc((size_t)n * sizeof(long long), c.stream));
-        PSB_CUDA(cudaMemcpyAsync(d_revoff.p, rev_off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+        rev_off_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)c.sms * 8), 256, 0, c.stream>>>(
+            d_qoff.as<long long>(), d_roff.as<long long>(), q_two ? 1 : 0, (long long)qbytes, (long long)q_lo, (long long)r_lo, (long long)n,
+            d_revoff.as<long long>());
+        c.launches++;
         PSB_TRY(d_nops.alloc(((size_t)n + 1) * sizeof(int), c.stream));
         PSB_CUDA(cudaMemsetAsync(d_nops.p, 0, ((size_t)n + 1) * sizeof(int), c.stream));
         PSB_TRY(d_beg[0].alloc((size_t)n * sizeof(int), c.stream));
