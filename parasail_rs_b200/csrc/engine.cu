@@ -371,7 +371,8 @@ static const void *wave32_fn(int K, bool v2) {
     }
     return nullptr;
 }
-static const void *wave32v3_fn(int K, bool is_sw) {
+static const void *wave32v3_fn(int K, bool is_sw, bool trace = false) {
+    if (trace) return K != 8 ? nullptr : (is_sw ? (const void *)wave32v3_kernel<8, 4, true, true> : (const void *)wave32v3_kernel<8, 4, false, true>);
     switch (K) {
         case 4: return is_sw ? (const void *)wave32v3_kernel<4, 4, true> : (const void *)wave32v3_kernel<4, 4, false>;
         case 8: return is_sw ? (const void *)wave32v3_kernel<8, 4, true> : (const void *)wave32v3_kernel<8, 4, false>;
@@ -384,7 +385,41 @@ static bool wave32_v2_ok(const HostMatrix &m, int open, int gap) {
     return open >= gap && gotoh32_profile_ok(m.size, m.min, m.max, open, m.type == PARASAIL_MATRIX_TYPE_PSSM);
 }
 
-static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long q_byte_off, int lq, long long r_byte_off, int lr, int out_index) {
+// Long pairs WITH traceback or statistics: the TRACE instantiation of the column-blocked generation leaves 1.25
+// bytes per cell (H low bytes + gap open/extend bits) and walk32_kernel follows the path (kern_wave32.cuh).
+struct WaveWalk {
+    bool stats;                   // count (matches, similar, length) instead of emitting CIGAR runs
+    unsigned *rev_ops;
+    const long long *rev_off;
+    int *nops, *beg_query, *beg_ref;
+};
+static constexpr int kWaveTraceK = 8;
+static size_t wave_trace_bytes(int lq, int lr) { return (size_t)wave32v3_trace_records(lq, lr, kWaveTraceK) * 40; }
+// preconditions of that path (anything else keeps the one-warp-per-pair kernels): the column-blocked generation's
+// own, H bytes that identify a neighbour's value, every strip resident at once, and the trace fits in `avail` bytes
+static bool wave_walk_ok(const HostMatrix &m, int open, int gap, bool is_sw, int lq, int lr, size_t avail) {
+    if (std::getenv("PSB_NO_WAVE_TRACE")) return false;
+    if (!wave32_v2_ok(m, open, gap) || !pairs16_trace_ok(m.min, m.max, open)) return false;
+    if ((lq + 32 * kWaveTraceK - 1) / (32 * kWaveTraceK) > g_ctx.sms * 16) return false;
+    if (!wave32v3_range_ok(kWaveTraceK, 4, is_sw, lq, lr, m.max, m.min, open, gap)) return false;
+    return wave_trace_bytes(lq, lr) + ((size_t)1 << 30) <= avail;
+}
+// what a new allocation can get: the driver's free figure + what the stream-ordered pool holds idle
+static size_t device_mem_available() {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaMemPool_t pool;
+    unsigned long long reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        free_b += (size_t)(reserved - used);
+    else cudaGetLastError();
+    return free_b;
+}
+
+static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long q_byte_off, int lq, long long r_byte_off, int lr, int out_index,
+                         const WaveWalk *ww = nullptr) {
     Ctx &c = g_ctx;
     // strips of 32*K rows: enough strips to occupy the chip, as few as possible beyond that
     int K = lq / 512 >= 2 * c.sms ? 16 : (lq / 256 >= 2 * c.sms ? 8 : 4);
@@ -411,9 +446,15 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
         if ((k == 1 || k == 2 || k == 4 || k == 8 || k == 16) && (!v3 || k >= 4)) K = k;
     }
     if (const char *ev = std::getenv("PSB_WAVE_WARPS")) { const int w = std::atoi(ev); if (w >= 1 && w <= 32) wpb = w; }
-    const void *fn = v3 ? wave32v3_fn(K, is_sw) : wave32_fn(K, v2);
+    if (ww) { v3 = true; K = kWaveTraceK; }   // (wave_walk_ok held when the pair was routed here)
+    const void *fn = v3 ? wave32v3_fn(K, is_sw, ww != nullptr) : wave32_fn(K, v2);
     const int nstrips = (lq + 32 * K - 1) / (32 * K);
-    DevMem d_bnd, d_ctl, d_cand;
+    DevMem d_bnd, d_ctl, d_cand, d_th, d_tb;
+    if (ww) {
+        const size_t nrec = (size_t)wave32v3_trace_records(lq, lr, K);
+        PSB_TRY(d_th.alloc(nrec * 32, c.stream));
+        PSB_TRY(d_tb.alloc(nrec * 8, c.stream));
+    }
     PSB_TRY(d_bnd.alloc((size_t)nstrips * 2 * (size_t)lr * sizeof(int), c.stream));
     PSB_TRY(d_ctl.alloc(((size_t)nstrips + 2) * sizeof(int), c.stream));
     PSB_TRY(d_cand.alloc((size_t)nstrips * 8 * sizeof(int), c.stream));
@@ -426,6 +467,7 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
     p.mode = g.mode; p.s1_beg = g.s1_beg; p.s1_end = g.s1_end; p.s2_beg = g.s2_beg; p.s2_end = g.s2_end;
     p.bnd = d_bnd.as<int>(); p.progress = d_ctl.as<int>() + 1; p.next_strip = d_ctl.as<int>(); p.cand = d_cand.as<int>();
     p.multi_n = 0; p.r_off = nullptr;
+    p.trace_h = d_th.as<uint4>(); p.trace_bits = d_tb.as<uint2>();
     const size_t smem = v3 ? wave32v3_smem_bytes(g.size, wpb, K) : (v2 ? wave32v2_smem_bytes(g.size, wpb) : wave32_smem_bytes(g.size, wpb));
     if (smem > 48 * 1024) PSB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -442,6 +484,33 @@ static int launch_wave32(const Gotoh32Params &g, const HostMatrix &m, long long 
     r.multi_n = 0; r.r_off = nullptr; r.out_map = nullptr; r.first_id = 0;
     wave32_reduce_kernel<<<1, 32, 0, c.stream>>>(r);
     c.launches += 2;
+    if (ww) {
+        Walk32Params w;
+        std::memset(&w, 0, sizeof(w));
+        w.q = p.q; w.r = p.r; w.Lq = lq; w.Lr = lr; w.K = K; w.trace_h = p.trace_h; w.trace_bits = p.trace_bits;
+        w.matrix = g.matrix; w.size = g.size; w.open = g.open; w.gap = g.gap; w.is_sw = is_sw ? 1 : 0;
+        w.top_free = (is_sw || (g.mode == MODE_SG && g.s1_beg)) ? 1 : 0;
+        w.left_free = (is_sw || (g.mode == MODE_SG && g.s2_beg)) ? 1 : 0;
+        w.pid = out_index; w.score = g.score; w.end_query = g.end_query; w.end_ref = g.end_ref;
+        w.rev_ops = ww->rev_ops; w.rev_off = ww->rev_off; w.nops = ww->nops; w.beg_query = ww->beg_query; w.beg_ref = ww->beg_ref;
+        w.matches = g.matches; w.similar = g.similar; w.length = g.length;
+        const size_t wsm = walk32_smem_bytes(g.size);
+        const bool dbg = std::getenv("PSB_DEBUG_TIMING") != nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c.stream); }
+        if (ww->stats) walk32_kernel<true><<<1, 32, wsm, c.stream>>>(w);
+        else walk32_kernel<false><<<1, 32, wsm, c.stream>>>(w);
+        PSB_CUDA(cudaGetLastError());
+        c.launches++;
+        if (dbg) {
+            cudaEventRecord(e1, c.stream);
+            cudaEventSynchronize(e1);
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e0, e1);
+            std::fprintf(stderr, "[psb] walk32 of a %d x %d pair: %.3f ms (trace %.2f GB)\n", lq, lr, t, (double)wave_trace_bytes(lq, lr) / 1e9);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+    }
     if (v3 && std::getenv("PSB_DEBUG_TIMING")) {
         // per-strip timeline of the column-blocked kernel: claimed / first columns available / done (us)
         std::vector<int> h((size_t)nstrips * 8);
@@ -575,7 +644,8 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
                         (!p16_walk || pairs16_trace_ok(m.min, m.max, req.open));
     std::vector<std::vector<int>> p16_ids(p16_on ? p16_num_classes() : 0);
     long long n_p16 = 0;
-    std::vector<int> wave_ids;   // long score-only pairs: spread over the whole GPU one at a time
+    std::vector<int> wave_ids;   // long pairs: spread over the whole GPU one at a time
+    size_t wave_avail = ~(size_t)0;   // device memory a traced wavefront launch may use (queried on the first long pair)
     int max_lr_multistrip = 0;
     int max_sum = 0, max_min = 0;
     bool uniform = true;
@@ -610,7 +680,14 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             }
         }
         const int cl = class_of_len(ct, lq);
-        const bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !cfg.stats && !cfg.trace && !(req.extra && (cfg.table || cfg.rowcol)) && !banded;
+        bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !(req.extra && (cfg.table || cfg.rowcol || cfg.trace)) && !banded;
+        if (wave && (cfg.stats || cfg.trace)) {
+            // with traceback / statistics: the traced wavefront launch + walk32_kernel when its preconditions hold
+            // and its 1.25 bytes per cell fit (the single-pair API's trace-table export needs the flag bytes of the
+            // one-warp kernel and stays there)
+            if (wave_avail == ~(size_t)0) wave_avail = device_mem_available();
+            wave = wave_walk_ok(m, req.open, req.gap, cfg.mode == MODE_SW, lq, lr, wave_avail);
+        }
         if (wave) { wave_ids.push_back((int)i); uniform = false; }
         else cls[cl].push_back((int)i);
         if (!wave && lq > 32 * ct.k[cl]) max_lr_multistrip = std::max(max_lr_multistrip, lr);
@@ -878,7 +955,11 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
         const long long qb = req.shared_query ? 0 : req.q_off[lo + id], rb = req.r_off[lo + id];
         const int lq = (int)(req.shared_query ? q_hi - q_lo : req.q_off[lo + id + 1] - req.q_off[lo + id]);
         const int lr = (int)(req.r_off[lo + id + 1] - req.r_off[lo + id]);
-        PSB_TRY(launch_wave32(p, m, qb, lq, rb, lr, id));
+        WaveWalk ww;
+        ww.stats = !cfg.trace;
+        ww.rev_ops = d_rev.as<unsigned>(); ww.rev_off = d_revoff.as<long long>();
+        ww.nops = d_nops.as<int>(); ww.beg_query = d_beg[0].as<int>(); ww.beg_ref = d_beg[1].as<int>();
+        PSB_TRY(launch_wave32(p, m, qb, lq, rb, lr, id, (cfg.stats || cfg.trace) ? &ww : nullptr));
     }
 
     // device-side trace walk -> CIGAR CSR

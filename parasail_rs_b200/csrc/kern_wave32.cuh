@@ -42,6 +42,10 @@ struct Wave32Params {
     // bnd / progress / cand are laid out subject-major (bnd at 2 * nstrips * r_off[s] ints).
     int multi_n;
     const long long *r_off;  // multi_n + 1 byte offsets into r
+    // TRACE instantiations of generation 3 (single pair, K = 8): per strip, step and lane one 32-byte record of
+    // the tile's H low bytes and one 8-byte record of its gap decisions (see wave32v3_kernel / walk32_kernel)
+    uint4 *trace_h;
+    uint2 *trace_bits;
 };
 
 inline size_t wave32_smem_bytes(int size, int warps) {
@@ -426,6 +430,17 @@ PSB_KERNEL void wave32v2_kernel(Wave32Params p) {
 //     (IS_SW = false): nothing reads a pad column's cells, the last row and last column are looked at
 //     per column as in generation 2.
 // `bnd` must be zero-filled before the launch; `progress` is not used by this generation.
+//
+// TRACE = true (long pairs WITH traceback or statistics, one pair per launch): every lane also leaves, per step,
+//   * the low byte of H of its K x C cells, bytes ordered [column][row] (one PRMT per 4/3 cells), and
+//   * one bit per cell and gap direction: "the horizontal gap E(i,j) was OPENED from H(i,j-1)" and "the vertical
+//     gap F(i+1,j) was OPENED from H(i,j)" (0 = extended; the sign bit of (gap - e) - (open candidate), shifted
+//     into a word: two instructions per bit), first cell of the tile in bit 31;
+// as two 16-byte and one 8-byte streaming store into records indexed [strip][step][lane], so a warp's stores of
+// one step are contiguous.  walk32_kernel follows the path from the end cell: H is recovered exactly from the
+// bytes along its way (neighbours differ by less than 128, pairs16_trace_ok), the diagonal is taken iff
+// H(i-1,j-1) + S == H(i,j), and the length of a gap comes from the open/extend bits -- the same decisions as the
+// flag bytes of gotoh32_kernel, at 1.25 bytes per cell and with a walk that is linear in the path.
 // per warp: a 64-residue ring and a profile of 32-bit (S + open) words, [letter][4-row chunk][lane][16 B]
 inline size_t wave32v3_smem_bytes(int size, int warps, int K) {
     return (((size_t)size * size * sizeof(int) + 15) & ~(size_t)15) + (size_t)warps * (64 + (size_t)(size + 1) * ((K + 3) / 4) * 512);
@@ -446,9 +461,14 @@ inline bool wave32v3_range_ok(int K, int C, bool is_sw, long long lq, long long 
 PSB_DEV bool wave32v3_valid(long long w) { const unsigned t = (unsigned)w; return (((t >> 30) ^ (t >> 31)) & 1u) != 0; }
 PSB_DEV long long wave32v3_pack(int T, int F) { return (long long)(((unsigned long long)(unsigned)F << 32) | (unsigned)(T ^ 0x40000000)); }
 
-template <int K, int C, bool IS_SW>
+template <bool B> struct WaveTag { static constexpr bool value = B; };
+inline long long wave32v3_trace_records(int lq, int lr, int K) {   // records of trace_h (x 32 B) and trace_bits (x 8 B)
+    return (long long)((lq + 32 * K - 1) / (32 * K)) * ((lr + 3) / 4 + 31) * 32;
+}
+template <int K, int C, bool IS_SW, bool TRACE = false>
 PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     static_assert(C == 4, "four residues travel in one word");
+    static_assert(!TRACE || K == 8, "a trace record is the 32 cells of an 8 x 4 tile");
     static_assert(K <= 16 && K % 4 == 0, "rows per lane come in 16-byte profile chunks of four");
     constexpr int CH = K / 4;
     constexpr int KC = K * C;
@@ -478,6 +498,8 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     // ready to use: the one-instruction chain of kern_pairs16.cuh).  Free / local top edge: H = 0, so
     // T = -o and Fh = H = 0 (F opened from the edge).
     const long long top_edge = wave32v3_pack(-o, 0);
+    const int e_tie = e + (rules::GAP_OPEN_ON_TIE ? 1 : 0);
+    (void)e_tie;
 
     for (;;) {
         int item = 0;
@@ -581,6 +603,16 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             if (b >= 0 && b < nblk) {
                 int cmax = -0x7fffffff - 1;
                 int Tdg = Tdiag_in;
+                unsigned ebits = 0, fbits = 0, hb[8];   // (TRACE only)
+                int Tc[K];                                // (ENDS only) T of reference column Lr - 1
+#pragma unroll
+                for (int k = 0; k < K; ++k) Tc[k] = 0;
+                // the K x C tile.  ENDS = true adds the global / semi-global end-cell candidates (last query row, last
+                // reference column) after each column; only the last strip and a lane's last block need them, and kept
+                // out of the common instantiation the tile is ONE basic block whose columns ptxas interleaves (the
+                // per-column tests used to cost nw / sg half their speed: 100 kb x 100 kb 38.9 ms against 20.4 local)
+                auto tile = [&](auto ends_tag) {
+                constexpr bool ENDS = decltype(ends_tag)::value;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const unsigned letter = (Lw >> (8 * c)) & 0xffu;
@@ -592,12 +624,20 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     }
                     int Td = Tdg;
                     int Fk = Fup[c];            // Fh = F + o of this lane's first row
+                    unsigned hrow[4];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int Tl = T[k];
                         const int En = viaddmax(E[k], -e, Tl);
                         const int h = viaddmax(Td, So[k], En);
                         const int H = IS_SW ? viaddmax_relu(Fk, -o, h) : viaddmax(Fk, -o, h);
+                        if (TRACE) {
+                            // sign bit set = the gap opens here (strictly better than extending it, rules::GAP_OPEN_ON_TIE)
+                            ebits = funnel_l1((unsigned)(E[k] - e_tie - Tl), ebits);
+                            fbits = funnel_l1((unsigned)(Fk - e_tie - h), fbits);
+                            hrow[k & 3] = (unsigned)H;
+                            if ((k & 3) == 3) hb[(2 * c + (k >> 2)) & 7] = prmt(prmt(hrow[0], hrow[1], 0x0040u), prmt(hrow[2], hrow[3], 0x0040u), 0x5410u);
+                        }
                         Fk = viaddmax(Fk, -e, h);        // the only loop-carried op per row
                         Td = Tl;
                         if (IS_SW) {
@@ -610,21 +650,31 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     Tout[c] = T[K - 1]; Fout[c] = Fk;
                     Tdg = Tup[c];
                     const int j = C * b + c;
-                    if (!IS_SW && j < Lr) {
-                        if (last_strip && klast >= 0 && klast < K && (row_ends || (j == Lr - 1 && !col_ends))) {
-                            // last row: sg scans it left to right (strict >); nw reads the corner only
-                            int hv = 0;
+                    if (ENDS) {
+                        // branch-free (selects), so that this instantiation stays one basic block as well: the last
+                        // strip of a semi-global pair runs it in every step and is the tail of the critical path.
+                        // Last row: sg scans it left to right (strict >), nw reads the corner only; the lane that
+                        // does not hold row Lq-1 keeps hv at -inf.
+                        int hv = NEG_INF32;
 #pragma unroll
-                            for (int k = 0; k < K; ++k) if (k == klast) hv = T[k] + o;
-                            if (hv > bestH) { bestH = hv; bestJ = j; bestI = Lq - 1; }
-                        }
-                        if (col_ends && j == Lr - 1) {
+                        for (int k = 0; k < K; ++k) hv = (k == klast) ? T[k] + o : hv;
+                        const bool upd = last_strip && j < Lr && (row_ends || (j == Lr - 1 && !col_ends)) && hv > bestH;
+                        bestH = upd ? hv : bestH; bestJ = upd ? j : bestJ; bestI = upd ? Lq - 1 : bestI;
+                        // last column: its cells are looked at after the tile
+                        const bool lastc = j == Lr - 1;
 #pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                const int hv = T[k] + o;
-                                if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
-                            }
-                        }
+                        for (int k = 0; k < K; ++k) Tc[k] = lastc ? T[k] : Tc[k];
+                    }
+                }
+                };
+                if (IS_SW) tile(WaveTag<false>{});
+                else if ((last_strip && (row_ends || (klast >= 0 && klast < K && b == nblk - 1))) || (col_ends && b == nblk - 1)) tile(WaveTag<true>{});
+                else tile(WaveTag<false>{});
+                if (!IS_SW && col_ends && b == nblk - 1) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int hv = Tc[k] + o;
+                        if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
                     }
                 }
                 Tdiag_in = Tup[C - 1];
@@ -632,6 +682,16 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         if (C * b + c < Lr) st_relaxed64(bnd_out + C * b + c, wave32v3_pack(Tout[c], Fout[c]));
+                }
+                if (TRACE) {
+                    const long long rec = ((long long)strip * nsteps + s) * 32 + lane;
+                    uint4 v0, v1;
+                    v0.x = hb[0]; v0.y = hb[1]; v0.z = hb[2]; v0.w = hb[3];
+                    v1.x = hb[4]; v1.y = hb[5]; v1.z = hb[6]; v1.w = hb[7];
+                    st_cs(p.trace_h + 2 * rec, v0);
+                    st_cs(p.trace_h + 2 * rec + 1, v1);
+                    uint2 bw; bw.x = ebits; bw.y = fbits;
+                    st_cs(p.trace_bits + rec, bw);
                 }
                 if (IS_SW) {
                     const bool upd = (cmax >> BITS) > bestH;
@@ -709,6 +769,188 @@ PSB_KERNEL void wave32_reduce_kernel(WaveReduceParams p) {
     if (p.mode == MODE_SW && bestH <= 0) { bestH = 0; bestJ = 0; bestI = 0; }
     const int o = p.multi_n > 0 ? (p.out_map ? p.out_map[p.first_id + subj] : p.first_id + subj) : 0;
     p.score[o] = bestH; p.end_query[o] = bestI; p.end_ref[o] = bestJ;
+}
+
+// ---- walk over the trace of a TRACE launch of wave32v3_kernel ----------------------------------
+// One warp follows the path of the one pair from its end cell.  walk32_kernel<false> writes the CIGAR run
+// list in reverse into the pair's scratch region (compact_cigar_kernel reverses it into the CSR);
+// walk32_kernel<true> counts (matches, similar, length) of the path -- the `_stats` result, as in walk16_kernel.
+struct Walk32Params {
+    const uint8_t *q, *r;        // mapped residues of the pair
+    int Lq, Lr;
+    int K;                       // rows per lane of the fill (8)
+    const uint4 *trace_h;
+    const uint2 *trace_bits;
+    const int *matrix;           // size x size substitution scores (no open added)
+    int size;
+    int open, gap;
+    int is_sw, top_free, left_free;
+    int pid;                     // index of the pair in the arrays below
+    const int *score, *end_query, *end_ref;
+    unsigned *rev_ops;           // CIGAR outputs
+    const long long *rev_off;
+    int *nops, *beg_query, *beg_ref;
+    int *matches, *similar, *length;   // statistics outputs
+};
+inline size_t walk32_smem_bytes(int size) { return (size_t)size * size * sizeof(int); }
+
+template <bool STATS>
+PSB_KERNEL void walk32_kernel(Walk32Params p) {
+    PSB_SHARED_DECL(smem_raw);
+    int *smat = (int *)smem_raw;
+    for (int x = thread_in_block(); x < p.size * p.size; x += threads_per_block()) smat[x] = p.matrix[x];
+    sync_block();
+    constexpr int K = 8, RPS = 32 * K;     // the fill's tile (TRACE instantiations exist for K = 8 only)
+    if (block_id() != 0 || warp_in_block() != 0 || p.K != K) return;
+    // ONE WARP walks the path.  Diagonal runs go 32 cells at a time: lane m looks at cell (i-m, j-m); if all cells
+    // before it were diagonal steps its value is v minus the substitution scores so far (a warp prefix sum), and the
+    // step from it is diagonal iff the low byte of (that value - S) is the stored byte of its predecessor (values
+    // of neighbours differ by less than 128, so equal low bytes mean equal values); the first lane that fails ends
+    // the run.  Gaps (rare) are resolved by lane 0 alone.  i, j, v and the output state are warp-uniform.
+    const int lane = lane_id();
+    const int pid = p.pid;
+    const int Lr = p.Lr;
+    const long long nsteps = (Lr + 3) / 4 + 31;
+    const int o = p.open, e = p.gap;
+    const uint8_t *hbytes = (const uint8_t *)p.trace_h;
+    unsigned *out = STATS ? nullptr : p.rev_ops + p.rev_off[pid];
+    // record and position inside the record of cell (i, j)
+    auto locate = [&](int i, int j, int &kc) -> long long {
+        const int strip = i / RPS, rem = i - strip * RPS, t = rem / K, k = rem - t * K;
+        kc = (j & 3) * K + k;
+        return ((long long)strip * nsteps + ((j >> 2) + t)) * 32 + t;
+    };
+    auto load = [&](int i, int j) -> unsigned { int kc; const long long rec = locate(i, j, kc); return hbytes[rec * 32 + kc]; };
+    // 1: the horizontal gap E(i, j) was opened from H(i, j-1)        (0: extended from E(i, j-1))
+    auto e_opened = [&](int i, int j) -> unsigned { int kc; const long long rec = locate(i, j, kc); return (p.trace_bits[rec].x >> (31 - kc)) & 1u; };
+    // 1: the vertical gap F(i+1, j) was opened from H(i, j)          (0: extended from F(i, j))
+    auto f_opened_below = [&](int i, int j) -> unsigned { int kc; const long long rec = locate(i, j, kc); return (p.trace_bits[rec].y >> (31 - kc)) & 1u; };
+    auto recon = [](unsigned byte, int ref) -> int { return ref + (int)(signed char)(unsigned char)(byte - (unsigned)ref); };
+    auto top = [&](int j) -> int { return (j < 0 || p.top_free) ? 0 : -o - j * e; };     // H[-1][j], corner 0
+    auto left = [&](int i) -> int { return (i < 0 || p.left_free) ? 0 : -o - i * e; };   // H[i][-1]
+    int i = p.end_query[pid], j = p.end_ref[pid];
+    int v = p.score[pid];            // exact H[i][j]
+    int cur = -1, n = 0;
+    unsigned len = 0;
+    int nm = 0, ns = 0, nl = 0;
+    auto emit = [&](int op, int count) {          // (uniform; lane 0 stores)
+        if (STATS || count <= 0) return;
+        if (op == cur) len += (unsigned)count;
+        else {
+            if (cur >= 0) { if (lane == 0) out[n] = (len << 4) | (unsigned)cur; ++n; }
+            cur = op; len = (unsigned)count;
+        }
+    };
+    constexpr int DG = 4;  // loads in flight per round trip along a gap
+    while (i >= 0 || j >= 0) {
+        if (i < 0 || j < 0) {
+            // off the table: statistics stop here; the CIGAR takes the rest of the other sequence as one run
+            if (i < 0) { emit((int)rules::CIGAR_OP_D, j + 1); j = -1; }
+            else { emit((int)rules::CIGAR_OP_I, i + 1); i = -1; }
+            break;
+        }
+        // ---- a run of diagonal steps, 32 candidates at a time ------------------------------------------------
+        const int ci = i - lane, cj = j - lane;
+        const bool in = ci >= 0 && cj >= 0;
+        const int a = in ? (int)p.q[ci] : 0, b = in ? (int)p.r[cj] : 0;
+        const int sub = in ? smat[a * p.size + b] : 0;
+        const bool inner = ci >= 1 && cj >= 1;
+        const unsigned hbyte = inner ? load(ci - 1, cj - 1) : 0u;
+        int pre = sub;                               // inclusive prefix sum of the substitution scores
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int up = shfl_up(pre, d); if (lane >= d) pre += up; }
+        const int vm = v - (pre - sub);              // H of cell m if every step before it was diagonal
+        const int need = vm - sub;                   // what its diagonal predecessor must hold (the diagonal wins ties)
+        bool diag_ok = false;
+        if (in) diag_ok = inner ? (((hbyte ^ (unsigned)need) & 0xffu) == 0u) : ((ci == 0 ? top(cj - 1) : left(ci - 1)) == need);
+        const bool stop = in && p.is_sw && vm <= 0;  // ZERO: the alignment starts after this cell
+        const unsigned badm = ballot(!in || stop || !diag_ok);
+        const int nd = badm ? find_first_set(badm) - 1 : 32;          // diagonal steps taken now
+        const unsigned take = nd >= 32 ? 0xffffffffu : ((1u << nd) - 1u);
+        const unsigned eqm = ballot(in && a == b) & take, posm = ballot(in && sub > 0) & take;
+        if (nd > 0) {
+            nm += pop_count(eqm); ns += pop_count(posm); nl += nd;
+            if (!STATS) {
+                int pos = 0;
+                while (pos < nd) {
+                    const unsigned bit = (eqm >> pos) & 1u;
+                    const unsigned x = (bit ? ~eqm : eqm) >> pos;        // zero bits while the run lasts
+                    int run = x ? find_first_set(x) - 1 : 32 - pos;
+                    if (run > nd - pos) run = nd - pos;
+                    emit(bit ? (int)rules::CIGAR_OP_EQ : (int)rules::CIGAR_OP_X, run);
+                    pos += run;
+                }
+            }
+            v = shfl(need, nd - 1);
+            i -= nd; j -= nd;
+        }
+        if (nd >= 32) continue;
+        const int why_out = shfl((int)!in, nd), why_stop = shfl((int)stop, nd);
+        if (why_out) continue;        // the run left the table: handled at the top of the loop
+        if (why_stop) break;
+        // ---- a gap at (i, j): lane 0 follows the open / extend bits ----------------------------------------------
+        int gk = 0, gu = 0, gop = 0;   // length, H where the gap was opened, 1 = vertical (I) / 2 = horizontal (D) / 0 = inconsistent
+        if (lane == 0) {
+            // vertical first (F wins ties over E): follow F(i, j) up to where it was opened
+            int u = v, k = 0, fval = 0;
+            bool opened = false;
+            while (!opened) {
+                unsigned bt[DG], ob[DG];
+#pragma unroll
+                for (int m = 0; m < DG; ++m) {
+                    const int row = i - k - 1 - m;
+                    bt[m] = row >= 0 ? load(row, j) : 0u;
+                    ob[m] = row >= 0 ? f_opened_below(row, j) : 1u;
+                }
+#pragma unroll
+                for (int m = 0; m < DG; ++m) {
+                    if (opened) break;
+                    ++k;
+                    const int row = i - k;
+                    u = row < 0 ? top(j) : recon(bt[m], u);
+                    if (ob[m]) { opened = true; fval = u - o - (k - 1) * e; }
+                }
+            }
+            if (fval == v) { gk = k; gu = u; gop = 1; }
+            else {
+                // horizontal: follow E(i, j) left to where it was opened
+                u = v; k = 0; opened = false;
+                int evalue = 0;
+                while (!opened) {
+                    unsigned bt[DG], ob[DG];
+#pragma unroll
+                    for (int m = 0; m < DG; ++m) {
+                        const int col = j - k - 1 - m;              // the H cell; the E cell right of it carries the bit
+                        bt[m] = col >= 0 ? load(i, col) : 0u;
+                        ob[m] = col + 1 >= 0 ? e_opened(i, col + 1) : 1u;
+                    }
+#pragma unroll
+                    for (int m = 0; m < DG; ++m) {
+                        if (opened) break;
+                        ++k;
+                        const int col = j - k;
+                        u = col < 0 ? left(i) : recon(bt[m], u);
+                        if (ob[m] || col < 0) { opened = true; evalue = u - o - (k - 1) * e; }
+                    }
+                }
+                if (evalue == v) { gk = k; gu = u; gop = 2; }
+            }
+        }
+        gk = shfl(gk, 0); gu = shfl(gu, 0); gop = shfl(gop, 0);
+        if (gop == 0) break;   // cannot happen for a table the fill produced
+        if (gop == 1) { emit((int)rules::CIGAR_OP_I, gk); i -= gk; }
+        else { emit((int)rules::CIGAR_OP_D, gk); j -= gk; }
+        nl += gk; v = gu;
+    }
+    if (lane != 0) return;
+    if (STATS) {
+        p.matches[pid] = nm; p.similar[pid] = ns; p.length[pid] = nl;
+    } else {
+        if (cur >= 0) out[n++] = (len << 4) | (unsigned)cur;
+        p.nops[pid] = n;
+        p.beg_query[pid] = i + 1;
+        p.beg_ref[pid] = j + 1;
+    }
 }
 
 }  // namespace psb

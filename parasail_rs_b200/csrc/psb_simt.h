@@ -47,6 +47,9 @@ PSB_DEV void st_cs(uint2 *p, uint2 v) { __stcs(p, v); }
 PSB_DEV void st_cg(uint4 *p, uint4 v) { __stcg(p, v); }
 PSB_DEV void st_cg(uint2 *p, uint2 v) { __stcg(p, v); }
 PSB_DEV unsigned vadd2(unsigned a, unsigned b) { return __vadd2(a, b); }
+PSB_DEV int find_first_set(unsigned v) { return __ffs((int)v); }   // 1-based position of the lowest set bit, 0 for 0
+PSB_DEV int pop_count(unsigned v) { return __popc(v); }
+PSB_DEV unsigned funnel_l1(unsigned lo, unsigned hi) { return __funnelshift_l(lo, hi, 1); }   // (hi << 1) | (lo >> 31)
 // prmt.b32 with the sign-replicate selector bit (the __byte_perm intrinsic masks it off)
 PSB_DEV unsigned prmt(unsigned a, unsigned b, unsigned sel) {
     unsigned d;
@@ -161,6 +164,9 @@ inline unsigned vimax2(unsigned a, unsigned b) {
     return pack16(std::max((int)lo16(a), (int)lo16(b)), std::max((int)hi16(a), (int)hi16(b)));
 }
 inline unsigned vadd2(unsigned a, unsigned b) { return pack16(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
+inline int find_first_set(unsigned v) { return __builtin_ffs((int)v); }
+inline int pop_count(unsigned v) { return __builtin_popcount(v); }
+inline unsigned funnel_l1(unsigned lo, unsigned hi) { return (hi << 1) | (lo >> 31); }
 inline unsigned vimax2_relu(unsigned a, unsigned b) {
     return pack16(std::max(std::max((int)lo16(a), (int)lo16(b)), 0), std::max(std::max((int)hi16(a), (int)hi16(b)), 0));
 }

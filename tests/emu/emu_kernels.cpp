@@ -89,6 +89,50 @@ extern "C" int emu_wave32(int K, const Wave32Params *pp, const WaveReduceParams 
 extern "C" int emu_sizeof_wave32() { return (int)sizeof(Wave32Params); }
 extern "C" int emu_sizeof_wavereduce() { return (int)sizeof(WaveReduceParams); }
 
+// long pair WITH traceback / statistics: TRACE instantiation of the column-blocked kernel + walk32_kernel.
+// q / r are mapped residues.  what: 1 = CIGAR walk (rev_ops: lq + lr + 2 words, reversed run list), 2 = statistics walk.
+// out: score, end_query, end_ref, then (what == 1) nops, beg_query, beg_ref or (what == 2) matches, similar, length.
+extern "C" int emu_wave32_trace(const uint8_t *q, int lq, const uint8_t *r, int lr, const int *table, int size, int open, int gap,
+                                int mode, int s1_beg, int s1_end, int s2_beg, int s2_end, int what, int nblocks, int *out, unsigned *rev_ops) {
+    constexpr int K = 8;
+    const int nstrips = (lq + 32 * K - 1) / (32 * K);
+    std::vector<long long> bnd((size_t)nstrips * lr + 8, 0);
+    std::vector<int> cand((size_t)nstrips * 8 + 8, 0);
+    int next = 0;
+    const long long nrec = wave32v3_trace_records(lq, lr, K);
+    std::vector<uint4> th((size_t)nrec * 2 + 2);
+    std::vector<uint2> tb((size_t)nrec + 2);
+    std::memset(th.data(), 0xee, th.size() * sizeof(uint4));
+    std::memset(tb.data(), 0xee, tb.size() * sizeof(uint2));
+    Wave32Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.q = q; p.r = r; p.Lq = lq; p.Lr = lr; p.matrix = table; p.size = size; p.open = open; p.gap = gap;
+    p.mode = mode; p.s1_beg = s1_beg; p.s1_end = s1_end; p.s2_beg = s2_beg; p.s2_end = s2_end;
+    p.bnd = (int *)bnd.data(); p.next_strip = &next; p.cand = cand.data();
+    p.trace_h = th.data(); p.trace_bits = tb.data();
+    const size_t smem = wave32v3_smem_bytes(size, 1, K);
+    if (mode == MODE_SW) emu::launch(nblocks, smem, [&]() { wave32v3_kernel<K, 4, true, true>(p); });
+    else emu::launch(nblocks, smem, [&]() { wave32v3_kernel<K, 4, false, true>(p); });
+    WaveReduceParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.cand = cand.data(); rp.nstrips = nstrips; rp.mode = mode; rp.s1_end = s1_end; rp.s2_end = s2_end; rp.Lr = lr;
+    rp.score = out; rp.end_query = out + 1; rp.end_ref = out + 2;
+    emu::launch(1, 64, [&]() { wave32_reduce_kernel(rp); });
+    const long long rev_off = 0;
+    Walk32Params w;
+    std::memset(&w, 0, sizeof(w));
+    w.q = q; w.r = r; w.Lq = lq; w.Lr = lr; w.K = K; w.trace_h = th.data(); w.trace_bits = tb.data();
+    w.matrix = table; w.size = size; w.open = open; w.gap = gap; w.is_sw = mode == MODE_SW;
+    w.top_free = (mode == MODE_SW || (mode == MODE_SG && s1_beg)) ? 1 : 0;
+    w.left_free = (mode == MODE_SW || (mode == MODE_SG && s2_beg)) ? 1 : 0;
+    w.pid = 0; w.score = out; w.end_query = out + 1; w.end_ref = out + 2;
+    w.rev_ops = rev_ops; w.rev_off = &rev_off; w.nops = out + 3; w.beg_query = out + 4; w.beg_ref = out + 5;
+    w.matches = out + 3; w.similar = out + 4; w.length = out + 5;
+    if (what == 2) emu::launch(1, walk32_smem_bytes(size), [&]() { walk32_kernel<true>(w); });
+    else emu::launch(1, walk32_smem_bytes(size), [&]() { walk32_kernel<false>(w); });
+    return 0;
+}
+
 // ---- packed 16-bit many-pairs kernel + walk -------------------------------------------------------------
 #include "../../parasail_rs_b200/csrc/kern_pairs16.cuh"
 

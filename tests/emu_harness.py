@@ -166,7 +166,7 @@ class Wave32Params(C.Structure):
                 ("size", C.c_int), ("open", C.c_int), ("gap", C.c_int), ("mode", C.c_int), ("s1_beg", C.c_int),
                 ("s1_end", C.c_int), ("s2_beg", C.c_int), ("s2_end", C.c_int), ("bnd", C.c_void_p),
                 ("progress", C.c_void_p), ("next_strip", C.c_void_p), ("cand", C.c_void_p), ("multi_n", C.c_int),
-                ("r_off", C.c_void_p)]
+                ("r_off", C.c_void_p), ("trace_h", C.c_void_p), ("trace_bits", C.c_void_p)]
 
 
 class WaveReduceParams(C.Structure):
@@ -192,7 +192,7 @@ def wave32(q, r, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nblocks=1, v2=Fals
     out = np.zeros(3, dtype=np.int32)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     p = Wave32Params(ptr(qm), ptr(rm), len(qm), len(rm), ptr(table), mat.size, open, gap, mode, flags[0], flags[1], flags[2],
-                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand), 0, None)
+                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand), 0, None, None, None)
     rp = WaveReduceParams(ptr(cand), nstrips, mode, flags[1], flags[3], len(rm), out.ctypes.data, out.ctypes.data + 4,
                           out.ctypes.data + 8, 0, None, None, 0)
     rc = lib().emu_wave32(K, C.byref(p), C.byref(rp), nblocks)
@@ -218,12 +218,33 @@ def wave32_multi(q, subjects, mat, K, mode, open, gap, flags=(1, 1, 1, 1), nbloc
     outs = [np.full(n, -777, dtype=np.int32) for _ in range(3)]
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     p = Wave32Params(ptr(qm), ptr(rcat), len(qm), 0, ptr(table), mat.size, open, gap, mode, flags[0], flags[1], flags[2],
-                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand), n, ptr(roff))
+                     flags[3], ptr(bnd), ptr(progress), ptr(nxt), ptr(cand), n, ptr(roff), None, None)
     rp = WaveReduceParams(ptr(cand), nstrips, mode, flags[1], flags[3], 0, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), n,
                           ptr(roff), None, 0)
     rc = lib().emu_wave32(K, C.byref(p), C.byref(rp), nblocks)
     assert rc == 0
     return outs
+
+
+def wave32_trace(q, r, mat, mode, open, gap, flags=(1, 1, 1, 1), what=1, nblocks=1):
+    """Long pair with traceback (what=1) or statistics (what=2): the TRACE instantiation of the column-blocked
+    wavefront kernel followed by walk32_kernel.  Returns a dict like the oracle's (cigar_ops in forward order)."""
+    mapper = mat.mapper.astype(np.uint8)
+    qm = np.ascontiguousarray(mapper[np.asarray(q, dtype=np.uint8)])
+    rm = np.ascontiguousarray(mapper[np.asarray(r, dtype=np.uint8)])
+    table = np.ascontiguousarray(mat.table, dtype=np.int32)
+    out = np.full(8, -777, dtype=np.int32)
+    rev = np.zeros(len(qm) + len(rm) + 4, dtype=np.uint32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emu_wave32_trace(ptr(qm), len(qm), ptr(rm), len(rm), ptr(table), mat.size, open, gap, mode, flags[0], flags[1],
+                                flags[2], flags[3], what, nblocks, ptr(out), ptr(rev))
+    assert rc == 0, rc
+    res = {"score": int(out[0]), "end_query": int(out[1]), "end_ref": int(out[2])}
+    if what == 1:
+        res.update(cigar_ops=rev[: out[3]][::-1].copy(), beg_query=int(out[4]), beg_ref=int(out[5]))
+    else:
+        res.update(matches=int(out[3]), similar=int(out[4]), length=int(out[5]))
+    return res
 
 
 def pairs16(qs, rs, mat, G, K, mode, open, gap, flags=(1, 1, 1, 1), what=0, nblocks=1):

@@ -111,3 +111,62 @@ def test_wave_gen3_sg_flags(oracle, blosum62, flags):
     exp = oracle.align(q, r, blosum62, mode=1, open=10, gap=1, s1_beg=flags[0], s1_end=flags[1], s2_beg=flags[2], s2_end=flags[3])
     got = emu_harness.wave32(q, r, blosum62, 4, 1, 10, 1, flags, v2=2)
     assert got == (exp["score"], exp["end_query"], exp["end_ref"])
+
+
+# ---- long pairs WITH traceback / statistics: TRACE instantiation of generation 3 + walk32_kernel -----------------
+def _check_trace(oracle, mat, q, r, mode, o, e, flags=(1, 1, 1, 1)):
+    exp = oracle.align(q, r, mat, mode=mode, open=o, gap=e, s1_beg=flags[0], s1_end=flags[1], s2_beg=flags[2], s2_end=flags[3], trace=True)
+    got = emu_harness.wave32_trace(q, r, mat, mode, o, e, flags, what=1)
+    tag = (len(q), len(r), mode, o, e, flags)
+    assert (got["score"], got["end_query"], got["end_ref"]) == (exp["score"], exp["end_query"], exp["end_ref"]), tag
+    assert np.array_equal(got["cigar_ops"], exp["cigar_ops"]), (tag, oracle.decode_cigar(got["cigar_ops"]), exp["cigar"])
+    assert (got["beg_query"], got["beg_ref"]) == (exp["beg_query"], exp["beg_ref"]), tag
+    exs = exp   # (the oracle's statistics recurrences run with every call)
+    gs = emu_harness.wave32_trace(q, r, mat, mode, o, e, flags, what=2)
+    assert (gs["matches"], gs["similar"], gs["length"]) == (exs["matches"], exs["similar"], exs["length"]), tag
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_wave_trace_matches_oracle(oracle, mode):
+    # several strips (256 rows each), reference lengths around the 4-column block, indels on the path,
+    # open == extend and 0/0 penalties (every decision is a tie)
+    mat = oracle.Matrix.create(b"ACGT", 2, -3)
+    for lr in (5, 33, 130, 259):
+        r = psb_data.random_seq(5401, lr, lr, protein=False)
+        base = np.concatenate([r] * (600 // lr + 2))[:640]
+        q = psb_data.mutate(base, 5402, lr, 0.10, 0.04, protein=False)[:600]
+        for o, e in ((5, 2), (3, 3), (0, 0)):
+            _check_trace(oracle, mat, q, r, mode, o, e)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_wave_trace_protein_long_gaps(oracle, blosum62, mode):
+    # protein scores; the reference lacks two stretches of the query and carries an insert, so the path has gaps
+    # that cross lane (8 rows) and strip (256 rows) boundaries
+    q = psb_data.random_seq(5403, 0, 560)
+    r = np.concatenate([q[:100], q[130:250], psb_data.random_seq(5404, 0, 37), q[250:270], q[300:]])
+    r = psb_data.mutate(r, 5405, 0, 0.08, 0.01)
+    for o, e in ((10, 1), (11, 11)):
+        _check_trace(oracle, blosum62, q, r, mode, o, e)
+
+
+@pytest.mark.parametrize("flags", SG_FLAGS[1:])
+def test_wave_trace_sg_flags(oracle, blosum62, flags):
+    q = psb_data.random_seq(5406, 0, 290)
+    r = psb_data.mutate(q, 5407, 0, 0.2, 0.04)[40:231]
+    _check_trace(oracle, blosum62, q, r, 1, 10, 1, flags)
+
+
+def test_wave_trace_ties_and_empty(oracle):
+    # repeats (equal maxima, equal-score paths) and an all-mismatch local pair (score 0, empty CIGAR)
+    dna = oracle.Matrix.create(b"ACGT", 2, -3)
+    unit = np.frombuffer(b"ACGTTGCAAC", dtype=np.uint8)
+    q = np.concatenate([unit] * 30)
+    r = np.concatenate([unit[:7]] * 20)
+    for mode in (0, 1, 2):
+        for o, e in ((5, 2), (1, 1), (0, 0), (2, 0)):
+            _check_trace(oracle, dna, q, r, mode, o, e)
+    a = np.frombuffer(b"A" * 300, dtype=np.uint8)
+    c = np.frombuffer(b"C" * 77, dtype=np.uint8)
+    for mode in (0, 1, 2):
+        _check_trace(oracle, dna, a, c, mode, 5, 2)

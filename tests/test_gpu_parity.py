@@ -319,6 +319,56 @@ def test_long_pair_wavefront(ps, oracle, mode):
     assert_same(gb, oracle_batch(oracle, qs, rs, m, mode, 5, 2), KEYS3, f"wave batch mode {mode}")
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_long_pairs_with_trace_and_stats_on_the_wavefront(ps, oracle, mode, monkeypatch):
+    # batches with traceback or statistics whose queries have >= 2048 rows: the traced launch of the column-blocked
+    # wavefront kernel (H low bytes + gap open/extend bits, 1.25 B per cell) + walk32_kernel, strips running
+    # concurrently on different SMs.  Compared with the oracle and with the one-warp-per-pair kernels
+    # (PSB_NO_WAVE_TRACE), in a batch that also holds short pairs.
+    m = oracle.Matrix.create(b"ACGT", 2, -3)
+    r = psb_data.random_seq(5601, 0, 5200, protein=False)
+    q = psb_data.mutate(r, 5601, 1, 0.10, 0.02, protein=False)[:5000]
+    # a query that lacks two stretches of the reference and carries an insert: long gaps across lanes and strips
+    q2 = np.concatenate([q[:900], q[1300:2500], psb_data.random_seq(5602, 0, 333, protein=False), q[2500:4100]])
+    qs = [q, q[:100], q2, q[:2048], q[1000:3100]]
+    rs = [r, r[:300], r[:4300], r[:67], psb_data.random_seq(5603, 0, 2500, protein=False)]
+    exp = oracle_batch(oracle, qs, rs, m, mode, 5, 2, cigar=True, stats=True)
+    dm = ps.Matrix.create(b"ACGT", 2, -3)
+    got = builder(ps, mode, dm, 5, 2).use_trace().build().align_batch(qs, rs)
+    assert_same(got, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"), f"wave trace mode {mode}")
+    gs = builder(ps, mode, dm, 5, 2).use_stats().build().align_batch(qs, rs)
+    assert_same(gs, exp, KEYS6, f"wave stats mode {mode}")
+    # single-pair API with statistics takes the same path
+    a = builder(ps, mode, dm, 5, 2).use_stats().build().align(q2, rs[2])
+    assert (a.get_score(), a.get_matches(), a.get_similar(), a.get_length()) == (exp["score"][2], exp["matches"][2], exp["similar"][2], exp["length"][2])
+    monkeypatch.setenv("PSB_NO_WAVE_TRACE", "1")
+    old = builder(ps, mode, dm, 5, 2).use_trace().build().align_batch(qs, rs)
+    assert_same(old, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"), f"one-warp trace mode {mode}")
+
+
+def test_long_pair_trace_ties_and_protein(ps, oracle, blosum62):
+    # equal-score paths (repeats, open == extend, 0/0 penalties) and protein scores on the traced wavefront path
+    b62 = ps.Matrix.from_name("blosum62")
+    q = psb_data.random_seq(5604, 0, 2300)
+    rep = np.concatenate([q[100:400]] * 8)
+    pr = psb_data.mutate(np.concatenate([q[:700], q[760:1500], q[1500:]]), 5605, 0, 0.15, 0.02)
+    for o, e in ((10, 1), (11, 11)):
+        for mode in (0, 1, 2):
+            exp = oracle_batch(oracle, [q, q], [rep, pr], blosum62, mode, o, e, cigar=True, stats=True)
+            got = builder(ps, mode, b62, o, e).use_trace().build().align_batch([q, q], [rep, pr])
+            assert_same(got, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"), f"protein {mode} {o}/{e}")
+            gs = builder(ps, mode, b62, o, e).use_stats().build().align_batch([q, q], [rep, pr])
+            assert_same(gs, exp, KEYS6, f"protein stats {mode} {o}/{e}")
+    dm, om = ps.Matrix.create(b"ACGT", 2, -3), oracle.Matrix.create(b"ACGT", 2, -3)
+    unit = np.frombuffer(b"ACGTTGCAAC", dtype=np.uint8)
+    dq, dr = np.concatenate([unit] * 230), np.concatenate([unit[:7]] * 150)
+    for o, e in ((0, 0), (2, 0), (1, 1)):
+        for mode in (0, 1, 2):
+            exp = oracle_batch(oracle, [dq], [dr], om, mode, o, e, cigar=True, stats=True)
+            got = builder(ps, mode, dm, o, e).use_trace().build().align_batch([dq], [dr])
+            assert_same(got, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"), f"ties {mode} {o}/{e}")
+
+
 @pytest.mark.parametrize("name", ["sw", "nw", "sg"])
 def test_long_pair_50kb_against_cached_oracle(ps, name):
     # 50 kb x 50 kb (2.5e9 cells, the scalar oracle needs about a minute per mode): compared with
