@@ -1024,12 +1024,11 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             return (((size_t)strip * nsteps + (j + lane)) * 32 + lane) * K + k;
         };
         if (want_trace) {
-            std::vector<uint8_t> blob((size_t)trace_total);
-            PSB_CUDA(cudaMemcpyAsync(blob.data(), d_trace.p, blob.size(), cudaMemcpyDeviceToHost, c.stream));
-            PSB_CUDA(cudaStreamSynchronize(c.stream));
-            x->trace.resize((size_t)lq * lr);
-            for (int i = 0; i < lq; ++i)
-                for (int j = 0; j < lr; ++j) x->trace[(size_t)i * lr + j] = (int8_t)blob[cell_index(i, j)];
+            // the block comes back as it is; psb_result_extra::trace_table() makes it row-major for the caller that
+            // asks (cell (i, j) sits at cell_index(i, j); the copy is synchronised with the results below)
+            x->trace_blob.resize((size_t)trace_total);
+            x->trace_K = K;
+            PSB_CUDA(cudaMemcpyAsync(x->trace_blob.data(), d_trace.p, x->trace_blob.size(), cudaMemcpyDeviceToHost, c.stream));
         }
         if (want_table) {
             std::vector<int> planes[4];

@@ -564,7 +564,112 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                 if (C + c < Lr) WB[c] = ld_relaxed64(bnd_in + C + c);
             }
         }
-        // one step of the sweep; W holds lane 0's words for block s and is reloaded with block s+2
+        // ---- the K x C tile of block b (step s) and what follows it: hand-over of the bottom row, trace records, best cell.
+        // ENDS = true adds the global / semi-global end-cell candidates (last query row, last reference column) after each
+        // column, as selects; only the last strip and a lane's last block need them.  Either way the tile is ONE basic block
+        // whose columns ptxas interleaves (per-column tests used to cost nw / sg half their speed: 100 kb x 100 kb 38.9 ms
+        // against 20.4 local).
+        auto tile = [&](auto ends_tag, const int b, const int s, const int (&Tup)[C], const int (&Fup)[C], const unsigned Lw) {
+            constexpr bool ENDS = decltype(ends_tag)::value;
+            int cmax = -0x7fffffff - 1;
+            int Tdg = Tdiag_in;
+            unsigned ebits = 0, fbits = 0, hb[8];   // (TRACE only)
+            int Tc[K];                                // (ENDS only) T of reference column Lr - 1
+#pragma unroll
+            for (int k = 0; k < K; ++k) Tc[k] = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const unsigned letter = (Lw >> (8 * c)) & 0xffu;
+                int So[K];
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                    const uint4 pv = *(const uint4 *)(wprof + (((size_t)letter * CH + ch) * 32 + lane) * 16);
+                    So[4 * ch] = (int)pv.x; So[4 * ch + 1] = (int)pv.y; So[4 * ch + 2] = (int)pv.z; So[4 * ch + 3] = (int)pv.w;
+                }
+                int Td = Tdg;
+                int Fk = Fup[c];            // Fh = F + o of this lane's first row
+                unsigned hrow[4];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int Tl = T[k];
+                    const int En = viaddmax(E[k], -e, Tl);
+                    const int h = viaddmax(Td, So[k], En);
+                    const int H = IS_SW ? viaddmax_relu(Fk, -o, h) : viaddmax(Fk, -o, h);
+                    if (TRACE) {
+                        // sign bit set = the gap opens here (strictly better than extending it, rules::GAP_OPEN_ON_TIE)
+                        ebits = funnel_l1((unsigned)(E[k] - e_tie - Tl), ebits);
+                        fbits = funnel_l1((unsigned)(Fk - e_tie - h), fbits);
+                        hrow[k & 3] = (unsigned)H;
+                        if ((k & 3) == 3) hb[(2 * c + (k >> 2)) & 7] = prmt(prmt(hrow[0], hrow[1], 0x0040u), prmt(hrow[2], hrow[3], 0x0040u), 0x5410u);
+                    }
+                    Fk = viaddmax(Fk, -e, h);        // the only loop-carried op per row
+                    Td = Tl;
+                    if (IS_SW) {
+                        // branch-free end cell: the maximum of (H, inverted tile index) prefers the smaller column, then the smaller row
+                        const int key = (H << BITS) + (KC - 1 - (c * K + k));
+                        cmax = cmax > key ? cmax : key;
+                    }
+                    T[k] = H - o; E[k] = En;
+                }
+                Tout[c] = T[K - 1]; Fout[c] = Fk;
+                Tdg = Tup[c];
+                const int j = C * b + c;
+                if (ENDS) {
+                    // last row: sg scans it left to right (strict >), nw reads the corner only; a lane that does not hold
+                    // row Lq-1 keeps hv at -inf
+                    int hv = NEG_INF32;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) hv = (k == klast) ? T[k] + o : hv;
+                    const bool upd = last_strip && j < Lr && (row_ends || (j == Lr - 1 && !col_ends)) && hv > bestH;
+                    bestH = upd ? hv : bestH; bestJ = upd ? j : bestJ; bestI = upd ? Lq - 1 : bestI;
+                    // last column: its cells are looked at after the tile
+                    const bool lastc = j == Lr - 1;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) Tc[k] = lastc ? T[k] : Tc[k];
+                }
+            }
+            if (ENDS && col_ends && b == nblk - 1) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int hv = Tc[k] + o;
+                    if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
+                }
+            }
+            Tdiag_in = Tup[C - 1];
+            if (lane == 31 && !last_strip) {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (C * b + c < Lr) st_relaxed64(bnd_out + C * b + c, wave32v3_pack(Tout[c], Fout[c]));
+            }
+            if (TRACE) {
+                const long long rec = ((long long)strip * nsteps + s) * 32 + lane;
+                uint4 v0, v1;
+                v0.x = hb[0]; v0.y = hb[1]; v0.z = hb[2]; v0.w = hb[3];
+                v1.x = hb[4]; v1.y = hb[5]; v1.z = hb[6]; v1.w = hb[7];
+                st_cs(p.trace_h + 2 * rec, v0);
+                st_cs(p.trace_h + 2 * rec + 1, v1);
+                uint2 bw; bw.x = ebits; bw.y = fbits;
+                st_cs(p.trace_bits + rec, bw);
+            }
+            if (IS_SW) {
+                const bool upd = (cmax >> BITS) > bestH;
+                bestH = upd ? (cmax >> BITS) : bestH;
+                bestKey = upd ? cmax : bestKey;
+                bestB = upd ? b : bestB;
+            }
+        };
+        // lane 0: the words of block s must have been written by the strip above; re-poll while this strip catches up
+        auto await_words = [&](const int s, long long (&W)[C]) {
+            for (;;) {
+                unsigned ok = 0x80000000u;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { const unsigned t = (unsigned)W[c]; ok &= t ^ (t << 1); }
+                if (ok & 0x80000000u) break;
+#pragma unroll
+                for (int c = 0; c < C; ++c) if (C * s + c < Lr) W[c] = ld_relaxed64(bnd_in + C * s + c);
+            }
+        };
+        // one step of the sweep, any step: W holds lane 0's words for block s and is reloaded with block s+2
         auto step = [&](const int s, long long (&W)[C]) {
             const int b = s - lane;
             int Tup[C], Fup[C];
@@ -572,17 +677,7 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             for (int c = 0; c < C; ++c) { Tup[c] = shfl_up(Tout[c], 1); Fup[c] = shfl_up(Fout[c], 1); }
             unsigned Lw = shfl_up(Lw_out, 1);
             if (lane == 0) {
-                if (strip > 0 && s < nblk) {
-                    // words the strip above has not written yet: re-poll (only while this strip catches up)
-                    for (;;) {
-                        unsigned ok = 0x80000000u;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) { const unsigned t = (unsigned)W[c]; ok &= t ^ (t << 1); }
-                        if (ok & 0x80000000u) break;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) if (C * s + c < Lr) W[c] = ld_relaxed64(bnd_in + C * s + c);
-                    }
-                }
+                if (strip > 0 && s < nblk) await_words(s, W);
 #pragma unroll
                 for (int c = 0; c < C; ++c) { Tup[c] = (int)((unsigned)W[c] ^ 0x40000000u); Fup[c] = (int)((unsigned long long)W[c] >> 32); }
                 if (!IS_SW && strip == 0 && !top_free) {
@@ -601,106 +696,40 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
             Lw_out = Lw;
             if (b >= 0 && b < nblk) {
-                int cmax = -0x7fffffff - 1;
-                int Tdg = Tdiag_in;
-                unsigned ebits = 0, fbits = 0, hb[8];   // (TRACE only)
-                int Tc[K];                                // (ENDS only) T of reference column Lr - 1
-#pragma unroll
-                for (int k = 0; k < K; ++k) Tc[k] = 0;
-                // the K x C tile.  ENDS = true adds the global / semi-global end-cell candidates (last query row, last
-                // reference column) after each column; only the last strip and a lane's last block need them, and kept
-                // out of the common instantiation the tile is ONE basic block whose columns ptxas interleaves (the
-                // per-column tests used to cost nw / sg half their speed: 100 kb x 100 kb 38.9 ms against 20.4 local)
-                auto tile = [&](auto ends_tag) {
-                constexpr bool ENDS = decltype(ends_tag)::value;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const unsigned letter = (Lw >> (8 * c)) & 0xffu;
-                    int So[K];
-#pragma unroll
-                    for (int ch = 0; ch < CH; ++ch) {
-                        const uint4 pv = *(const uint4 *)(wprof + (((size_t)letter * CH + ch) * 32 + lane) * 16);
-                        So[4 * ch] = (int)pv.x; So[4 * ch + 1] = (int)pv.y; So[4 * ch + 2] = (int)pv.z; So[4 * ch + 3] = (int)pv.w;
-                    }
-                    int Td = Tdg;
-                    int Fk = Fup[c];            // Fh = F + o of this lane's first row
-                    unsigned hrow[4];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int Tl = T[k];
-                        const int En = viaddmax(E[k], -e, Tl);
-                        const int h = viaddmax(Td, So[k], En);
-                        const int H = IS_SW ? viaddmax_relu(Fk, -o, h) : viaddmax(Fk, -o, h);
-                        if (TRACE) {
-                            // sign bit set = the gap opens here (strictly better than extending it, rules::GAP_OPEN_ON_TIE)
-                            ebits = funnel_l1((unsigned)(E[k] - e_tie - Tl), ebits);
-                            fbits = funnel_l1((unsigned)(Fk - e_tie - h), fbits);
-                            hrow[k & 3] = (unsigned)H;
-                            if ((k & 3) == 3) hb[(2 * c + (k >> 2)) & 7] = prmt(prmt(hrow[0], hrow[1], 0x0040u), prmt(hrow[2], hrow[3], 0x0040u), 0x5410u);
-                        }
-                        Fk = viaddmax(Fk, -e, h);        // the only loop-carried op per row
-                        Td = Tl;
-                        if (IS_SW) {
-                            // branch-free end cell: the maximum of (H, inverted tile index) prefers the smaller column, then the smaller row
-                            const int key = (H << BITS) + (KC - 1 - (c * K + k));
-                            cmax = cmax > key ? cmax : key;
-                        }
-                        T[k] = H - o; E[k] = En;
-                    }
-                    Tout[c] = T[K - 1]; Fout[c] = Fk;
-                    Tdg = Tup[c];
-                    const int j = C * b + c;
-                    if (ENDS) {
-                        // branch-free (selects), so that this instantiation stays one basic block as well: the last
-                        // strip of a semi-global pair runs it in every step and is the tail of the critical path.
-                        // Last row: sg scans it left to right (strict >), nw reads the corner only; the lane that
-                        // does not hold row Lq-1 keeps hv at -inf.
-                        int hv = NEG_INF32;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) hv = (k == klast) ? T[k] + o : hv;
-                        const bool upd = last_strip && j < Lr && (row_ends || (j == Lr - 1 && !col_ends)) && hv > bestH;
-                        bestH = upd ? hv : bestH; bestJ = upd ? j : bestJ; bestI = upd ? Lq - 1 : bestI;
-                        // last column: its cells are looked at after the tile
-                        const bool lastc = j == Lr - 1;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) Tc[k] = lastc ? T[k] : Tc[k];
-                    }
-                }
-                };
-                if (IS_SW) tile(WaveTag<false>{});
-                else if ((last_strip && (row_ends || (klast >= 0 && klast < K && b == nblk - 1))) || (col_ends && b == nblk - 1)) tile(WaveTag<true>{});
-                else tile(WaveTag<false>{});
-                if (!IS_SW && col_ends && b == nblk - 1) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int hv = Tc[k] + o;
-                        if (i0 + k < Lq && hv > colH) { colH = hv; colI = i0 + k; }
-                    }
-                }
-                Tdiag_in = Tup[C - 1];
-                if (lane == 31 && !last_strip) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        if (C * b + c < Lr) st_relaxed64(bnd_out + C * b + c, wave32v3_pack(Tout[c], Fout[c]));
-                }
-                if (TRACE) {
-                    const long long rec = ((long long)strip * nsteps + s) * 32 + lane;
-                    uint4 v0, v1;
-                    v0.x = hb[0]; v0.y = hb[1]; v0.z = hb[2]; v0.w = hb[3];
-                    v1.x = hb[4]; v1.y = hb[5]; v1.z = hb[6]; v1.w = hb[7];
-                    st_cs(p.trace_h + 2 * rec, v0);
-                    st_cs(p.trace_h + 2 * rec + 1, v1);
-                    uint2 bw; bw.x = ebits; bw.y = fbits;
-                    st_cs(p.trace_bits + rec, bw);
-                }
-                if (IS_SW) {
-                    const bool upd = (cmax >> BITS) > bestH;
-                    bestH = upd ? (cmax >> BITS) : bestH;
-                    bestKey = upd ? cmax : bestKey;
-                    bestB = upd ? b : bestB;
-                }
+                if (IS_SW) tile(WaveTag<false>{}, b, s, Tup, Fup, Lw);
+                else if ((last_strip && (row_ends || (klast >= 0 && klast < K && b == nblk - 1))) || (col_ends && b == nblk - 1)) tile(WaveTag<true>{}, b, s, Tup, Fup, Lw);
+                else tile(WaveTag<false>{}, b, s, Tup, Fup, Lw);
             }
         };
+        // the same step where every lane is inside the table and no lane is at its last block (31 <= s <= nblk - 4: the
+        // steady state, all but ~64 steps of a long sweep): after lane 0's validity test everything -- its unpacking of the
+        // words, the ring read, the loads for block s+2 (all lanes load the same words: one sector, no branch), the tile,
+        // the predicated stores -- is ONE basic block, so the latency of lane 0's part hides under the tile instead of
+        // preceding it
+        const long long *bnd_safe = strip > 0 ? bnd_in : bnd_out;     // (strip 0 has no line above: loads go somewhere harmless)
+        auto fstep = [&](auto ends_tag, const int s, long long (&W)[C]) {
+            const bool l0 = lane == 0;
+            if (l0 && strip > 0) await_words(s, W);
+            int Tup[C], Fup[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int tu = shfl_up(Tout[c], 1), fu = shfl_up(Fout[c], 1);
+                int t0 = (int)((unsigned)W[c] ^ 0x40000000u), f0 = (int)((unsigned long long)W[c] >> 32);
+                if (!IS_SW && strip == 0 && !top_free) { f0 = -o - (C * s + c) * e; t0 = f0 - o; }
+                Tup[c] = l0 ? t0 : tu; Fup[c] = l0 ? f0 : fu;
+            }
+            const unsigned lw_up = shfl_up(Lw_out, 1);
+            const unsigned lw0 = *(const unsigned *)(ringL + ((C * s) & 63));
+            const unsigned Lw = l0 ? lw0 : lw_up;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const long long w = ld_relaxed64(bnd_safe + C * (s + 2) + c);
+                W[c] = strip > 0 ? w : top_edge;
+            }
+            Lw_out = Lw;
+            tile(ends_tag, s - lane, s, Tup, Fup, Lw);
+        };
+        const bool ends_all = !IS_SW && last_strip && row_ends;   // sg: the last strip looks at its last row in every step
         for (int s0 = 0; s0 < nsteps; s0 += 8) {
             // ---- every 8 steps: 32 residues into the ring, the next 32 into registers ----------------
             sync_warp();
@@ -710,10 +739,22 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                 pre_l = c + 32 < Lr ? (unsigned)rseq[c + 32] : (unsigned)size;
                 sync_warp();
             }
-            PSB_UNROLL(1)
-            for (int s = s0; s < s0 + 8; s += 2) {
-                step(s, WA);
-                step(s + 1, WB);
+            // (measured on 100 kb x 100 kb: global 21.0 -> 18.4 ms, semi-global 26.3 -> 24.8 ms, but local 20.3 -> 22.1 ms:
+            // the local kernel keeps the general step)
+            if (!IS_SW && s0 >= 32 && s0 + 7 <= nblk - 4) {
+                if (ends_all) {
+                    PSB_UNROLL(1)
+                    for (int s = s0; s < s0 + 8; s += 2) { fstep(WaveTag<!IS_SW>{}, s, WA); fstep(WaveTag<!IS_SW>{}, s + 1, WB); }
+                } else {
+                    PSB_UNROLL(1)
+                    for (int s = s0; s < s0 + 8; s += 2) { fstep(WaveTag<false>{}, s, WA); fstep(WaveTag<false>{}, s + 1, WB); }
+                }
+            } else {
+                PSB_UNROLL(1)
+                for (int s = s0; s < s0 + 8; s += 2) {
+                    step(s, WA);
+                    step(s + 1, WB);
+                }
             }
         }
         sync_warp();

@@ -49,7 +49,27 @@ struct psb_result_extra {
     std::vector<int> score_table, matches_table, similar_table, length_table;
     std::vector<int> score_row, matches_row, similar_row, length_row;
     std::vector<int> score_col, matches_col, similar_col, length_col;
-    std::vector<int8_t> trace;  // row-major TraceFlags bytes (qlen x rlen)
+    std::vector<int8_t> trace;  // row-major TraceFlags bytes (qlen x rlen): built on the first parasail_result_get_trace_table
+    // the device's trace block as it came back, [strip][step][lane][K] (gotoh32_kernel): every traced single-pair
+    // call fetches it, only a caller that asks for the table pays for the row-major copy
+    std::vector<uint8_t> trace_blob;
+    int trace_K = 0;
+    std::once_flag trace_once;
+    const int8_t *trace_table() {
+        std::call_once(trace_once, [this]() {
+            if (trace_blob.empty() || trace_K <= 0) return;
+            const int K = trace_K, nsteps = rlen + 31;
+            trace.resize((size_t)qlen * rlen);
+            for (int i = 0; i < qlen; ++i) {
+                const int strip = i / (32 * K), rem = i % (32 * K), lane = rem / K, k = rem % K;
+                const uint8_t *src = trace_blob.data() + (((size_t)strip * nsteps + lane) * 32 + lane) * K + k;   // cell (i, 0)
+                int8_t *dst = trace.data() + (size_t)i * rlen;
+                for (int j = 0; j < rlen; ++j) dst[j] = (int8_t)src[(size_t)j * 32 * K];
+            }
+            std::vector<uint8_t>().swap(trace_blob);
+        });
+        return trace.empty() ? nullptr : trace.data();
+    }
     // _trace: the CIGAR the device walk produced (len<<4|op, forward order) and where it starts
     std::vector<uint32_t> cigar_ops;
     int beg_query = 0, beg_ref = 0;

@@ -107,7 +107,7 @@ PSB_ARRAY_GETTER(score_col) PSB_ARRAY_GETTER(matches_col) PSB_ARRAY_GETTER(simil
 
 // row-major int8 TraceFlags, the layout parasail-rs's TracebackTable reads [REF src/alignment/mod.rs:291-303]
 int *parasail_result_get_trace_table(const parasail_result_t *r) {
-    return (r->extra && !r->extra->trace.empty()) ? (int *)r->extra->trace.data() : nullptr;
+    return r->extra ? (int *)r->extra->trace_table() : nullptr;
 }
 
 int parasail_result_is_nw(const parasail_result_t *r) { return (r->flag & PARASAIL_FLAG_NW) != 0; }

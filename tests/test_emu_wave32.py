@@ -170,3 +170,20 @@ def test_wave_trace_ties_and_empty(oracle):
     c = np.frombuffer(b"C" * 77, dtype=np.uint8)
     for mode in (0, 1, 2):
         _check_trace(oracle, dna, a, c, mode, 5, 2)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_wave_gen3_steady_state_steps(oracle, mode):
+    # references long enough that most steps take the all-lanes-active form of the step (31 <= s <= blocks - 4), with
+    # lengths around the 4-column block, three strips (K = 8), score-only and traced launches
+    mat = oracle.Matrix.create(b"ACGT", 2, -3)
+    for lr in (689, 690, 691, 692):
+        r = psb_data.random_seq(5501, lr, lr, protein=False)
+        q = psb_data.mutate(r, 5502, lr, 0.10, 0.03, protein=False)[:600]
+        exp = oracle.align(q, r, mat, mode=mode, open=5, gap=2)
+        assert emu_harness.wave32(q, r, mat, 8, mode, 5, 2, v2=2) == (exp["score"], exp["end_query"], exp["end_ref"]), lr
+    _check_trace(oracle, mat, q, r, mode, 5, 2)
+    if mode == 1:
+        for flags in SG_FLAGS[1:]:
+            exp = oracle.align(q, r, mat, mode=1, open=5, gap=2, s1_beg=flags[0], s1_end=flags[1], s2_beg=flags[2], s2_end=flags[3])
+            assert emu_harness.wave32(q, r, mat, 8, 1, 5, 2, flags, v2=2) == (exp["score"], exp["end_query"], exp["end_ref"]), flags
