@@ -472,7 +472,6 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     static_assert(K <= 16 && K % 4 == 0, "rows per lane come in 16-byte profile chunks of four");
     constexpr int CH = K / 4;
     constexpr int KC = K * C;
-    constexpr int BITS = KC <= 16 ? 4 : (KC <= 32 ? 5 : 6);
     PSB_SHARED_DECL(smem_raw);
     const int lane = lane_id();
     const int size = p.size, o = p.open, e = p.gap;
@@ -547,7 +546,7 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
 #pragma unroll
         for (int c = 0; c < C; ++c) { Tout[c] = -o; Fout[c] = 0; }
         unsigned Lw_out = 0;
-        int bestH = IS_SW ? 0 : NEG_INF32, bestKey = 0, bestB = 0;    // local: a score must exceed 0 to count
+        int bestH = IS_SW ? 0 : NEG_INF32;    // local: a score must exceed 0 to count
         int bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
         const int klast = (Lq - 1) - i0;
         const int t_claim = wave_time_us();   // debugging aid (PSB_DEBUG_TIMING): when the strip was claimed
@@ -571,7 +570,8 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
         // against 20.4 local).
         auto tile = [&](auto ends_tag, const int b, const int s, const int (&Tup)[C], const int (&Fup)[C], const unsigned Lw) {
             constexpr bool ENDS = decltype(ends_tag)::value;
-            int cmax = -0x7fffffff - 1;
+            int cmax = 0;
+            int Hs[IS_SW ? KC : 1];                   // (local only) the tile's H values
             int Tdg = Tdiag_in;
             unsigned ebits = 0, fbits = 0, hb[8];   // (TRACE only)
             int Tc[K];                                // (ENDS only) T of reference column Lr - 1
@@ -605,9 +605,10 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     Fk = viaddmax(Fk, -e, h);        // the only loop-carried op per row
                     Td = Tl;
                     if (IS_SW) {
-                        // branch-free end cell: the maximum of (H, inverted tile index) prefers the smaller column, then the smaller row
-                        const int key = (H << BITS) + (KC - 1 - (c * K + k));
-                        cmax = cmax > key ? cmax : key;
+                        // end cell: only the tile's maximum is formed here (one VIMNMX3 per two cells); the H values stay
+                        // in their registers until the test after the tile
+                        Hs[c * K + k] = H;
+                        if (k & 1) cmax = vimax3(cmax, Hs[c * K + k - 1], H);
                     }
                     T[k] = H - o; E[k] = En;
                 }
@@ -652,10 +653,15 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                 st_cs(p.trace_bits + rec, bw);
             }
             if (IS_SW) {
-                const bool upd = (cmax >> BITS) > bestH;
-                bestH = upd ? (cmax >> BITS) : bestH;
-                bestKey = upd ? cmax : bestKey;
-                bestB = upd ? b : bestB;
+                if (cmax > bestH) {
+                    // rare (a lane's best improves in a few steps of a sweep) and after the tile, so the tile stays one
+                    // basic block: the first cell in column-major order that holds the maximum -- the smaller column,
+                    // then the smaller row, as the tie-break wants
+                    int idx = 0;
+#pragma unroll
+                    for (int x = KC - 1; x >= 0; --x) idx = Hs[x] == cmax ? x : idx;
+                    bestH = cmax; bestJ = C * b + idx / K; bestI = i0 + idx % K;
+                }
             }
         };
         // lane 0: the words of block s must have been written by the strip above; re-poll while this strip catches up
@@ -758,15 +764,7 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
         }
         sync_warp();
-        if (IS_SW) {
-            if (bestH > 0) {
-                const int idx = KC - 1 - (bestKey & ((1 << BITS) - 1));
-                bestJ = C * bestB + idx / K;
-                bestI = i0 + idx % K;
-            } else {
-                bestH = NEG_INF32;
-            }
-        }
+        if (IS_SW && !(bestH > 0)) bestH = NEG_INF32;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
             const int oH = shfl_xor(bestH, m), oJ = shfl_xor(bestJ, m), oI = shfl_xor(bestI, m);
