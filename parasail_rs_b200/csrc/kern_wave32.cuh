@@ -461,6 +461,9 @@ inline bool wave32v3_range_ok(int K, int C, bool is_sw, long long lq, long long 
 PSB_DEV bool wave32v3_valid(long long w) { const unsigned t = (unsigned)w; return (((t >> 30) ^ (t >> 31)) & 1u) != 0; }
 PSB_DEV long long wave32v3_pack(int T, int F) { return (long long)(((unsigned long long)(unsigned)F << 32) | (unsigned)(T ^ 0x40000000)); }
 
+#ifndef WAVE32_SW_KEYED
+#define WAVE32_SW_KEYED 1   // measured on 100 kb x 100 kb local (profiles/r4g): score only keyed 20.4 ms / late 21.3; traced keyed 37.2 / late 33.9
+#endif
 template <bool B> struct WaveTag { static constexpr bool value = B; };
 inline long long wave32v3_trace_records(int lq, int lr, int K) {   // records of trace_h (x 32 B) and trace_bits (x 8 B)
     return (long long)((lq + 32 * K - 1) / (32 * K)) * ((lr + 3) / 4 + 31) * 32;
@@ -472,6 +475,12 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
     static_assert(K <= 16 && K % 4 == 0, "rows per lane come in 16-byte profile chunks of four");
     constexpr int CH = K / 4;
     constexpr int KC = K * C;
+    // local end cell, two forms (WAVE32_SW_KEYED: bit 0 = score-only launches, bit 1 = traced launches use the key):
+    //   keyed: a branch-free running maximum of (H << BITS) + inverted tile index (1.5 instructions per cell);
+    //   late:  only the tile's maximum inside the tile, the cell located after it when a lane's best improves
+    //          (0.5 instructions per cell, one short branch per step, the tile's H values live to its end)
+    constexpr bool KEYED = IS_SW && (((WAVE32_SW_KEYED) >> (TRACE ? 1 : 0)) & 1) != 0;
+    constexpr int BITS = KC <= 16 ? 4 : (KC <= 32 ? 5 : 6);
     PSB_SHARED_DECL(smem_raw);
     const int lane = lane_id();
     const int size = p.size, o = p.open, e = p.gap;
@@ -547,6 +556,7 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
         for (int c = 0; c < C; ++c) { Tout[c] = -o; Fout[c] = 0; }
         unsigned Lw_out = 0;
         int bestH = IS_SW ? 0 : NEG_INF32;    // local: a score must exceed 0 to count
+        int bestKey = 0, bestB = 0;           // (keyed form)
         int bestJ = 0x7fffffff, bestI = 0x7fffffff, colH = NEG_INF32, colI = 0x7fffffff;
         const int klast = (Lq - 1) - i0;
         const int t_claim = wave_time_us();   // debugging aid (PSB_DEBUG_TIMING): when the strip was claimed
@@ -570,8 +580,8 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
         // against 20.4 local).
         auto tile = [&](auto ends_tag, const int b, const int s, const int (&Tup)[C], const int (&Fup)[C], const unsigned Lw) {
             constexpr bool ENDS = decltype(ends_tag)::value;
-            int cmax = 0;
-            int Hs[IS_SW ? KC : 1];                   // (local only) the tile's H values
+            int cmax = KEYED ? -0x7fffffff - 1 : 0;
+            int Hs[IS_SW && !KEYED ? KC : 1];         // (local, late form) the tile's H values
             int Tdg = Tdiag_in;
             unsigned ebits = 0, fbits = 0, hb[8];   // (TRACE only)
             int Tc[K];                                // (ENDS only) T of reference column Lr - 1
@@ -604,7 +614,11 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                     }
                     Fk = viaddmax(Fk, -e, h);        // the only loop-carried op per row
                     Td = Tl;
-                    if (IS_SW) {
+                    if (KEYED) {
+                        // branch-free end cell: the maximum of (H, inverted tile index) prefers the smaller column, then the smaller row
+                        const int key = (H << BITS) + (KC - 1 - (c * K + k));
+                        cmax = cmax > key ? cmax : key;
+                    } else if (IS_SW) {
                         // end cell: only the tile's maximum is formed here (one VIMNMX3 per two cells); the H values stay
                         // in their registers until the test after the tile
                         Hs[c * K + k] = H;
@@ -652,7 +666,12 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
                 uint2 bw; bw.x = ebits; bw.y = fbits;
                 st_cs(p.trace_bits + rec, bw);
             }
-            if (IS_SW) {
+            if (KEYED) {
+                const bool upd = (cmax >> BITS) > bestH;
+                bestH = upd ? (cmax >> BITS) : bestH;
+                bestKey = upd ? cmax : bestKey;
+                bestB = upd ? b : bestB;
+            } else if (IS_SW) {
                 if (cmax > bestH) {
                     // rare (a lane's best improves in a few steps of a sweep) and after the tile, so the tile stays one
                     // basic block: the first cell in column-major order that holds the maximum -- the smaller column,
@@ -764,6 +783,11 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
         }
         sync_warp();
+        if (KEYED && bestH > 0) {
+            const int idx = KC - 1 - (bestKey & ((1 << BITS) - 1));
+            bestJ = C * bestB + idx / K;
+            bestI = i0 + idx % K;
+        }
         if (IS_SW && !(bestH > 0)) bestH = NEG_INF32;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {

@@ -9,6 +9,7 @@ variants:
   prof8     scan kernel with the int8 profile joined by PRMT (SW16_PROF32=0)
   nopp      scan kernel without the ping-pong column copies (SW16_PINGPONG=0)
   shifted   scan kernel with round 1's shifted recurrence (three dependent instructions per row)
+  wavekey   wavefront kernel, local mode: keyed (branch-free) end cell in score-only and traced launches
 """
 import os
 import subprocess
@@ -22,6 +23,7 @@ VARIANTS = {
     "prof8": ["SW16_PROF32=0"],
     "nopp": ["SW16_PINGPONG=0"],
     "shifted": ["SW16_DECOUPLE=0"],
+    "wavekey": ["WAVE32_SW_KEYED=3"],
 }
 
 

@@ -44,7 +44,7 @@ def main():
         r = psb_data.random_seq(5001, 0, L, protein=False)
         q = psb_data.mutate(r, 5001, 1, 0.10, 0.01, protein=False)
         q = q[:L] if len(q) >= L else np.concatenate([q, psb_data.random_seq(5002, 0, L - len(q), protein=False)])
-        for mode in ("local", "global_", "semi_global"):
+        for mode in [m for m in ("local", "global_", "semi_global") if m in os.environ.get("PROBE_MODES", "local global_ semi_global").split()]:
             base = getattr(ps.Aligner.new(), mode)().matrix(dna).gap_open(OPEN).gap_extend(EXT)
             score_only = getattr(ps.Aligner.new(), mode)().matrix(dna).gap_open(OPEN).gap_extend(EXT).solution_width(32).build()
             tr, st = base.use_trace().build(), getattr(ps.Aligner.new(), mode)().matrix(dna).gap_open(OPEN).gap_extend(EXT).use_stats().build()
