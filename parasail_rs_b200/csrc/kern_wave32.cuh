@@ -464,6 +464,9 @@ PSB_DEV long long wave32v3_pack(int T, int F) { return (long long)(((unsigned lo
 #ifndef WAVE32_SW_KEYED
 #define WAVE32_SW_KEYED 1   // measured on 100 kb x 100 kb local (profiles/r4g): score only keyed 20.4 ms / late 21.3; traced keyed 37.2 / late 33.9
 #endif
+#ifndef WAVE32_SW_FSTEP
+#define WAVE32_SW_FSTEP 0   // 1: local launches take the all-lanes-active step too (measured slower with the keyed end cell: 22.1 ms)
+#endif
 template <bool B> struct WaveTag { static constexpr bool value = B; };
 inline long long wave32v3_trace_records(int lq, int lr, int K) {   // records of trace_h (x 32 B) and trace_bits (x 8 B)
     return (long long)((lq + 32 * K - 1) / (32 * K)) * ((lr + 3) / 4 + 31) * 32;
@@ -766,10 +769,10 @@ PSB_KERNEL void wave32v3_kernel(Wave32Params p) {
             }
             // (measured on 100 kb x 100 kb: global 21.0 -> 18.4 ms, semi-global 26.3 -> 24.8 ms, but local 20.3 -> 22.1 ms:
             // the local kernel keeps the general step)
-            if (!IS_SW && s0 >= 32 && s0 + 7 <= nblk - 4) {
+            if ((!IS_SW || WAVE32_SW_FSTEP) && s0 >= 32 && s0 + 7 <= nblk - 4) {
                 if (ends_all) {
                     PSB_UNROLL(1)
-                    for (int s = s0; s < s0 + 8; s += 2) { fstep(WaveTag<!IS_SW>{}, s, WA); fstep(WaveTag<!IS_SW>{}, s + 1, WB); }
+                    for (int s = s0; s < s0 + 8; s += 2) { fstep(WaveTag<!IS_SW>{}, s, WA); fstep(WaveTag<!IS_SW>{}, s + 1, WB); }   // (ends_all is never set for local)
                 } else {
                     PSB_UNROLL(1)
                     for (int s = s0; s < s0 + 8; s += 2) { fstep(WaveTag<false>{}, s, WA); fstep(WaveTag<false>{}, s + 1, WB); }

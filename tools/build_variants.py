@@ -9,6 +9,8 @@ variants:
   prof8     scan kernel with the int8 profile joined by PRMT (SW16_PROF32=0)
   nopp      scan kernel without the ping-pong column copies (SW16_PINGPONG=0)
   shifted   scan kernel with round 1's shifted recurrence (three dependent instructions per row)
+  wavefl    wavefront kernel, local mode: all-lanes-active step + late end cell
+  wavefk    wavefront kernel, local mode: all-lanes-active step + keyed end cell
   wavekey   wavefront kernel, local mode: keyed (branch-free) end cell in score-only and traced launches
 """
 import os
@@ -24,6 +26,8 @@ VARIANTS = {
     "nopp": ["SW16_PINGPONG=0"],
     "shifted": ["SW16_DECOUPLE=0"],
     "wavekey": ["WAVE32_SW_KEYED=3"],
+    "wavefl": ["WAVE32_SW_KEYED=0", "WAVE32_SW_FSTEP=1"],
+    "wavefk": ["WAVE32_SW_KEYED=3", "WAVE32_SW_FSTEP=1"],
 }
 
 
