@@ -680,11 +680,11 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
             }
         }
         const int cl = class_of_len(ct, lq);
-        bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !(req.extra && (cfg.table || cfg.rowcol || cfg.trace)) && !banded;
+        bool wave = lq >= kWaveMinLq && lr >= 64 && !pssm && !(req.extra && (cfg.table || cfg.rowcol || (cfg.trace && req.want_flag_bytes))) && !banded;
         if (wave && (cfg.stats || cfg.trace)) {
             // with traceback / statistics: the traced wavefront launch + walk32_kernel when its preconditions hold
             // and its 1.25 bytes per cell fit (the single-pair API's trace-table export needs the flag bytes of the
-            // one-warp kernel and stays there)
+            // one-warp kernel: align_one fetches them with a second, want_flag_bytes call when the table is asked for)
             if (wave_avail == ~(size_t)0) wave_avail = device_mem_available();
             wave = wave_walk_ok(m, req.open, req.gap, cfg.mode == MODE_SW, lq, lr, wave_avail);
         }
@@ -1017,13 +1017,13 @@ static int run_pairs_range(const PairsRequest &req, int64_t lo, int64_t hi, psb_
     // single-pair extras: row-major trace bytes, tables, last row / column
     if (req.extra && n == 1 && (want_trace || want_table)) {
         psb_result_extra *x = req.extra;
-        const int cl = first_cls, K = ct.k[cl];
+        const int cl = first_cls, K = cl >= 0 ? ct.k[cl] : 1;
         const int lq = x->qlen, lr = x->rlen, nsteps = lr + 31;
         auto cell_index = [&](int i, int j) {
             const int strip = i / (32 * K), rem = i % (32 * K), lane = rem / K, k = rem % K;
             return (((size_t)strip * nsteps + (j + lane)) * 32 + lane) * K + k;
         };
-        if (want_trace) {
+        if (want_trace && first_cls >= 0 && trace_total > 0) {   // (a pair on the wavefront kernel has no flag bytes)
             // the block comes back as it is; psb_result_extra::trace_table() makes it row-major for the caller that
             // asks (cell (i, j) sits at cell_index(i, j); the copy is synchronised with the results below)
             x->trace_blob.resize((size_t)trace_total);

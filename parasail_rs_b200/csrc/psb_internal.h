@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -54,9 +55,14 @@ struct psb_result_extra {
     // call fetches it, only a caller that asks for the table pays for the row-major copy
     std::vector<uint8_t> trace_blob;
     int trace_K = 0;
+    // a long pair's traced call runs on the whole-GPU wavefront kernel, whose records serve the walk (CIGAR,
+    // traceback strings) but are not flag bytes: the block is then fetched by this closure -- the pair once
+    // more, on the one-warp flag-byte kernel -- only when a caller asks for the table
+    std::function<void(psb_result_extra *)> trace_lazy;
     std::once_flag trace_once;
     const int8_t *trace_table() {
         std::call_once(trace_once, [this]() {
+            if (trace_blob.empty() && trace_lazy) { trace_lazy(this); trace_lazy = nullptr; }
             if (trace_blob.empty() || trace_K <= 0) return;
             const int K = trace_K, nsteps = rlen + 31;
             trace.resize((size_t)qlen * rlen);
@@ -100,6 +106,9 @@ struct PairsRequest {
     int64_t n = 0;
     // single-pair API extras (n == 1): full tables / last row+col / row-major trace bytes
     psb_result_extra *extra = nullptr;
+    // single-pair API, `_trace`: the flag-byte block itself is wanted (the lazy trace-table export), so even a long
+    // pair stays on the one-warp kernel that writes it
+    bool want_flag_bytes = false;
 };
 int run_pairs(const PairsRequest &req, psb_batch_t **out);
 void free_batch(psb_batch_t *b);

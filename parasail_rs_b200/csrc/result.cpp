@@ -66,6 +66,25 @@ parasail_result_t *align_one(const FnConfig &cfg, const HostMatrix &m, const uin
         // the trace walk ran on the device (walk_trace_kernel); keep its CIGAR with the result
         res->extra->cigar_ops.assign(b->cigar_ops + b->cigar_off[0], b->cigar_ops + b->cigar_off[1]);
         res->extra->beg_query = b->beg_query[0]; res->extra->beg_ref = b->beg_ref[0];
+        if (res->extra->trace_blob.empty()) {
+            // the pair ran on the wavefront kernel (a long pair): its flag bytes are fetched only if the caller asks for the
+            // trace table [REF src/alignment/mod.rs:291-303], by running the pair once more on the kernel that writes them
+            const std::vector<uint8_t> qv(q, q + qlen), rv(r, r + rlen);
+            const HostMatrix mc = m;
+            res->extra->trace_lazy = [cfg, mc, qv, rv, open, gap](psb_result_extra *x) {
+                psb_result_extra tmp;
+                tmp.qlen = x->qlen; tmp.rlen = x->rlen;
+                const int64_t qo[2] = {0, (int64_t)qv.size()}, ro[2] = {0, (int64_t)rv.size()};
+                PairsRequest again;
+                again.cfg = cfg; again.matrix = &mc; again.open = open; again.gap = gap;
+                again.q_cat = qv.data(); again.q_off = qo; again.r_cat = rv.data(); again.r_off = ro; again.n = 1;
+                again.extra = &tmp; again.want_flag_bytes = true;
+                psb_batch_t *b2 = nullptr;
+                if (run_pairs(again, &b2) == PSB_OK) { x->trace_blob.swap(tmp.trace_blob); x->trace_K = tmp.trace_K; }
+                else std::fprintf(stderr, "libparasail_b200: trace table of a long pair: %s\n", psb_last_error());
+                if (b2) free_batch(b2);
+            };
+        }
     }
     free_batch(b);
     if (saturates(cfg, m, res->score, qlen, rlen, open, gap)) {

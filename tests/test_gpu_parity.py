@@ -346,6 +346,24 @@ def test_long_pairs_with_trace_and_stats_on_the_wavefront(ps, oracle, mode, monk
     assert_same(old, exp, KEYS3 + ("beg_query", "beg_ref", "cigar_off", "cigar_ops"), f"one-warp trace mode {mode}")
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_single_long_pair_trace_api(ps, oracle, mode):
+    # Aligner::align of ONE long pair with use_trace(): score, CIGAR and traceback strings come from the traced wavefront
+    # launch; the TraceFlags table is fetched only when asked for (the pair once more on the flag-byte kernel) and
+    # equals the oracle's
+    m = oracle.Matrix.create(b"ACGT", 2, -3)
+    r = psb_data.random_seq(5701, 0, 2400, protein=False)
+    q = psb_data.mutate(r, 5701, 1, 0.10, 0.02, protein=False)[:2200]
+    exp = oracle.align(q, r, m, mode=mode, open=5, gap=2, trace=True)
+    a = builder(ps, mode, ps.Matrix.create(b"ACGT", 2, -3), 5, 2).use_trace().build().align(q, r)
+    assert (a.get_score(), a.get_end_query(), a.get_end_ref()) == (exp["score"], exp["end_query"], exp["end_ref"])
+    assert a.get_cigar(q, r) == exp["cigar"] and a.cigar_beg == (exp["beg_query"], exp["beg_ref"])
+    tb = a.get_traceback_strings(q, r)
+    assert (tb.query, tb.comparison, tb.reference) == exp["traceback"]
+    assert np.array_equal(a.get_trace_table(), exp["trace"])
+    assert np.array_equal(a.get_trace_table(), exp["trace"])   # the second call hands out the same table
+
+
 def test_long_pair_trace_ties_and_protein(ps, oracle, blosum62):
     # equal-score paths (repeats, open == extend, 0/0 penalties) and protein scores on the traced wavefront path
     b62 = ps.Matrix.from_name("blosum62")
