@@ -187,7 +187,10 @@ int *parasail_result_get_score_col(const parasail_result_t *result);
 int *parasail_result_get_matches_col(const parasail_result_t *result);
 int *parasail_result_get_similar_col(const parasail_result_t *result);
 int *parasail_result_get_length_col(const parasail_result_t *result);
-int *parasail_result_get_trace_table(const parasail_result_t *result); /* row-major int8 TraceFlags */
+/* row-major int8 TraceFlags [REF src/alignment/table.rs:127-142].  Built on the first call: the device's flag-byte
+ * block is made row-major then; for a long pair (query >= 2048 residues, traced on the whole-GPU wavefront kernel) the
+ * block itself is fetched then, by running the pair once more on the kernel that writes flag bytes. */
+int *parasail_result_get_trace_table(const parasail_result_t *result);
 int parasail_result_is_nw(const parasail_result_t *result);
 int parasail_result_is_sg(const parasail_result_t *result);
 int parasail_result_is_sw(const parasail_result_t *result);
